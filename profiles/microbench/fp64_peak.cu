@@ -1,0 +1,145 @@
+// Microbenchmark: FP64 issue peaks on B200 (sm_100a): DFMA vs mma.sync f64 shapes.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp64_peak fp64_peak.cu
+// Run:   ./fp64_peak     (prints TFLOP/s per variant; CUDA-event timed, 3 warm-ups)
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+constexpr int ITERS = 4096;
+
+template <int ILP>
+__global__ void k_dfma(double* out, double a, double b) {
+    double acc[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc[i] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += acc[i];
+    if (s == 12345.678) out[0] = s;
+}
+
+template <int ILP>
+__global__ void k_m8n8k4(double* out, double a, double b) {
+    double c0[ILP], c1[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { c0[i] = threadIdx.x; c1[i] = i; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += c0[i] + c1[i];
+    if (s == 12345.678) out[0] = s;
+}
+
+template <int ILP>
+__global__ void k_m16n8k4(double* out, double a, double b) {
+    double c[ILP][4];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; c[i][2] = 1; c[i][3] = 2; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i)
+            asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]), "+d"(c[i][2]), "+d"(c[i][3]) : "d"(a), "d"(b), "d"(a));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    if (s == 12345.678) out[0] = s;
+}
+
+template <int ILP>
+__global__ void k_m16n8k8(double* out, double a, double b) {
+    double c[ILP][4];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; c[i][2] = 1; c[i][3] = 2; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]), "+d"(c[i][2]), "+d"(c[i][3])
+                         : "d"(a), "d"(b), "d"(a), "d"(b), "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    if (s == 12345.678) out[0] = s;
+}
+
+template <int ILP>
+__global__ void k_m16n8k16(double* out, double a, double b) {
+    double c[ILP][4];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; c[i][2] = 1; c[i][3] = 2; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i)
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]), "+d"(c[i][2]), "+d"(c[i][3])
+                         : "d"(a), "d"(b), "d"(a), "d"(b), "d"(a), "d"(b), "d"(a), "d"(b), "d"(a), "d"(b), "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    if (s == 12345.678) out[0] = s;
+}
+
+// double-precision exp throughput (software): count exps/s
+__global__ void k_exp(double* out, double a, double) {
+    double x = a + threadIdx.x * 1e-3, s = 0;
+    for (int it = 0; it < 512; ++it) { s += exp(x); x += 1e-3; }
+    if (s == 12345.678) out[0] = s;
+}
+
+template <typename K>
+static int run(const char* name, K kern, int threads, int blocks_per_sm, double flop_per_thread_iter, int iters, double* d) {
+    int nsm = 148;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int w = 0; w < 3; ++w) kern<<<nsm * blocks_per_sm, threads>>>(d, 1.0000001, 1e-9);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(e0);
+        kern<<<nsm * blocks_per_sm, threads>>>(d, 1.0000001, 1e-9);
+        cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    double flops = flop_per_thread_iter * (double)iters * threads * blocks_per_sm * nsm;
+    printf("%-28s threads=%4d blk/SM=%d  %8.3f ms  %8.2f TFLOP/s\n", name, threads, blocks_per_sm, best, flops / best / 1e9);
+    return 0;
+}
+
+int main() {
+    double* d; CK(cudaMalloc(&d, 1024));
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    printf("device %s SMs=%d clock=%d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
+    for (int thr : {128, 256, 512, 1024}) {
+        run("dfma ilp8", k_dfma<8>, thr, 1, 2.0 * 8, ITERS, d);
+        run("dfma ilp16", k_dfma<16>, thr, 1, 2.0 * 16, ITERS, d);
+    }
+    for (int thr : {128, 256, 512, 1024}) {
+        // per warp-instruction flops: m8n8k4 = 2*8*8*4=512 -> per thread 16
+        run("mma m8n8k4 ilp4", k_m8n8k4<4>, thr, 1, 16.0 * 4, ITERS, d);
+        run("mma m8n8k4 ilp8", k_m8n8k4<8>, thr, 1, 16.0 * 8, ITERS, d);
+        run("mma m8n8k4 ilp16", k_m8n8k4<16>, thr, 1, 16.0 * 16, ITERS, d);
+        run("mma m16n8k4 ilp8", k_m16n8k4<8>, thr, 1, 32.0 * 8, ITERS, d);
+        run("mma m16n8k8 ilp8", k_m16n8k8<8>, thr, 1, 64.0 * 8, ITERS, d);
+        run("mma m16n8k16 ilp4", k_m16n8k16<4>, thr, 1, 128.0 * 4, ITERS, d);
+        run("mma m16n8k16 ilp8", k_m16n8k16<8>, thr, 1, 128.0 * 8, ITERS, d);
+    }
+    // exp: report Gexp/s (flop_per_thread_iter=1 -> "TFLOP/s" column = Texp/s)
+    run("exp f64 (T exp/s)", k_exp, 256, 4, 1.0, 512, d);
+    run("exp f64 (T exp/s)", k_exp, 1024, 2, 1.0, 512, d);
+    return 0;
+}
