@@ -1,0 +1,149 @@
+/* rmhmc_b200.h -- C ABI of the B200-native batched RMHMC / HMC hot path.
+ *
+ * The reference (emilemathieu/RiemannHamiltonianMonteCarlo) has no FFI: its boundary is the
+ * Python call convention of code/rmhmc.py:13 (RMHMC), code/hmc.py:12 (HMC) and
+ * code/tools.py:10-74 (LogNormPDF, nextpow2, ac, CalculateESS), driven from code/main.py:49-53,71.
+ * This header is what a ctypes binding of that path binds instead (INTEGRATION.md shows the stub);
+ * each entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative RMHMC_E_* code on failure; the message is
+ *     available from rmhmc_last_error(handle) (or rmhmc_last_error(NULL) for create failures);
+ *   - nothing throws, nothing frees or allocates caller-visible memory;
+ *   - all data pointers are DEVICE pointers on the handle's device (float64 unless stated),
+ *     C-contiguous, never mutated when const; work is enqueued on the handle's CUDA stream and the
+ *     call returns without synchronising unless stated;
+ *   - one handle per (device, stream); a handle is not re-entrant, different handles may be used
+ *     from different host threads;
+ *   - D (number of parameters incl. intercept) must be <= 32 in this version.
+ *
+ * Library: librmhmc_b200.so, built for sm_100a only.  There is no CPU fallback.
+ */
+#ifndef RMHMC_B200_H
+#define RMHMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rmhmc_handle rmhmc_handle;
+
+enum {
+    RMHMC_OK = 0,
+    RMHMC_E_INVALID = -1,   /* bad argument */
+    RMHMC_E_CUDA = -2,      /* CUDA runtime error (message has the detail) */
+    RMHMC_E_STATE = -3,     /* call sequence error (e.g. advance before chains_init) */
+    RMHMC_E_UNSUPPORTED = -4
+};
+
+const char* rmhmc_version(void);
+
+/* Bind a data set: XX (n_rows x dim, row-major) and t (n_rows, values 0/1), alpha = prior variance
+ * (the reference hard-codes alpha = 100: rmhmc.py:19, hmc.py:18).  The data are copied into the
+ * handle's padded device layout; the caller's buffers are not referenced afterwards. */
+int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double alpha,
+                 const double* xx_dev, const double* t_dev);
+void rmhmc_destroy(rmhmc_handle* h);
+const char* rmhmc_last_error(const rmhmc_handle* h);
+/* cudaStream_t to enqueue on (0 = legacy default stream). */
+int rmhmc_set_stream(rmhmc_handle* h, void* cuda_stream);
+
+/* ---- parity seams: the model pieces the reference inlines in rmhmc.py ----------------------- */
+
+/* For each of n_chains positions theta[c] (n_chains x dim):
+ *   G        (n_chains x dim x dim)  Fisher metric X^T diag(v) X + I/alpha     rmhmc.py:51-57
+ *   grad     (n_chains x dim)        X^T (t - sigma(X theta)) - theta/alpha    rmhmc.py:100
+ *   logjoint (n_chains)              f^T t - sum log(1+e^f) + log N(theta;0,alpha I)  rmhmc.py:31-34
+ * Any output may be NULL.  Synchronises the stream. */
+int rmhmc_metric(rmhmc_handle* h, int64_t n_chains, const double* theta, double* G, double* grad,
+                 double* logjoint);
+
+/* dG (n_chains x dim x dim x dim): dG[c][d] = X^T diag(v (1-2p) x_d) X         rmhmc.py:64-75
+ * trace (n_chains x dim): tr(G^-1 dG_d)                                       rmhmc.py:76-77
+ * Either may be NULL.  Synchronises the stream. */
+int rmhmc_metric_partials(rmhmc_handle* h, int64_t n_chains, const double* theta, double* dG,
+                          double* trace);
+
+/* Lower Cholesky factor, inverse and sum(log(diag(L))) of n_chains dense SPD matrices
+ * (np.linalg.cholesky / inv / the log-det of rmhmc.py:58-60,171).  Outputs may be NULL. */
+int rmhmc_chol_logdet(rmhmc_handle* h, int64_t n_chains, const double* G, double* L, double* Ginv,
+                      double* logdet);
+
+/* ---- the sampler engine: rmhmc.py:37-191 batched over independent chains -------------------- */
+
+/* Allocate state for n_chains chains and evaluate it at theta0 (n_chains x dim; NULL = the
+ * reference's start 1e-3, rmhmc.py:27).  Resets iteration counters. */
+int rmhmc_chains_init(rmhmc_handle* h, int64_t n_chains, const double* theta0);
+
+/* NumOfLeapFrogSteps, StepSize, NumOfNewtonSteps of rmhmc.py:13. */
+int rmhmc_configure(rmhmc_handle* h, int n_leapfrog, double step_size, int n_fixed);
+
+/* Randomness, one of:
+ *  tape   -- host-supplied draws in the reference's consumption order (rmhmc.py:80,89,90,181) for
+ *            iterations [it_base, it_base + n_window): z (n_window x n_chains x dim),
+ *            u_step, z_dir, u_acc (n_window x n_chains).  u_acc is consumed only if Ratio <= 0.
+ *  philox -- counter-based Philox4x32-10 keyed by (seed, chain_offset + chain, iteration). */
+int rmhmc_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const double* z,
+                   const double* u_step, const double* z_dir, const double* u_acc);
+int rmhmc_set_philox(rmhmc_handle* h, uint64_t seed, int64_t chain_offset);
+
+/* Sample store (rmhmc.py:190-191): samples (n_chains x capacity x dim); the state after
+ * iteration `it` goes to row it - burn_in for it > burn_in (row 0 is never written, as in the
+ * reference).  NULL disables storing. */
+int rmhmc_set_samples(rmhmc_handle* h, double* samples, int64_t capacity, int64_t burn_in);
+
+/* Optional per-step trace of the first n_iters iterations (parity tests).  Shapes:
+ * theta_steps (n_chains x n_iters x n_leapfrog x dim): position after each leapfrog step;
+ * mom_end, theta_end, mom0 (n_chains x n_iters x dim); h_current, h_proposed (n_chains x n_iters);
+ * flags int32 (n_chains x n_iters): bit0 accepted, bit1 uniform consumed, bit4 direction > 0,
+ * bits 8.. RandomStep.  All-or-nothing: pass NULL for theta_steps to disable. */
+int rmhmc_set_trace(rmhmc_handle* h, int64_t n_iters, double* theta_steps, double* mom_end,
+                    double* theta_end, double* mom0, double* h_current, double* h_proposed,
+                    int32_t* flags);
+
+/* Enqueue n_rounds rounds.  One round = one generalized leapfrog step (rmhmc.py:96-163) for every
+ * chain that has completed fewer than it_stop iterations, plus that chain's accept/reject and next
+ * momentum draw when its trajectory ends.  Does not synchronise. */
+int rmhmc_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop);
+
+/* Run rounds until every chain has completed it_stop iterations; synchronises.  rounds_done (host
+ * pointer, may be NULL) receives the number of rounds executed. */
+int rmhmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
+
+/* Copy out per-chain state (device pointers, any may be NULL): theta (n_chains x dim) current
+ * position, iters / accepted / leapfrogs int64 (n_chains), renorm_mom / renorm_pos int32. */
+int rmhmc_read_state(rmhmc_handle* h, double* theta, int64_t* iters, int64_t* accepted,
+                     int64_t* leapfrogs, int32_t* renorm_mom, int32_t* renorm_pos);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t rmhmc_launch_count(const rmhmc_handle* h);
+
+/* CUDA-event timing of the engine's kernels: when enabled, every launch of a given kernel class is
+ * bracketed by events on the handle's stream.  kind: 0 metric build (position iterates),
+ * 1 metric build (closing), 2 partials build, 3 per-chain stages.  Returns accumulated
+ * milliseconds and launch count since the last reset; synchronises. */
+int rmhmc_profile_enable(rmhmc_handle* h, int enable);
+int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches);
+
+/* ---- Euclidean HMC: hmc.py:38-89 batched over chains ---------------------------------------- */
+int hmc_chains_init(rmhmc_handle* h, int64_t n_chains, const double* theta0);  /* NULL = zeros, hmc.py:27 */
+int hmc_configure(rmhmc_handle* h, int n_leapfrog, double step_size);
+/* tape without z_dir (hmc.py:41,48,78), or rmhmc_set_philox; samples via rmhmc_set_samples. */
+int hmc_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const double* z,
+                 const double* u_step, const double* u_acc);
+int hmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
+
+/* ---- tools.py:32-74 batched ------------------------------------------------------------------ */
+/* ESS of every (chain, parameter) series: samples (n_chains x n_samples x dim) with the given
+ * strides in doubles; ess (n_chains x dim).  Exactly tools.CalculateESS(series, max_lag) incl. the
+ * nFFT = nextpow2(n)+1 circular aliasing.  n_samples <= 24000.  Does not need a handle. */
+int blr_ess_batched(int device, void* cuda_stream, const double* samples, int64_t n_chains,
+                    int64_t n_samples, int dim, int64_t chain_stride, int64_t row_stride,
+                    int64_t max_lag, double* ess);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMHMC_B200_H */

@@ -1,0 +1,15 @@
+"""B200-native batched Riemann-manifold HMC for Bayesian logistic regression.
+
+Drop-in entry points with the reference's names (code/rmhmc.py, code/hmc.py, code/tools.py):
+``RMHMC``, ``HMC``, ``LogNormPDF``, ``nextpow2``, ``ac``, ``CalculateESS``; batched engines
+``RMHMCSampler`` / ``HMCSampler`` / ``rmhmc_batched`` / ``hmc_batched`` on top of the C ABI in
+``include/rmhmc_b200.h`` (``librmhmc_b200.so``, sm_100a only, no CPU fallback).
+"""
+from . import datasets  # noqa: F401
+from .engine import HMCSampler, LogisticData, RMHMCSampler, ess_batched  # noqa: F401
+from .hmc import HMC, hmc_batched  # noqa: F401
+from .rmhmc import RMHMC, rmhmc_batched  # noqa: F401
+from .tools import CalculateESS, LogNormPDF, ac, nextpow2  # noqa: F401
+
+__all__ = ["RMHMC", "HMC", "LogNormPDF", "nextpow2", "ac", "CalculateESS", "RMHMCSampler", "HMCSampler",
+           "LogisticData", "rmhmc_batched", "hmc_batched", "ess_batched", "datasets"]

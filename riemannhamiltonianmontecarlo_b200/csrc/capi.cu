@@ -1,0 +1,804 @@
+// C ABI of librmhmc_b200.so (include/rmhmc_b200.h): handle, device layouts, round scheduling.
+// Host side only orchestrates; all arithmetic is in the kernels of this directory.
+#include "../../include/rmhmc_b200.h"
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "chain_kernels.cuh"
+#include "common.cuh"
+#include "ess_kernel.cuh"
+#include "hmc_kernels.cuh"
+#include "metric_kernel.cuh"
+#include "tbuild_kernel.cuh"
+
+using namespace rmhmc;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct ProfSlot {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    double ms = 0.0;
+    int64_t launches = 0;
+};
+}  // namespace
+
+struct rmhmc_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t n_rows = 0;
+    int dim = 0, xs = 0, n_rows_pad = 0, p2 = 0, p2p = 0, p3 = 0, p3p = 0, nt = 0;
+    double alpha = 100.0;
+    // data set
+    double* x_pad = nullptr;
+    uchar2* pair_tab = nullptr;
+    uchar4* tri_tab = nullptr;
+    unsigned short* qidx = nullptr;
+    unsigned char *pair_a = nullptr, *pair_b = nullptr;
+    // chains
+    int64_t n_chains = 0, c_pad = 0;
+    bool is_hmc = false;
+    std::vector<void*> chain_allocs;
+    ChainArrays S{};
+    EngineParams P{};
+    long long* d_remaining = nullptr;
+    bool configured = false, rng_set = false;
+    int64_t launches = 0;
+    bool profiling = false;
+    ProfSlot prof[4];
+    mutable std::string err;
+};
+
+namespace {
+
+#define CUDA_TRY(h, expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
+            return RMHMC_E_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+int fail(rmhmc_handle* h, int code, const std::string& msg) {
+    h->err = msg;
+    return code;
+}
+
+// ------------------------------------------------------------------ small layout kernels
+__global__ void k_pad_design(const double* __restrict__ xx, const double* __restrict__ t, double* __restrict__ xp,
+                             int64_t n_rows, int dim, int xs, int64_t n_rows_pad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_rows_pad * xs) return;
+    int64_t r = i / xs;
+    int col = (int)(i - r * xs);
+    double v = 0.0;
+    if (r < n_rows) {
+        if (col < dim) v = xx[r * dim + col];
+        else if (col == xs - 1) v = t[r];
+    }
+    xp[i] = v;
+}
+
+__global__ void k_fill(double* p, int64_t n, double v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// packed G -> dense symmetric
+__global__ void k_unpack_g(const double* __restrict__ gp, double* __restrict__ G, int64_t C, int D, int p2p) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= C * D * D) return;
+    int64_t c = i / (D * D);
+    int r = (int)(i - c * D * D);
+    int a = r / D, b = r - a * D;
+    int lo = a < b ? a : b, hi = a < b ? b : a;
+    G[i] = gp[c * p2p + pair_index(lo, hi, D)];
+}
+// dense symmetric -> packed
+__global__ void k_pack_g(const double* __restrict__ G, double* __restrict__ gp, int64_t C, int D, int p2, int p2p,
+                         const unsigned char* __restrict__ pa, const unsigned char* __restrict__ pb) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= C * p2p) return;
+    int64_t c = i / p2p;
+    int pr = (int)(i - c * p2p);
+    gp[i] = pr < p2 ? G[c * D * D + pa[pr] * D + pb[pr]] : 0.0;
+}
+// packed T -> dense dG[c][d][a][b]
+__global__ void k_unpack_t(const double* __restrict__ tp, double* __restrict__ dG, int64_t C, int D, int p3p) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t d3 = (int64_t)D * D * D;
+    if (i >= C * d3) return;
+    int64_t c = i / d3;
+    int r = (int)(i - c * d3);
+    int d = r / (D * D), a = (r / D) % D, b = r % D;
+    dG[i] = tp[c * p3p + triple_index_any(d, a, b, D)];
+}
+// full gradient and log joint from the closing build's raw outputs
+__global__ void k_seam_finish(const double* __restrict__ theta, const double* __restrict__ grad_raw,
+                              const double* __restrict__ loglik, double* grad, double* logjoint, int64_t C, int D,
+                              double alpha) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double lp = 0.0;
+    for (int d = 0; d < D; ++d) {
+        double th = theta[c * D + d];
+        if (grad) grad[c * D + d] = grad_raw[c * D + d] - th / alpha;
+        lp += -0.5 * log(2.0 * 3.14159265358979323846 * alpha) - th * th / (2.0 * alpha);
+    }
+    if (logjoint) logjoint[c] = loglik[c] + lp;
+}
+// per chain: factor packed G; optional L, inverse, logdet, trace(G^-1 dG_d) from packed T
+__global__ void __launch_bounds__(32) k_seam_factor(EngineParams P, const double* __restrict__ gp,
+                                                    const double* __restrict__ tp, double* L, double* Ginv,
+                                                    double* logdet, double* trace) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int c = blockIdx.x, lane = threadIdx.x, D = P.dim, DS = P.ds;
+    ChainSmem sm = carve_chain_smem(smem_raw, P, tp != nullptr);
+    unpack_sym(gp + (size_t)c * P.p2p, sm.A, D, DS, lane);
+    double ld = chol_warp(sm.A, D, DS, lane);
+    if (logdet && lane == 0) logdet[c] = ld;
+    if (L)
+        for (int idx = lane; idx < D * D; idx += 32) {
+            int i = idx / D, j = idx % D;
+            L[(size_t)c * D * D + idx] = j <= i ? sm.A[i * DS + j] : 0.0;
+        }
+    if (Ginv || trace) {
+        chol_inverse_warp(sm.A, sm.B, D, DS, lane);
+        if (Ginv)
+            for (int idx = lane; idx < D * D; idx += 32) Ginv[(size_t)c * D * D + idx] = sm.B[(idx / D) * DS + (idx % D)];
+    }
+    if (trace) {
+        load_t_smem(sm.T, tp + (size_t)c * P.p3p, P.p3p, lane);
+        for (int pr = lane; pr < P.p2; pr += 32) {
+            int pa = P.pair_a[pr], pb = P.pair_b[pr];
+            double w = sm.B[pa * DS + pb];
+            sm.Q[pr] = pa == pb ? w : 2.0 * w;
+        }
+        __syncwarp();
+        double tr = tensor_contract(sm.T, sm.Q, P.qidx, P.p2, lane);
+        if (lane < D) trace[(size_t)c * D + lane] = tr;
+    }
+}
+
+__global__ void k_remaining(const long long* __restrict__ iter, int64_t C, long long it_stop, long long* out) {
+    long long m = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < C; i += (int64_t)gridDim.x * blockDim.x) {
+        long long r = it_stop - iter[i];
+        if (r > m) m = r;
+    }
+    if (m > 0) atomicMax(out, m);
+}
+
+__global__ void k_copy_i64(const long long* src, int64_t* dst, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+__global__ void k_copy_i32(const int* src, int32_t* dst, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+__global__ void k_copy_theta(const double* theta, const int* cur, size_t slot_stride, double* dst, int64_t C, int D) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= C * D) return;
+    int64_t c = i / D;
+    dst[i] = theta[(size_t)cur[c] * slot_stride + i];
+}
+
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------ profiling brackets
+struct Bracket {
+    rmhmc_handle* h;
+    int kind;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    Bracket(rmhmc_handle* h_, int kind_) : h(h_), kind(kind_) {
+        if (h->profiling) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, h->stream);
+        }
+    }
+    ~Bracket() {
+        if (h->profiling) {
+            cudaEventRecord(e1, h->stream);
+            h->prof[kind].ev.emplace_back(e0, e1);
+        }
+    }
+};
+
+void drain_profile(rmhmc_handle* h) {
+    for (auto& slot : h->prof) {
+        for (auto& pr : slot.ev) {
+            float ms = 0.f;
+            cudaEventSynchronize(pr.second);
+            cudaEventElapsedTime(&ms, pr.first, pr.second);
+            slot.ms += ms;
+            slot.launches += 1;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        slot.ev.clear();
+    }
+}
+
+// ------------------------------------------------------------------ kernel launch helpers
+template <int MODE>
+int launch_metric(rmhmc_handle* h, const MetricArgs& a) {
+    size_t smem = metric_smem_bytes(h->xs);
+    unsigned grid = blocks_for(a.n_chains, kMetricChains);
+    void (*kern)(MetricArgs) = nullptr;
+    int nt = MODE == 2 ? 1 : h->nt;
+    switch (nt) {
+        case 1: kern = k_metric<1, MODE>; break;
+        case 2: kern = k_metric<2, MODE>; break;
+        case 3: kern = k_metric<3, MODE>; break;
+        case 4: kern = k_metric<4, MODE>; break;
+        case 5: kern = k_metric<5, MODE>; break;
+        case 6: kern = k_metric<6, MODE>; break;
+        case 7: kern = k_metric<7, MODE>; break;
+        case 8: kern = k_metric<8, MODE>; break;
+        case 9: kern = k_metric<9, MODE>; break;
+        default: return fail(h, RMHMC_E_UNSUPPORTED, "metric kernel: dim too large");
+    }
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        Bracket b(h, MODE == 0 ? 0 : 1);
+        kern<<<grid, kMetricWarps * 32, smem, h->stream>>>(a);
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+MetricArgs metric_args(rmhmc_handle* h, int64_t C, const double* theta, double* g_out, double* grad_out,
+                       double* loglik_out, double* cbuf) {
+    MetricArgs a{};
+    a.x = h->x_pad; a.pair_tab = h->pair_tab; a.theta = theta;
+    a.g_out = g_out; a.grad_out = grad_out; a.loglik_out = loglik_out; a.cbuf = cbuf; a.skip = nullptr;
+    a.n_chains = (int)C; a.n_rows = (int)h->n_rows; a.n_rows_pad = h->n_rows_pad;
+    a.dim = h->dim; a.xs = h->xs; a.p2 = h->p2; a.p2p = h->p2p; a.alpha_inv = 1.0 / h->alpha;
+    return a;
+}
+
+int launch_tbuild(rmhmc_handle* h, int64_t C, const double* cbuf, double* tpack, const int* cur, int flip,
+                  size_t slot_stride) {
+    TBuildArgs a{};
+    a.x = h->x_pad; a.tri_tab = h->tri_tab; a.cbuf = cbuf; a.tpack = tpack; a.cur = cur; a.flip = flip;
+    a.slot_stride = slot_stride; a.n_chains = (int)C; a.n_rows_pad = h->n_rows_pad; a.xs = h->xs;
+    a.p3 = h->p3; a.p3p = h->p3p;
+    size_t smem = tbuild_smem_bytes(h->xs);
+    CUDA_TRY(h, cudaFuncSetAttribute(k_tbuild, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((h->p3p + kTbCols - 1) / kTbCols), blocks_for(C, kTbChains));
+    {
+        Bracket b(h, 2);
+        k_tbuild<<<grid, 256, smem, h->stream>>>(a);
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+template <typename T>
+int dev_alloc(rmhmc_handle* h, T** p, size_t count, std::vector<void*>* track) {
+    void* q = nullptr;
+    CUDA_TRY(h, cudaMalloc(&q, count * sizeof(T) + 16));
+    CUDA_TRY(h, cudaMemsetAsync(q, 0, count * sizeof(T) + 16, h->stream));
+    *p = reinterpret_cast<T*>(q);
+    if (track) track->push_back(q);
+    return RMHMC_OK;
+}
+
+void free_chains(rmhmc_handle* h) {
+    for (void* p : h->chain_allocs) cudaFree(p);
+    h->chain_allocs.clear();
+    h->S = ChainArrays{};
+    h->n_chains = 0;
+}
+
+void fill_engine_params(rmhmc_handle* h) {
+    EngineParams& P = h->P;
+    P.n_chains = (int)h->n_chains; P.dim = h->dim; P.ds = h->dim | 1;
+    P.p2 = h->p2; P.p2p = h->p2p; P.p3 = h->p3; P.p3p = h->p3p; P.n_rows_pad = h->n_rows_pad;
+    P.alpha = h->alpha; P.qidx = h->qidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
+    size_t C = (size_t)h->n_chains;
+    P.slot_theta = C * h->dim; P.slot_scalar = C; P.slot_gp = C * h->p2p;
+    P.slot_invg = C * h->dim * h->dim; P.slot_t = C * h->p3p;
+}
+
+int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
+    free_chains(h);
+    h->n_chains = C;
+    h->c_pad = pad_up((int)C, 64);
+    h->is_hmc = hmc;
+    auto* tr = &h->chain_allocs;
+    size_t c = (size_t)C, D = (size_t)h->dim;
+    ChainArrays& S = h->S;
+    int rc = 0;
+    rc |= dev_alloc(h, &S.theta, 2 * c * D, tr);
+    rc |= dev_alloc(h, &S.logjoint, 2 * c, tr);
+    rc |= dev_alloc(h, &S.grad, 2 * c * D, tr);
+    if (!hmc) {
+        rc |= dev_alloc(h, &S.gp, 2 * c * h->p2p, tr);
+        rc |= dev_alloc(h, &S.invg, 2 * c * D * D, tr);
+        rc |= dev_alloc(h, &S.logdet, 2 * c, tr);
+        rc |= dev_alloc(h, &S.tpack, 2 * c * h->p3p, tr);
+        rc |= dev_alloc(h, &S.trace, 2 * c * D, tr);
+        rc |= dev_alloc(h, &S.u0, c * D, tr);
+        rc |= dev_alloc(h, &S.g_tmp, c * h->p2p, tr);
+        rc |= dev_alloc(h, &S.cbuf, (size_t)h->c_pad * h->n_rows_pad, tr);
+    }
+    rc |= dev_alloc(h, &S.mom, c * D, tr);
+    rc |= dev_alloc(h, &S.theta_w, c * D, tr);
+    rc |= dev_alloc(h, &S.hcur, c, tr);
+    rc |= dev_alloc(h, &S.grad_tmp, c * D, tr);
+    rc |= dev_alloc(h, &S.loglik_tmp, c, tr);
+    rc |= dev_alloc(h, &S.cur, c, tr);
+    rc |= dev_alloc(h, &S.step, c, tr);
+    rc |= dev_alloc(h, &S.nsteps, c, tr);
+    rc |= dev_alloc(h, &S.dir, c, tr);
+    rc |= dev_alloc(h, &S.iter, c, tr);
+    rc |= dev_alloc(h, &S.accepted, c, tr);
+    rc |= dev_alloc(h, &S.leapfrogs, c, tr);
+    rc |= dev_alloc(h, &S.renorm_mom, c, tr);
+    rc |= dev_alloc(h, &S.renorm_pos, c, tr);
+    if (rc) { free_chains(h); return RMHMC_E_CUDA; }
+    fill_engine_params(h);
+    return RMHMC_OK;
+}
+
+size_t chain_smem(rmhmc_handle* h, bool with_t) { return chain_smem_bytes(h->dim, h->p2, h->p3p, with_t); }
+
+int set_chain_smem_attrs(rmhmc_handle* h) {
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem(h, true)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem(h, true)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem(h, false)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem(h, true)));
+    return RMHMC_OK;
+}
+
+// one RMHMC round: rmhmc.py:96-163 for every chain (+ trajectory start/end handling)
+int rmhmc_round(rmhmc_handle* h) {
+    const int64_t C = h->n_chains;
+    ChainArrays& S = h->S;
+    {
+        Bracket b(h, 3);
+        k_chain_front<<<(unsigned)C, 32, chain_smem(h, true), h->stream>>>(h->P, S);
+    }
+    h->launches += 1;
+    for (int fi = 2; fi <= h->P.n_fixed; ++fi) {
+        MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, nullptr, nullptr, nullptr);
+        int rc = launch_metric<0>(h, a);
+        if (rc) return rc;
+        {
+            Bracket b(h, 3);
+            k_chain_solve<<<(unsigned)C, 32, chain_smem(h, false), h->stream>>>(h->P, S, fi == h->P.n_fixed ? 1 : 0);
+        }
+        h->launches += 1;
+    }
+    MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, S.grad_tmp, S.loglik_tmp, S.cbuf);
+    int rc = launch_metric<1>(h, a);
+    if (rc) return rc;
+    rc = launch_tbuild(h, C, S.cbuf, S.tpack, S.cur, 1, h->P.slot_t);
+    if (rc) return rc;
+    {
+        Bracket b(h, 3);
+        k_chain_back<<<(unsigned)C, 32, chain_smem(h, true), h->stream>>>(h->P, S, 0);
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+int hmc_round(rmhmc_handle* h) {
+    const int64_t C = h->n_chains;
+    ChainArrays& S = h->S;
+    {
+        Bracket b(h, 3);
+        k_hmc_front<<<(unsigned)C, 32, 0, h->stream>>>(h->P, S);
+    }
+    MetricArgs a = metric_args(h, C, S.theta_w, nullptr, S.grad_tmp, S.loglik_tmp, nullptr);
+    int rc = launch_metric<2>(h, a);
+    if (rc) return rc;
+    {
+        Bracket b(h, 3);
+        k_hmc_back<<<(unsigned)C, 32, 0, h->stream>>>(h->P, S, 0);
+    }
+    h->launches += 2;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+int run_until(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done, bool hmc) {
+    if (h->n_chains <= 0 || h->is_hmc != hmc) return fail(h, RMHMC_E_STATE, "chains not initialised for this sampler");
+    if (!h->configured || !h->rng_set) return fail(h, RMHMC_E_STATE, "configure and set a tape / philox seed first");
+    h->P.it_stop = it_stop;
+    int64_t total = 0;
+    for (;;) {
+        long long rem = 0;
+        CUDA_TRY(h, cudaMemsetAsync(h->d_remaining, 0, sizeof(long long), h->stream));
+        k_remaining<<<64, 256, 0, h->stream>>>(h->S.iter, h->n_chains, it_stop, h->d_remaining);
+        CUDA_TRY(h, cudaMemcpyAsync(&rem, h->d_remaining, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (rem <= 0) break;
+        // every unfinished iteration needs at least one round; keep the host a bounded distance ahead
+        int64_t chunk = rem < 512 ? rem : 512;
+        for (int64_t r = 0; r < chunk; ++r) {
+            int rc = hmc ? hmc_round(h) : rmhmc_round(h);
+            if (rc) return rc;
+        }
+        total += chunk;
+    }
+    if (rounds_done) *rounds_done = total;
+    return RMHMC_OK;
+}
+
+}  // namespace
+
+// ====================================================================== extern "C"
+extern "C" {
+
+const char* rmhmc_version(void) { return "rmhmc_b200 0.1 (sm_100a, fp64 dmma)"; }
+
+const char* rmhmc_last_error(const rmhmc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double alpha, const double* xx_dev,
+                 const double* t_dev) {
+    if (!out) return RMHMC_E_INVALID;
+    *out = nullptr;
+    if (n_rows <= 0 || dim <= 0 || !xx_dev || !t_dev || !(alpha > 0)) {
+        g_create_error = "rmhmc_create: bad arguments";
+        return RMHMC_E_INVALID;
+    }
+    if (dim > kMaxDimWarp) {
+        g_create_error = "rmhmc_create: dim > 32 is not supported by this version";
+        return RMHMC_E_UNSUPPORTED;
+    }
+    auto* h = new rmhmc_handle();
+    auto bail = [&](int code) {
+        g_create_error = h->err;
+        rmhmc_destroy(h);
+        return code;
+    };
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return bail(RMHMC_E_CUDA);
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        h->err = "rmhmc_create: this library is built for sm_100a (B200) only";
+        return bail(RMHMC_E_UNSUPPORTED);
+    }
+    h->device = device;
+    h->n_rows = n_rows; h->dim = dim; h->alpha = alpha;
+    h->xs = x_stride(dim);
+    h->n_rows_pad = pad_up((int)n_rows, 32);
+    h->p2 = num_pairs(dim); h->p2p = pad_up(h->p2, 8);
+    h->p3 = num_triples(dim); h->p3p = pad_up(h->p3, 8);
+    h->nt = (h->p2p / 8 + kMetricWarps - 1) / kMetricWarps;
+
+    // index tables
+    std::vector<uchar2> pair_tab(h->p2p, make_uchar2(0, 0));
+    std::vector<unsigned char> pa(h->p2), pb(h->p2);
+    for (int a = 0; a < dim; ++a)
+        for (int b = a; b < dim; ++b) {
+            int i = pair_index(a, b, dim);
+            pair_tab[i] = make_uchar2((unsigned char)a, (unsigned char)b);
+            pa[i] = (unsigned char)a; pb[i] = (unsigned char)b;
+        }
+    std::vector<uchar4> tri_tab(h->p3p, make_uchar4(0, 0, 0, 0));
+    for (int i = 0; i < dim; ++i)
+        for (int j = i; j < dim; ++j)
+            for (int k = j; k < dim; ++k)
+                tri_tab[triple_index(i, j, k, dim)] = make_uchar4((unsigned char)i, (unsigned char)j, (unsigned char)k, 0);
+    std::vector<unsigned short> qidx((size_t)h->p2 * 32, 0);
+    for (int pr = 0; pr < h->p2; ++pr)
+        for (int d = 0; d < dim; ++d) qidx[(size_t)pr * 32 + d] = (unsigned short)triple_index_any(pa[pr], pb[pr], d, dim);
+    if (h->p3p > 65535) {
+        h->err = "packed triple index exceeds 16 bits";
+        return bail(RMHMC_E_UNSUPPORTED);
+    }
+
+#define CREATE_TRY(expr)                                                          \
+    do {                                                                          \
+        cudaError_t e__ = (expr);                                                 \
+        if (e__ != cudaSuccess) {                                                 \
+            h->err = std::string(#expr) + ": " + cudaGetErrorString(e__);         \
+            return bail(RMHMC_E_CUDA);                                            \
+        }                                                                         \
+    } while (0)
+    CREATE_TRY(cudaMalloc((void**)&h->x_pad, (size_t)h->n_rows_pad * h->xs * 8));
+    CREATE_TRY(cudaMalloc((void**)&h->pair_tab, pair_tab.size() * sizeof(uchar2)));
+    CREATE_TRY(cudaMalloc((void**)&h->tri_tab, tri_tab.size() * sizeof(uchar4)));
+    CREATE_TRY(cudaMalloc((void**)&h->qidx, qidx.size() * sizeof(unsigned short)));
+    CREATE_TRY(cudaMalloc((void**)&h->pair_a, pa.size()));
+    CREATE_TRY(cudaMalloc((void**)&h->pair_b, pb.size()));
+    CREATE_TRY(cudaMalloc((void**)&h->d_remaining, sizeof(long long)));
+    CREATE_TRY(cudaMemcpy(h->pair_tab, pair_tab.data(), pair_tab.size() * sizeof(uchar2), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(h->tri_tab, tri_tab.data(), tri_tab.size() * sizeof(uchar4), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(h->qidx, qidx.data(), qidx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(h->pair_a, pa.data(), pa.size(), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(h->pair_b, pb.data(), pb.size(), cudaMemcpyHostToDevice));
+    int64_t total = (int64_t)h->n_rows_pad * h->xs;
+    k_pad_design<<<blocks_for(total, 256), 256>>>(xx_dev, t_dev, h->x_pad, n_rows, dim, h->xs, h->n_rows_pad);
+    CREATE_TRY(cudaGetLastError());
+    CREATE_TRY(cudaDeviceSynchronize());
+#undef CREATE_TRY
+    h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
+    h->P.it_stop = 0; h->P.burn_in = 0; h->P.sample_cap = 0;
+    *out = h;
+    return RMHMC_OK;
+}
+
+void rmhmc_destroy(rmhmc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    drain_profile(h);
+    free_chains(h);
+    cudaFree(h->x_pad); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->qidx);
+    cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
+    delete h;
+}
+
+int rmhmc_set_stream(rmhmc_handle* h, void* cuda_stream) {
+    if (!h) return RMHMC_E_INVALID;
+    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return RMHMC_OK;
+}
+
+// ---------------------------------------------------------------------- seams
+int rmhmc_metric(rmhmc_handle* h, int64_t C, const double* theta, double* G, double* grad, double* logjoint) {
+    if (!h || C <= 0 || !theta) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_metric: bad arguments") : RMHMC_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    std::vector<void*> tmp;
+    double *gp = nullptr, *graw = nullptr, *ll = nullptr;
+    int rc = dev_alloc(h, &gp, (size_t)C * h->p2p, &tmp) | dev_alloc(h, &graw, (size_t)C * h->dim, &tmp) |
+             dev_alloc(h, &ll, (size_t)C, &tmp);
+    if (!rc) {
+        MetricArgs a = metric_args(h, C, theta, gp, graw, ll, nullptr);
+        rc = launch_metric<2>(h, a);                       // gradient + log-likelihood
+        if (!rc) { a.grad_out = nullptr; a.loglik_out = nullptr; rc = launch_metric<0>(h, a); }   // G
+    }
+    if (!rc) {
+        if (G) k_unpack_g<<<blocks_for(C * h->dim * h->dim, 256), 256, 0, h->stream>>>(gp, G, C, h->dim, h->p2p);
+        if (grad || logjoint)
+            k_seam_finish<<<blocks_for(C, 128), 128, 0, h->stream>>>(theta, graw, ll, grad, logjoint, C, h->dim, h->alpha);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { h->err = std::string("rmhmc_metric: ") + cudaGetErrorString(e); rc = RMHMC_E_CUDA; }
+    }
+    for (void* p : tmp) cudaFree(p);
+    return rc;
+}
+
+int rmhmc_metric_partials(rmhmc_handle* h, int64_t C, const double* theta, double* dG, double* trace) {
+    if (!h || C <= 0 || !theta) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_metric_partials: bad arguments") : RMHMC_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    std::vector<void*> tmp;
+    double *gp = nullptr, *graw = nullptr, *ll = nullptr, *cbuf = nullptr, *tp = nullptr;
+    int* cur = nullptr;
+    int64_t cpad = pad_up((int)C, 64);
+    int rc = dev_alloc(h, &gp, (size_t)C * h->p2p, &tmp) | dev_alloc(h, &graw, (size_t)C * h->dim, &tmp) |
+             dev_alloc(h, &ll, (size_t)C, &tmp) | dev_alloc(h, &cbuf, (size_t)cpad * h->n_rows_pad, &tmp) |
+             dev_alloc(h, &tp, (size_t)C * h->p3p, &tmp) | dev_alloc(h, &cur, (size_t)C, &tmp);
+    if (!rc) {
+        MetricArgs a = metric_args(h, C, theta, gp, graw, ll, cbuf);
+        rc = launch_metric<1>(h, a);
+    }
+    if (!rc) rc = launch_tbuild(h, C, cbuf, tp, cur, 0, 0);
+    if (!rc) {
+        if (dG) k_unpack_t<<<blocks_for(C * h->dim * h->dim * h->dim, 256), 256, 0, h->stream>>>(tp, dG, C, h->dim, h->p3p);
+        if (trace) {
+            EngineParams P = h->P;
+            P.n_chains = (int)C; P.dim = h->dim; P.ds = h->dim | 1; P.p2 = h->p2; P.p2p = h->p2p; P.p3 = h->p3;
+            P.p3p = h->p3p; P.qidx = h->qidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
+            rc = set_chain_smem_attrs(h);
+            if (!rc) k_seam_factor<<<(unsigned)C, 32, chain_smem(h, true), h->stream>>>(P, gp, tp, nullptr, nullptr, nullptr, trace);
+        }
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { h->err = std::string("rmhmc_metric_partials: ") + cudaGetErrorString(e); rc = RMHMC_E_CUDA; }
+    }
+    for (void* p : tmp) cudaFree(p);
+    return rc;
+}
+
+int rmhmc_chol_logdet(rmhmc_handle* h, int64_t C, const double* G, double* L, double* Ginv, double* logdet) {
+    if (!h || C <= 0 || !G) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_chol_logdet: bad arguments") : RMHMC_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    std::vector<void*> tmp;
+    double* gp = nullptr;
+    int rc = dev_alloc(h, &gp, (size_t)C * h->p2p, &tmp);
+    if (!rc) {
+        k_pack_g<<<blocks_for(C * h->p2p, 256), 256, 0, h->stream>>>(G, gp, C, h->dim, h->p2, h->p2p, h->pair_a, h->pair_b);
+        EngineParams P = h->P;
+        P.n_chains = (int)C; P.dim = h->dim; P.ds = h->dim | 1; P.p2 = h->p2; P.p2p = h->p2p; P.p3 = h->p3;
+        P.p3p = h->p3p; P.qidx = h->qidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
+        rc = set_chain_smem_attrs(h);
+        if (!rc) k_seam_factor<<<(unsigned)C, 32, chain_smem(h, false), h->stream>>>(P, gp, nullptr, L, Ginv, logdet, nullptr);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { h->err = std::string("rmhmc_chol_logdet: ") + cudaGetErrorString(e); rc = RMHMC_E_CUDA; }
+    }
+    for (void* p : tmp) cudaFree(p);
+    return rc;
+}
+
+// ---------------------------------------------------------------------- engine
+static int chains_init_common(rmhmc_handle* h, int64_t C, const double* theta0, bool hmc) {
+    if (!h || C <= 0) return h ? fail(h, RMHMC_E_INVALID, "chains_init: bad arguments") : RMHMC_E_INVALID;
+    if (C > 0x7fffffff / 64) return fail(h, RMHMC_E_INVALID, "chains_init: too many chains");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = alloc_chains(h, C, hmc);
+    if (rc) return rc;
+    ChainArrays& S = h->S;
+    if (theta0)
+        CUDA_TRY(h, cudaMemcpyAsync(S.theta_w, theta0, (size_t)C * h->dim * 8, cudaMemcpyDeviceToDevice, h->stream));
+    else
+        k_fill<<<blocks_for(C * h->dim, 256), 256, 0, h->stream>>>(S.theta_w, C * h->dim, hmc ? 0.0 : 1e-3);
+    // trace pointers / samples refer to the previous chain set
+    h->P.samples = nullptr; h->P.tr_theta_steps = nullptr; h->P.tr_mom_end = nullptr; h->P.tr_theta_end = nullptr;
+    h->P.tr_mom0 = nullptr; h->P.tr_hcur = nullptr; h->P.tr_hprop = nullptr; h->P.tr_flags = nullptr; h->P.tr_iters = 0;
+    h->rng_set = false;
+    if (hmc) {
+        MetricArgs a = metric_args(h, C, S.theta_w, nullptr, S.grad_tmp, S.loglik_tmp, nullptr);
+        rc = launch_metric<2>(h, a);
+        if (rc) return rc;
+        k_hmc_back<<<(unsigned)C, 32, 0, h->stream>>>(h->P, S, 1);
+    } else {
+        rc = set_chain_smem_attrs(h);
+        if (rc) return rc;
+        MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, S.grad_tmp, S.loglik_tmp, S.cbuf);
+        rc = launch_metric<1>(h, a);
+        if (rc) return rc;
+        rc = launch_tbuild(h, C, S.cbuf, S.tpack, S.cur, 0, h->P.slot_t);
+        if (rc) return rc;
+        k_chain_back<<<(unsigned)C, 32, chain_smem(h, true), h->stream>>>(h->P, S, 1);
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return RMHMC_OK;
+}
+
+int rmhmc_chains_init(rmhmc_handle* h, int64_t C, const double* theta0) { return chains_init_common(h, C, theta0, false); }
+int hmc_chains_init(rmhmc_handle* h, int64_t C, const double* theta0) { return chains_init_common(h, C, theta0, true); }
+
+int rmhmc_configure(rmhmc_handle* h, int n_leapfrog, double step_size, int n_fixed) {
+    if (!h || n_leapfrog < 1 || n_fixed < 0 || !(step_size > 0)) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_configure: bad arguments") : RMHMC_E_INVALID;
+    h->P.n_leapfrog = n_leapfrog; h->P.step_size = step_size; h->P.n_fixed = n_fixed;
+    h->configured = true;
+    return RMHMC_OK;
+}
+int hmc_configure(rmhmc_handle* h, int n_leapfrog, double step_size) {
+    if (!h || n_leapfrog < 1 || !(step_size > 0)) return h ? fail(h, RMHMC_E_INVALID, "hmc_configure: bad arguments") : RMHMC_E_INVALID;
+    h->P.n_leapfrog = n_leapfrog; h->P.step_size = step_size; h->P.n_fixed = 0;
+    h->configured = true;
+    return RMHMC_OK;
+}
+
+int rmhmc_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const double* z, const double* u_step,
+                   const double* z_dir, const double* u_acc) {
+    if (!h || n_window <= 0 || !z || !u_step || !z_dir || !u_acc) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_set_tape: bad arguments") : RMHMC_E_INVALID;
+    h->P.rng_mode = 0; h->P.tape_base = it_base; h->P.tape_z = z; h->P.tape_u_step = u_step;
+    h->P.tape_z_dir = z_dir; h->P.tape_u_acc = u_acc;
+    h->rng_set = true;
+    return RMHMC_OK;
+}
+int hmc_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const double* z, const double* u_step,
+                 const double* u_acc) {
+    if (!h || n_window <= 0 || !z || !u_step || !u_acc) return h ? fail(h, RMHMC_E_INVALID, "hmc_set_tape: bad arguments") : RMHMC_E_INVALID;
+    h->P.rng_mode = 0; h->P.tape_base = it_base; h->P.tape_z = z; h->P.tape_u_step = u_step;
+    h->P.tape_z_dir = nullptr; h->P.tape_u_acc = u_acc;
+    h->rng_set = true;
+    return RMHMC_OK;
+}
+int rmhmc_set_philox(rmhmc_handle* h, uint64_t seed, int64_t chain_offset) {
+    if (!h) return RMHMC_E_INVALID;
+    h->P.rng_mode = 1; h->P.seed = seed; h->P.chain_offset = chain_offset;
+    h->rng_set = true;
+    return RMHMC_OK;
+}
+
+int rmhmc_set_samples(rmhmc_handle* h, double* samples, int64_t capacity, int64_t burn_in) {
+    if (!h || (samples && capacity <= 0)) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_set_samples: bad arguments") : RMHMC_E_INVALID;
+    h->P.samples = samples; h->P.sample_cap = capacity; h->P.burn_in = burn_in;
+    return RMHMC_OK;
+}
+
+int rmhmc_set_trace(rmhmc_handle* h, int64_t n_iters, double* theta_steps, double* mom_end, double* theta_end,
+                    double* mom0, double* h_current, double* h_proposed, int32_t* flags) {
+    if (!h) return RMHMC_E_INVALID;
+    if (theta_steps && (!mom_end || !theta_end || !mom0 || !h_current || !h_proposed || !flags || n_iters <= 0))
+        return fail(h, RMHMC_E_INVALID, "rmhmc_set_trace: all buffers are required");
+    h->P.tr_iters = theta_steps ? n_iters : 0;
+    h->P.tr_theta_steps = theta_steps; h->P.tr_mom_end = theta_steps ? mom_end : nullptr;
+    h->P.tr_theta_end = theta_steps ? theta_end : nullptr; h->P.tr_mom0 = theta_steps ? mom0 : nullptr;
+    h->P.tr_hcur = theta_steps ? h_current : nullptr; h->P.tr_hprop = theta_steps ? h_proposed : nullptr;
+    h->P.tr_flags = theta_steps ? flags : nullptr;
+    return RMHMC_OK;
+}
+
+int rmhmc_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop) {
+    if (!h || n_rounds < 0) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_advance: bad arguments") : RMHMC_E_INVALID;
+    if (h->n_chains <= 0 || h->is_hmc) return fail(h, RMHMC_E_STATE, "rmhmc_advance: call rmhmc_chains_init first");
+    if (!h->configured || !h->rng_set) return fail(h, RMHMC_E_STATE, "rmhmc_advance: configure and set a tape / philox seed first");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->P.it_stop = it_stop;
+    for (int64_t r = 0; r < n_rounds; ++r) {
+        int rc = rmhmc_round(h);
+        if (rc) return rc;
+    }
+    return RMHMC_OK;
+}
+
+int rmhmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done) {
+    if (!h) return RMHMC_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return run_until(h, it_stop, rounds_done, false);
+}
+int hmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done) {
+    if (!h) return RMHMC_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return run_until(h, it_stop, rounds_done, true);
+}
+
+int rmhmc_read_state(rmhmc_handle* h, double* theta, int64_t* iters, int64_t* accepted, int64_t* leapfrogs,
+                     int32_t* renorm_mom, int32_t* renorm_pos) {
+    if (!h) return RMHMC_E_INVALID;
+    if (h->n_chains <= 0) return fail(h, RMHMC_E_STATE, "rmhmc_read_state: no chains");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int64_t C = h->n_chains;
+    ChainArrays& S = h->S;
+    unsigned gb = blocks_for(C, 256);
+    if (theta) k_copy_theta<<<blocks_for(C * h->dim, 256), 256, 0, h->stream>>>(S.theta, S.cur, h->P.slot_theta, theta, C, h->dim);
+    if (iters) k_copy_i64<<<gb, 256, 0, h->stream>>>(S.iter, iters, C);
+    if (accepted) k_copy_i64<<<gb, 256, 0, h->stream>>>(S.accepted, accepted, C);
+    if (leapfrogs) k_copy_i64<<<gb, 256, 0, h->stream>>>(S.leapfrogs, leapfrogs, C);
+    if (renorm_mom) k_copy_i32<<<gb, 256, 0, h->stream>>>(S.renorm_mom, renorm_mom, C);
+    if (renorm_pos) k_copy_i32<<<gb, 256, 0, h->stream>>>(S.renorm_pos, renorm_pos, C);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return RMHMC_OK;
+}
+
+int64_t rmhmc_launch_count(const rmhmc_handle* h) { return h ? h->launches : 0; }
+
+int rmhmc_profile_enable(rmhmc_handle* h, int enable) {
+    if (!h) return RMHMC_E_INVALID;
+    drain_profile(h);
+    for (auto& s : h->prof) { s.ms = 0.0; s.launches = 0; }
+    h->profiling = enable != 0;
+    return RMHMC_OK;
+}
+int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches) {
+    if (!h || kind < 0 || kind > 3) return RMHMC_E_INVALID;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    drain_profile(h);
+    if (ms) *ms = h->prof[kind].ms;
+    if (launches) *launches = h->prof[kind].launches;
+    return RMHMC_OK;
+}
+
+int blr_ess_batched(int device, void* cuda_stream, const double* samples, int64_t n_chains, int64_t n_samples,
+                    int dim, int64_t chain_stride, int64_t row_stride, int64_t max_lag, double* ess) {
+    if (!samples || !ess || n_chains <= 0 || n_samples < 2 || dim <= 0 || max_lag < 1 || max_lag > n_samples - 1)
+        return RMHMC_E_INVALID;
+    if (n_samples > 24000 || dim > 65535) return RMHMC_E_UNSUPPORTED;
+    if (cudaSetDevice(device) != cudaSuccess) return RMHMC_E_CUDA;
+    int n_fft = 1;
+    while (n_fft < n_samples) n_fft *= 2;           // tools.py:16-19
+    n_fft += 1;                                     // tools.py:23
+    size_t smem = (size_t)n_samples * 8;
+    if (cudaFuncSetAttribute(k_ess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return RMHMC_E_CUDA;
+    dim3 grid((unsigned)n_chains, (unsigned)dim);
+    k_ess<<<grid, kEssThreads, smem, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+        samples, (size_t)chain_stride, (size_t)row_stride, (int)n_samples, (int)max_lag, n_fft, ess, dim);
+    return cudaGetLastError() == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// Batched effective sample size with the reference's exact semantics (tools.py:21-74):
+// circular autocorrelation with period nFFT = nextpow2(S)+1 (a port quirk),
+// Geyer's initial monotone sequence, clip at 1.  The reference goes through an FFT of every
+// series; here each (chain, parameter) series is handled by one CTA that evaluates lags directly
+// and stops at the first non-positive monotone Gamma pair -- nothing beyond it enters the
+// estimate.  The circular aliasing of the reference is reproduced term by term:
+//   acf_circ[k] = lin[k] + lin[nFFT - k]   (lin[j] = sum_t y_t y_{t+j}, 0 for j >= S).
+#pragma once
+#include "common.cuh"
+
+namespace rmhmc {
+
+constexpr int kEssThreads = 128;
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double block_sum_128(double v, double* scratch) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return scratch[0] + scratch[1] + scratch[2] + scratch[3];
+}
+
+__device__ __forceinline__ double lin_lag(const double* y, int S, int lag, double* scratch) {
+    double s = 0.0;
+    if (lag < S)
+        for (int t = threadIdx.x; t + lag < S; t += kEssThreads) s += y[t] * y[t + lag];
+    return block_sum_128(s, scratch);
+}
+
+// samples: series (c, d) element s at samples[c*chain_stride + s*row_stride + d]
+__global__ void __launch_bounds__(kEssThreads) k_ess(const double* __restrict__ samples, size_t chain_stride,
+                                                      size_t row_stride, int S, int max_lag, int n_fft,
+                                                      double* __restrict__ ess_out, int D) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* y = reinterpret_cast<double*>(smem_raw);
+    __shared__ double scratch[4];
+    const int c = blockIdx.x, d = blockIdx.y;
+    const double* src = samples + (size_t)c * chain_stride + d;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < S; t += kEssThreads) {
+        double v = src[(size_t)t * row_stride];
+        y[t] = v;
+        s += v;
+    }
+    double mean = block_sum_128(s, scratch) / S;
+    for (int t = threadIdx.x; t < S; t += kEssThreads) y[t] -= mean;
+    __syncthreads();
+    const double a0 = lin_lag(y, S, 0, scratch);        // circular lag 0: alias lag n_fft >= S is empty
+    const int half = (max_lag + 1) / 2;
+    double run_min = 0.0, sum_pos = 0.0;
+    for (int j = 0; j < half; ++j) {
+        double gam = 0.0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int k = 2 * j + e;
+            double a = (k == 0) ? a0 : lin_lag(y, S, k, scratch);
+            if (k > 0 && n_fft - k < S) a += lin_lag(y, S, n_fft - k, scratch);
+            gam += a / a0;
+        }
+        run_min = (j == 0) ? gam : fmin(gam, run_min);
+        if (!(run_min > 0.0)) break;       // monotone sequence: nothing after this is positive
+        sum_pos += run_min;
+    }
+    if (threadIdx.x == 0) {
+        double mono = -1.0 + 2.0 * sum_pos;              // -rho_0 + 2 sum Gamma  (rho_0 = 1)
+        if (mono < 1.0) mono = 1.0;
+        // a frozen series has zero variance: the reference divides 0/0 and returns NaN
+        ess_out[(size_t)c * D + d] = (a0 > 0.0) ? (double)S / mono : __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+#endif
+
+}  // namespace rmhmc

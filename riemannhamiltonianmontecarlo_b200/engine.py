@@ -1,0 +1,264 @@
+"""Host side of the batched samplers: device buffers (torch) + calls into the C ABI.
+
+``LogisticData``   a data set bound to a device handle; also exposes the parity seams
+                   (metric / partials / Cholesky) the reference inlines in rmhmc.py.
+``RMHMCSampler``   many independent RMHMC chains (rmhmc.py:37-191 per chain).
+``HMCSampler``     many independent Euclidean-HMC chains (hmc.py:38-89 per chain).
+
+PyTorch is plumbing here (allocation, H2D/D2H, streams); every number is produced by the CUDA
+kernels in ``csrc/``.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int64, c_void_p
+
+import numpy as np
+
+from . import _capi
+
+HUGE_ITERS = 1 << 60
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+class LogisticData:
+    """``(XX, t)`` of the Bayesian logistic regression, resident on one GPU."""
+
+    def __init__(self, xx, t, alpha: float = 100.0, device: str | int = "cuda:0"):
+        torch = _capi.require_cuda()
+        self._lib = _capi.load()
+        self.torch = torch
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        xx = np.ascontiguousarray(xx, dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(-1)
+        if xx.ndim != 2 or xx.shape[0] != t.shape[0]:
+            raise ValueError("XX must be (N, D) and t must have N entries")
+        self.n_rows, self.dim = xx.shape
+        self.alpha = float(alpha)
+        self.h2d_bytes = xx.nbytes + t.nbytes
+        xx_d = torch.from_numpy(xx).to(self.device)
+        t_d = torch.from_numpy(t).to(self.device)
+        handle = c_void_p()
+        rc = self._lib.rmhmc_create(ctypes.byref(handle), self.device.index or 0, self.n_rows, self.dim,
+                                    self.alpha, _ptr(xx_d), _ptr(t_d))
+        _capi.check(rc, None, "rmhmc_create")
+        self.handle = handle
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _capi.check(self._lib.rmhmc_set_stream(self.handle, c_void_p(stream)), self.handle, "rmhmc_set_stream")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.rmhmc_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self, arr, dtype=np.float64):
+        return self.torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(self.device)
+
+    def _empty(self, *shape, dtype=None):
+        return self.torch.empty(*shape, dtype=dtype or self.torch.float64, device=self.device)
+
+    # ---------------------------------------------------------------- parity seams
+    def metric(self, theta):
+        """G (C,D,D), grad (C,D), logjoint (C,) at theta (C,D)   [rmhmc.py:51-57, :100, :31-34]."""
+        th = self._dev(np.atleast_2d(theta))
+        c = th.shape[0]
+        g, grad, lj = self._empty(c, self.dim, self.dim), self._empty(c, self.dim), self._empty(c)
+        _capi.check(self._lib.rmhmc_metric(self.handle, c, _ptr(th), _ptr(g), _ptr(grad), _ptr(lj)),
+                    self.handle, "rmhmc_metric")
+        return g.cpu().numpy(), grad.cpu().numpy(), lj.cpu().numpy()
+
+    def metric_partials(self, theta):
+        """dG (C,D,D,D) and tr(G^-1 dG_d) (C,D) at theta (C,D)   [rmhmc.py:64-77]."""
+        th = self._dev(np.atleast_2d(theta))
+        c = th.shape[0]
+        dg, tr = self._empty(c, self.dim, self.dim, self.dim), self._empty(c, self.dim)
+        _capi.check(self._lib.rmhmc_metric_partials(self.handle, c, _ptr(th), _ptr(dg), _ptr(tr)),
+                    self.handle, "rmhmc_metric_partials")
+        return dg.cpu().numpy(), tr.cpu().numpy()
+
+    def chol_logdet(self, g):
+        """Lower Cholesky factor, inverse and sum log diag of SPD matrices g (C,D,D)   [rmhmc.py:58-60,171]."""
+        gd = self._dev(g)
+        c = gd.shape[0]
+        l, gi, ld = self._empty(c, self.dim, self.dim), self._empty(c, self.dim, self.dim), self._empty(c)
+        _capi.check(self._lib.rmhmc_chol_logdet(self.handle, c, _ptr(gd), _ptr(l), _ptr(gi), _ptr(ld)),
+                    self.handle, "rmhmc_chol_logdet")
+        return l.cpu().numpy(), gi.cpu().numpy(), ld.cpu().numpy()
+
+
+class _SamplerBase:
+    _is_hmc = False
+
+    def __init__(self, data: LogisticData, n_chains: int, theta0=None):
+        self.data = data
+        self._lib = data._lib
+        self.torch = data.torch
+        self.h = data.handle
+        self.n_chains = int(n_chains)
+        self.dim = data.dim
+        self._keep = {}          # device buffers the handle points into
+        self.samples = None
+        self.burn_in = 0
+        self.trace = None
+        th0 = None if theta0 is None else data._dev(np.asarray(theta0, dtype=np.float64).reshape(self.n_chains, self.dim))
+        fn = self._lib.hmc_chains_init if self._is_hmc else self._lib.rmhmc_chains_init
+        _capi.check(fn(self.h, self.n_chains, _ptr(th0)), self.h, "chains_init")
+
+    # ---------------------------------------------------------------- randomness
+    def set_philox(self, seed: int, chain_offset: int = 0):
+        _capi.check(self._lib.rmhmc_set_philox(self.h, int(seed) & (2**64 - 1), int(chain_offset)), self.h, "set_philox")
+
+    # ---------------------------------------------------------------- outputs
+    def set_samples(self, capacity: int, burn_in: int):
+        """Allocate the (C, capacity, D) sample store; row it-burn_in receives the state after iteration it."""
+        self.samples = self.torch.zeros(self.n_chains, int(capacity), self.dim, dtype=self.torch.float64,
+                                        device=self.data.device)
+        self.burn_in = int(burn_in)
+        _capi.check(self._lib.rmhmc_set_samples(self.h, _ptr(self.samples), int(capacity), int(burn_in)),
+                    self.h, "set_samples")
+        return self.samples
+
+    def set_trace(self, n_iters: int, n_leapfrog: int):
+        t, dev, c, d = self.torch, self.data.device, self.n_chains, self.dim
+        nan = float("nan")
+        self.trace = {
+            "theta_steps": t.full((c, n_iters, n_leapfrog, d), nan, dtype=t.float64, device=dev),
+            "mom_end": t.zeros(c, n_iters, d, dtype=t.float64, device=dev),
+            "theta_end": t.zeros(c, n_iters, d, dtype=t.float64, device=dev),
+            "mom0": t.zeros(c, n_iters, d, dtype=t.float64, device=dev),
+            "h_current": t.zeros(c, n_iters, dtype=t.float64, device=dev),
+            "h_proposed": t.zeros(c, n_iters, dtype=t.float64, device=dev),
+            "flags": t.zeros(c, n_iters, dtype=t.int32, device=dev),
+        }
+        tr = self.trace
+        _capi.check(self._lib.rmhmc_set_trace(self.h, int(n_iters), _ptr(tr["theta_steps"]), _ptr(tr["mom_end"]),
+                                              _ptr(tr["theta_end"]), _ptr(tr["mom0"]), _ptr(tr["h_current"]),
+                                              _ptr(tr["h_proposed"]), _ptr(tr["flags"])), self.h, "set_trace")
+
+    def trace_numpy(self):
+        out = {k: v.cpu().numpy() for k, v in self.trace.items()}
+        fl = out["flags"]
+        out["accepted"] = (fl & 1).astype(bool)
+        out["used_uniform"] = (fl & 2).astype(bool)
+        out["direction"] = np.where(fl & 16, 1, -1)
+        out["n_steps"] = fl >> 8
+        return out
+
+    def state(self):
+        t, dev, c = self.torch, self.data.device, self.n_chains
+        theta = t.empty(c, self.dim, dtype=t.float64, device=dev)
+        iters = t.empty(c, dtype=t.int64, device=dev)
+        acc = t.empty(c, dtype=t.int64, device=dev)
+        lf = t.empty(c, dtype=t.int64, device=dev)
+        rm = t.empty(c, dtype=t.int32, device=dev)
+        rp = t.empty(c, dtype=t.int32, device=dev)
+        _capi.check(self._lib.rmhmc_read_state(self.h, _ptr(theta), _ptr(iters), _ptr(acc), _ptr(lf), _ptr(rm), _ptr(rp)),
+                    self.h, "read_state")
+        return {"theta": theta.cpu().numpy(), "iters": iters.cpu().numpy(), "accepted": acc.cpu().numpy(),
+                "leapfrogs": lf.cpu().numpy(), "renorm_momentum": rm.cpu().numpy(), "renorm_position": rp.cpu().numpy()}
+
+    def launch_count(self) -> int:
+        return int(self._lib.rmhmc_launch_count(self.h))
+
+
+class RMHMCSampler(_SamplerBase):
+    """C independent RMHMC chains; every ``round`` advances each chain by one generalized leapfrog step."""
+
+    def __init__(self, data: LogisticData, n_chains: int, n_leapfrog: int = 6, step_size: float = 0.5,
+                 n_fixed: int = 4, theta0=None):
+        super().__init__(data, n_chains, theta0)
+        self.n_leapfrog, self.step_size, self.n_fixed = int(n_leapfrog), float(step_size), int(n_fixed)
+        _capi.check(self._lib.rmhmc_configure(self.h, self.n_leapfrog, self.step_size, self.n_fixed), self.h, "configure")
+
+    def set_tape(self, z, u_step, z_dir, u_acc, it_base: int = 0):
+        """Host draws in the C-ABI layout: z (W,C,D), u_step/z_dir/u_acc (W,C)."""
+        d = self.data
+        self._keep["tape"] = [d._dev(z), d._dev(u_step), d._dev(z_dir), d._dev(u_acc)]
+        w = self._keep["tape"][0].shape[0]
+        zt, us, zd, ua = self._keep["tape"]
+        assert zt.shape == (w, self.n_chains, self.dim) and us.shape == (w, self.n_chains)
+        _capi.check(self._lib.rmhmc_set_tape(self.h, int(it_base), int(w), _ptr(zt), _ptr(us), _ptr(zd), _ptr(ua)),
+                    self.h, "set_tape")
+
+    def set_trace(self, n_iters: int):          # noqa: D102
+        super().set_trace(n_iters, self.n_leapfrog)
+
+    def run(self, it_stop: int) -> int:
+        """Run rounds until every chain has completed ``it_stop`` iterations; returns the round count."""
+        rounds = c_int64(0)
+        _capi.check(self._lib.rmhmc_run(self.h, int(it_stop), ctypes.byref(rounds)), self.h, "rmhmc_run")
+        return rounds.value
+
+    def advance(self, n_rounds: int, it_stop: int = HUGE_ITERS):
+        """Enqueue ``n_rounds`` rounds without synchronising (free-running chains)."""
+        _capi.check(self._lib.rmhmc_advance(self.h, int(n_rounds), int(it_stop)), self.h, "rmhmc_advance")
+
+    def profile(self, enable: bool):
+        _capi.check(self._lib.rmhmc_profile_enable(self.h, 1 if enable else 0), self.h, "profile_enable")
+
+    def profile_read(self):
+        """{kind: (milliseconds, launches)} for metric_fp, metric_closing, partials, chain stages."""
+        names = ["metric_fp", "metric_closing", "partials", "chain"]
+        out = {}
+        for k, nm in enumerate(names):
+            ms, n = ctypes.c_double(0), c_int64(0)
+            _capi.check(self._lib.rmhmc_profile_read(self.h, k, ctypes.byref(ms), ctypes.byref(n)), self.h, "profile_read")
+            out[nm] = (ms.value, n.value)
+        return out
+
+
+class HMCSampler(_SamplerBase):
+    """C independent Euclidean-HMC chains (identity mass)."""
+
+    _is_hmc = True
+
+    def __init__(self, data: LogisticData, n_chains: int, n_leapfrog: int = 100, step_size: float = 0.14, theta0=None):
+        super().__init__(data, n_chains, theta0)
+        self.n_leapfrog, self.step_size = int(n_leapfrog), float(step_size)
+        _capi.check(self._lib.hmc_configure(self.h, self.n_leapfrog, self.step_size), self.h, "hmc_configure")
+
+    def set_tape(self, z, u_step, u_acc, it_base: int = 0):
+        d = self.data
+        self._keep["tape"] = [d._dev(z), d._dev(u_step), d._dev(u_acc)]
+        zt, us, ua = self._keep["tape"]
+        _capi.check(self._lib.hmc_set_tape(self.h, int(it_base), int(zt.shape[0]), _ptr(zt), _ptr(us), _ptr(ua)),
+                    self.h, "hmc_set_tape")
+
+    def set_trace(self, n_iters: int):          # noqa: D102
+        super().set_trace(n_iters, 1)
+
+    def run(self, it_stop: int) -> int:
+        rounds = c_int64(0)
+        _capi.check(self._lib.hmc_run(self.h, int(it_stop), ctypes.byref(rounds)), self.h, "hmc_run")
+        return rounds.value
+
+
+def ess_batched(samples, max_lag: int | None = None):
+    """ESS of every (chain, parameter) series of a device or host array (C, S, D) -> numpy (C, D).
+
+    Exactly ``tools.CalculateESS(samples[c], max_lag)`` (tools.py:32-74), computed on the GPU.
+    """
+    torch = _capi.require_cuda()
+    lib = _capi.load()
+    if isinstance(samples, np.ndarray):
+        samples = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)).cuda()
+    assert samples.dim() == 3 and samples.dtype == torch.float64
+    c, s, d = samples.shape
+    if max_lag is None:
+        max_lag = s - 1
+    out = torch.empty(c, d, dtype=torch.float64, device=samples.device)
+    stream = torch.cuda.current_stream(samples.device).cuda_stream
+    rc = lib.blr_ess_batched(samples.device.index or 0, c_void_p(stream), _ptr(samples), c, s, d,
+                             samples.stride(0), samples.stride(1), int(max_lag), _ptr(out))
+    if rc != 0:
+        raise _capi.RmhmcError(f"blr_ess_batched failed (code {rc})")
+    return out

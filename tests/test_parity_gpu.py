@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures generated from the unmodified reference.  Tolerances follow BASELINE.json's north_star:
+per-step theta, p, H within 1e-9 relative in FP64; accept/reject decisions bit-exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import blr_oracle as bo
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9      # north_star: per-step theta, p and H agree within 1e-9 relative in FP64
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / scale
+
+
+@pytest.fixture(scope="module")
+def pkg(built_library):
+    import riemannhamiltonianmontecarlo_b200 as r
+    return r
+
+
+def _thetas(d, n, seed):
+    rng = np.random.default_rng(seed)
+    th = rng.normal(0, 0.5, (n, d))
+    th[0] = 1e-3          # the reference's starting point
+    return th
+
+
+@pytest.mark.parametrize("shape", ["australian", "german"])
+def test_metric_seam_matches_oracle(pkg, shape):
+    xx, t = pkg.datasets.shaped(shape)
+    d = xx.shape[1]
+    thetas = _thetas(d, 37, 11)      # 37: a ragged last tile of chains
+    data = pkg.LogisticData(xx, t)
+    g, grad, lj = data.metric(thetas)
+    for c in range(thetas.shape[0]):
+        w = thetas[c].reshape(-1, 1)
+        _, _, _, g_ref = bo.fisher_metric(xx, w)
+        assert rel_err(g[c], g_ref) < 1e-12
+        assert rel_err(grad[c], bo.likelihood_gradient(xx, t, w)[:, 0]) < 1e-11
+        assert abs(lj[c] - bo._scalar(bo.log_joint(xx, t, w))) < 1e-11 * abs(lj[c])
+    data.close()
+
+
+@pytest.mark.parametrize("shape", ["australian", "german"])
+def test_partials_seam_matches_oracle(pkg, shape):
+    xx, t = pkg.datasets.shaped(shape)
+    d = xx.shape[1]
+    thetas = _thetas(d, 9, 12)
+    data = pkg.LogisticData(xx, t)
+    dg, tr = data.metric_partials(thetas)
+    for c in range(thetas.shape[0]):
+        w = thetas[c].reshape(-1, 1)
+        t_ref = bo.metric_tensor(xx, w)
+        assert rel_err(dg[c], t_ref) < 1e-12
+        _, p, v, g_ref = bo.fisher_metric(xx, w)
+        _, tr_ref = bo.metric_partials(xx, p, v, np.linalg.inv(g_ref))
+        assert rel_err(tr[c], tr_ref[:, 0]) < 1e-11
+    data.close()
+
+
+def test_chol_seam_matches_numpy(pkg):
+    xx, t = pkg.datasets.shaped("german")
+    thetas = _thetas(xx.shape[1], 5, 13)
+    data = pkg.LogisticData(xx, t)
+    g, _, _ = data.metric(thetas)
+    l, gi, ld = data.chol_logdet(g)
+    for c in range(5):
+        l_ref = np.linalg.cholesky(g[c])
+        assert rel_err(l[c], l_ref) < 1e-13
+        assert rel_err(gi[c], np.linalg.inv(g[c])) < 1e-12
+        assert abs(ld[c] - np.sum(np.log(np.diag(l_ref)))) < 1e-12 * abs(ld[c])
+    data.close()
+
+
+def _run_tape_fixture(pkg, fx, n_chains=None):
+    xx, t = fx["xx"], fx["t"]
+    n_iter, burn_in = int(fx["n_iter"]), int(fx["burn_in"])
+    c = fx["z"].shape[1] if n_chains is None else n_chains
+    data = pkg.LogisticData(xx, t)
+    s = pkg.RMHMCSampler(data, c, int(fx["n_leapfrog"]), float(fx["step_size"]), int(fx["n_fixed"]))
+    s.set_tape(fx["z"][:, :c], fx["u_step"][:, :c], fx["z_dir"][:, :c], fx["u_acc"][:, :c])
+    s.set_samples(n_iter - burn_in, burn_in)
+    s.set_trace(n_iter)
+    s.run(n_iter)
+    tr = s.trace_numpy()
+    samples = s.samples.cpu().numpy()
+    st = s.state()
+    data.close()
+    return tr, samples, st
+
+
+@pytest.mark.parametrize("name", ["rmhmc_australian_shaped", "rmhmc_german_shaped", "rmhmc_german_real",
+                                  "rmhmc_pima_real"])
+def test_rmhmc_trajectories_match_reference(pkg, golden, name):
+    """Same data, same host draws: per-step theta, end momentum, H and the accept decisions."""
+    fx = golden(name)
+    tr, samples, st = _run_tape_fixture(pkg, fx)
+    c, n_iter = fx["n_steps"].shape
+    # decisions and integer draws: bit-exact
+    assert np.array_equal(tr["n_steps"], fx["n_steps"])
+    assert np.array_equal(tr["direction"], fx["direction"])
+    assert np.array_equal(tr["accepted"], fx["accepted"])
+    assert np.array_equal(tr["used_uniform"], fx["used_uniform"])
+    assert np.array_equal(st["iters"], np.full(c, n_iter))
+    assert np.array_equal(st["accepted"], fx["accepted"].sum(axis=1))
+    assert np.array_equal(st["leapfrogs"], fx["n_steps"].sum(axis=1))
+    worst = 0.0
+    for ci in range(c):
+        for it in range(n_iter):
+            ns = int(fx["n_steps"][ci, it])
+            for s_ in range(ns):
+                worst = max(worst, rel_err(tr["theta_steps"][ci, it, s_], fx["theta_steps"][ci, it, s_]))
+            worst = max(worst, rel_err(tr["mom_end"][ci, it], fx["mom_end"][ci, it]))
+            worst = max(worst, rel_err(tr["mom0"][ci, it], fx["mom0"][ci, it]))
+            worst = max(worst, abs(tr["h_current"][ci, it] - fx["h_current"][ci, it]) / abs(fx["h_current"][ci, it]))
+            worst = max(worst, abs(tr["h_proposed"][ci, it] - fx["h_proposed"][ci, it]) / abs(fx["h_proposed"][ci, it]))
+    assert worst < RTOL, worst
+    # stored samples: rows 1.. equal the reference's wSaved rows 1.. (row 0 is never written)
+    assert rel_err(samples[:, 1:], fx["samples"][:, 1:]) < RTOL
+    assert np.all(samples[:, 0] == 0.0)
+
+
+def test_rmhmc_matches_live_oracle_on_fresh_tape(pkg):
+    """Not just the committed vectors: a tape drawn now, oracle run now."""
+    xx, t = pkg.datasets.shaped("australian")
+    n_iter, burn = 10, 2
+    tapes = [bo.make_tape(n_iter, xx.shape[1], 9000 + i) for i in range(5)]
+    st = bo.stack_tapes(tapes)
+    samples_o, infos = bo.rmhmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=6, step_size=0.5,
+                                       n_fixed=6, record=True)
+    out, _, info = pkg.rmhmc_batched(xx, t, 5, n_iter, burn, 6, 0.5, 6, draws=st)
+    assert rel_err(out[:, 1:], samples_o[:, 1:]) < RTOL
+    assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
+
+
+def test_chains_are_independent_of_batch_composition(pkg, golden):
+    """A chain's result does not depend on which other chains share its tile (bit-exact)."""
+    fx = golden("rmhmc_australian_shaped")
+    tr_all, s_all, _ = _run_tape_fixture(pkg, fx)
+    tr_two, s_two, _ = _run_tape_fixture(pkg, fx, n_chains=2)
+    assert np.array_equal(s_all[:2], s_two)
+    assert np.array_equal(tr_all["h_proposed"][:2], tr_two["h_proposed"])
+
+
+@pytest.mark.parametrize("name", ["hmc_australian_shaped", "hmc_pima_real"])
+def test_hmc_matches_reference(pkg, golden, name):
+    fx = golden(name)
+    xx, t = fx["xx"], fx["t"]
+    n_iter, burn_in = int(fx["n_iter"]), int(fx["burn_in"])
+    c = fx["z"].shape[1]
+    data = pkg.LogisticData(xx, t)
+    s = pkg.HMCSampler(data, c, int(fx["n_leapfrog"]), float(fx["step_size"]))
+    s.set_tape(fx["z"], fx["u_step"], fx["u_acc"])
+    s.set_samples(n_iter - burn_in, burn_in)
+    s.set_trace(n_iter)
+    s.run(n_iter)
+    tr = s.trace_numpy()
+    samples = s.samples.cpu().numpy()
+    data.close()
+    assert np.array_equal(tr["accepted"], fx["accepted"])
+    assert rel_err(tr["theta_end"], fx["theta_end"]) < RTOL
+    assert rel_err(tr["mom_end"], fx["mom_end"]) < RTOL
+    ratio = tr["h_current"] - tr["h_proposed"]
+    assert np.abs(ratio - fx["ratio"]).max() < 1e-8
+    assert rel_err(samples[:, 1:], fx["samples"][:, 1:]) < RTOL
+
+
+def test_ess_matches_reference(pkg, golden):
+    fx = golden("tools_ess")
+    x = fx["x"]
+    got = pkg.CalculateESS(x, x.shape[0] - 1)
+    assert got.shape == (x.shape[1], 1)
+    assert rel_err(got, fx["ess_full"]) < 1e-9
+    assert rel_err(pkg.CalculateESS(x[:599], 598), fx["ess_599"]) < 1e-9
+    assert rel_err(pkg.CalculateESS(x, 50), fx["ess_lag50"]) < 1e-9
+    # batched = column by column
+    many = np.stack([x[:2000], x[1000:3000], x[3000:5000]])
+    got = pkg.ess_batched(many).cpu().numpy()
+    for c in range(3):
+        assert rel_err(got[c], bo.ess(many[c], 1999)[:, 0]) < 1e-9
+
+
+def test_dropin_rmhmc_follows_global_numpy_rng(pkg, golden):
+    """RMHMC(XX, t, ...) consumes np.random like the reference: replay a golden chain through it."""
+    fx = golden("rmhmc_pima_real")
+    n_iter, burn_in, d = int(fx["n_iter"]), int(fx["burn_in"]), fx["xx"].shape[1]
+    # build the np.random call sequence the reference would make for chain 0 of the fixture
+    calls = []
+    for it in range(n_iter):
+        calls += [("randn2", fx["z"][it, 0]), ("rand", fx["u_step"][it, 0]), ("randn", fx["z_dir"][it, 0])]
+        if fx["used_uniform"][0, it]:
+            calls.append(("rand", fx["u_acc"][it, 0]))
+    state = {"i": 0}
+    real = (np.random.randn, np.random.rand, np.random.get_state, np.random.set_state)
+
+    def randn(*shape):
+        kind, val = calls[state["i"]]
+        state["i"] += 1
+        assert kind == ("randn2" if shape else "randn"), (kind, shape)
+        return val.reshape(shape).copy() if shape else float(val)
+
+    def rand(*shape):
+        if state["i"] >= len(calls) or calls[state["i"]][0] != "rand":
+            return 0.5                      # speculative draw that will be rolled back
+        kind, val = calls[state["i"]]
+        state["i"] += 1
+        return float(val)
+
+    np.random.randn, np.random.rand = randn, rand
+    np.random.get_state = lambda: ("fake", state["i"])
+    np.random.set_state = lambda s: state.update(i=s[1])
+    try:
+        w, secs = pkg.RMHMC(fx["xx"], fx["t"], n_iter, burn_in, int(fx["n_leapfrog"]), float(fx["step_size"]),
+                            int(fx["n_fixed"]), verbose=False)
+    finally:
+        np.random.randn, np.random.rand, np.random.get_state, np.random.set_state = real
+    assert w.shape == (n_iter - burn_in, d) and secs > 0
+    assert rel_err(w[1:], fx["samples"][0, 1:]) < RTOL
+
+
+def test_philox_chains_reach_the_reference_posterior(pkg, golden):
+    """Long-run agreement: pooled posterior mean/variance of many short Philox chains vs a
+    6000-iteration reference chain, within Monte-Carlo error."""
+    fx = golden("posterior_australian_shaped")
+    xx, t = pkg.datasets.shaped("australian")
+    c, n_iter, burn = 512, 140, 40
+    out, _, info = pkg.rmhmc_batched(xx, t, c, n_iter, burn, 6, 0.5, 6, seed=77)
+    s = out[:, 1:].reshape(-1, xx.shape[1])
+    ref_mean, ref_var, ref_ess = fx["mean"], fx["var"], fx["ess"]
+    se = np.sqrt(ref_var / ref_ess)                       # the reference chain's own MC error dominates
+    assert np.all(np.abs(s.mean(axis=0) - ref_mean) < 5 * se)
+    assert np.all(np.abs(s.var(axis=0) / ref_var - 1) < 0.15)
+    acc = info["accepted"].sum() / info["iters"].sum()
+    assert 0.8 < acc < 0.99
