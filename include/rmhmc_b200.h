@@ -122,7 +122,8 @@ int64_t rmhmc_launch_count(const rmhmc_handle* h);
 
 /* CUDA-event timing of the engine's kernels: when enabled, every launch of a given kernel class is
  * bracketed by events on the handle's stream.  kind: 0 metric build (position iterates),
- * 1 metric build (closing), 2 partials build, 3 per-chain stages.  Returns accumulated
+ * 1 metric build (closing), 2 partials build, 3 per-chain turn (end of one leapfrog step + start of
+ * the next), 4 per-chain position solve.  Returns accumulated
  * milliseconds and launch count since the last reset; synchronises. */
 int rmhmc_profile_enable(rmhmc_handle* h, int enable);
 int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches);

@@ -36,7 +36,7 @@ struct rmhmc_handle {
     double* x_pad = nullptr;
     uchar2* pair_tab = nullptr;
     uchar4* tri_tab = nullptr;
-    unsigned short* qidx = nullptr;
+    unsigned short* tidx = nullptr;
     unsigned char *pair_a = nullptr, *pair_b = nullptr;
     // chains
     int64_t n_chains = 0, c_pad = 0;
@@ -48,7 +48,7 @@ struct rmhmc_handle {
     bool configured = false, rng_set = false;
     int64_t launches = 0;
     bool profiling = false;
-    ProfSlot prof[4];
+    ProfSlot prof[5];
     mutable std::string err;
 };
 
@@ -132,35 +132,48 @@ __global__ void k_seam_finish(const double* __restrict__ theta, const double* __
     if (logjoint) logjoint[c] = loglik[c] + lp;
 }
 // per chain: factor packed G; optional L, inverse, logdet, trace(G^-1 dG_d) from packed T
+__host__ inline size_t seam_smem_bytes(int dim, int p3p, bool with_t) {
+    return ((size_t)3 * dim * (dim | 1) + 32) * 8 + 8 + (with_t ? (size_t)p3p * 8 : 0);
+}
+template <int DMAX, int NCH>
 __global__ void __launch_bounds__(32) k_seam_factor(EngineParams P, const double* __restrict__ gp,
                                                     const double* __restrict__ tp, double* L, double* Ginv,
                                                     double* logdet, double* trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = blockIdx.x, lane = threadIdx.x, D = P.dim, DS = P.ds;
-    ChainSmem sm = carve_chain_smem(smem_raw, P, tp != nullptr);
-    unpack_sym(gp + (size_t)c * P.p2p, sm.A, D, DS, lane);
-    double ld = chol_warp(sm.A, D, DS, lane);
-    if (logdet && lane == 0) logdet[c] = ld;
+    double* Lsm = reinterpret_cast<double*>(smem_raw);
+    double* Msm = Lsm + D * DS;
+    double* IG = Msm + D * DS;
+    double* outv = IG + D * DS;
+    double* Tsm = outv + 32;
+    if ((Tsm - Lsm) & 1) ++Tsm;
+    double dinv, ig[DMAX];
+    {
+        double lrow[DMAX];
+        load_packed_rows<DMAX>(gp + (size_t)c * P.p2p, lrow, D, lane);
+        double ld = chol_regs<DMAX>(lrow, D, lane, dinv);
+        store_rows<DMAX>(Lsm, lrow, D, DS, lane);
+        if (logdet && lane == 0) logdet[c] = ld;
+    }
     if (L)
-        for (int idx = lane; idx < D * D; idx += 32) {
-            int i = idx / D, j = idx % D;
-            L[(size_t)c * D * D + idx] = j <= i ? sm.A[i * DS + j] : 0.0;
-        }
+        for (int idx = lane; idx < D * D; idx += 32) L[(size_t)c * D * D + idx] = Lsm[(idx / D) * DS + (idx % D)];
     if (Ginv || trace) {
-        chol_inverse_warp(sm.A, sm.B, D, DS, lane);
+        chol_inverse_regs<DMAX>(Lsm, Msm, dinv, ig, D, DS, lane);
+#pragma unroll
+        for (int b = 0; b < DMAX; ++b)
+            if (b < D && lane < D) IG[lane * DS + b] = ig[b];
+        __syncwarp();
         if (Ginv)
-            for (int idx = lane; idx < D * D; idx += 32) Ginv[(size_t)c * D * D + idx] = sm.B[(idx / D) * DS + (idx % D)];
+            for (int idx = lane; idx < D * D; idx += 32) Ginv[(size_t)c * D * D + idx] = IG[(idx / D) * DS + (idx % D)];
     }
     if (trace) {
-        load_t_smem(sm.T, tp + (size_t)c * P.p3p, P.p3p, lane);
-        for (int pr = lane; pr < P.p2; pr += 32) {
-            int pa = P.pair_a[pr], pb = P.pair_b[pr];
-            double w = sm.B[pa * DS + pb];
-            sm.Q[pr] = pa == pb ? w : 2.0 * w;
-        }
+        PairRegs<NCH> pr;
+        load_pairs<NCH>(P, pr, lane);
+        const double2* ts = reinterpret_cast<const double2*>(tp + (size_t)c * P.p3p);
+        for (int i = lane; i < P.p3p / 2; i += 32) reinterpret_cast<double2*>(Tsm)[i] = ts[i];
         __syncwarp();
-        double tr = tensor_contract(sm.T, sm.Q, P.qidx, P.p2, lane);
-        if (lane < D) trace[(size_t)c * D + lane] = tr;
+        trace_terms<NCH>(P, pr, Tsm, IG, outv, 0, 1, lane);
+        if (lane < D) trace[(size_t)c * D + lane] = outv[lane];
     }
 }
 
@@ -303,9 +316,9 @@ void fill_engine_params(rmhmc_handle* h) {
     EngineParams& P = h->P;
     P.n_chains = (int)h->n_chains; P.dim = h->dim; P.ds = h->dim | 1;
     P.p2 = h->p2; P.p2p = h->p2p; P.p3 = h->p3; P.p3p = h->p3p; P.n_rows_pad = h->n_rows_pad;
-    P.alpha = h->alpha; P.qidx = h->qidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
+    P.alpha = h->alpha; P.tidx = h->tidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
     size_t C = (size_t)h->n_chains;
-    P.slot_theta = C * h->dim; P.slot_scalar = C; P.slot_gp = C * h->p2p;
+    P.slot_theta = C * h->dim; P.slot_scalar = C;
     P.slot_invg = C * h->dim * h->dim; P.slot_t = C * h->p3p;
 }
 
@@ -322,7 +335,7 @@ int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
     rc |= dev_alloc(h, &S.logjoint, 2 * c, tr);
     rc |= dev_alloc(h, &S.grad, 2 * c * D, tr);
     if (!hmc) {
-        rc |= dev_alloc(h, &S.gp, 2 * c * h->p2p, tr);
+        rc |= dev_alloc(h, &S.lfac, 2 * c * D * D, tr);
         rc |= dev_alloc(h, &S.invg, 2 * c * D * D, tr);
         rc |= dev_alloc(h, &S.logdet, 2 * c, tr);
         rc |= dev_alloc(h, &S.tpack, 2 * c * h->p3p, tr);
@@ -350,47 +363,112 @@ int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
     return RMHMC_OK;
 }
 
-size_t chain_smem(rmhmc_handle* h, bool with_t) { return chain_smem_bytes(h->dim, h->p2, h->p3p, with_t); }
+// per-chain kernel variants: DMAX = 16 / 32 (unroll bound of the register linear algebra) and
+// NCH = ceil(P2 / 32) rounded up to 4 / 11 / 17 (packed pairs per lane in the tensor contractions)
+int dmax_variant(const rmhmc_handle* h) { return h->dim <= 16 ? 0 : 1; }
+int nch_variant(const rmhmc_handle* h) { return h->p2 <= 128 ? 0 : (h->p2 <= 352 ? 1 : 2); }
 
 int set_chain_smem_attrs(rmhmc_handle* h) {
-    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem(h, true)));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem(h, true)));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem(h, false)));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem(h, true)));
+    int turn = (int)turn_smem_bytes(h->dim, h->p3p), seam = (int)seam_smem_bytes(h->dim, h->p3p, true);
+    int fac = (int)factor_smem_bytes(h->dim);
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<32, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<32, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_factor<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fac));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_factor<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, fac));
     return RMHMC_OK;
 }
 
-// one RMHMC round: rmhmc.py:96-163 for every chain (+ trajectory start/end handling)
-int rmhmc_round(rmhmc_handle* h) {
-    const int64_t C = h->n_chains;
-    ChainArrays& S = h->S;
+int launch_turn(rmhmc_handle* h, int do_back, int do_front, int init) {
+    const unsigned C = (unsigned)h->n_chains;
+    size_t smem = turn_smem_bytes(h->dim, h->p3p);
     {
         Bracket b(h, 3);
-        k_chain_front<<<(unsigned)C, 32, chain_smem(h, true), h->stream>>>(h->P, S);
+        switch (nch_variant(h)) {
+            case 0: k_chain_turn<4><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init); break;
+            case 1: k_chain_turn<11><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init); break;
+            default: k_chain_turn<17><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init);
+        }
     }
     h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+int launch_factor(rmhmc_handle* h, int init) {
+    const unsigned C = (unsigned)h->n_chains;
+    size_t smem = factor_smem_bytes(h->dim);
+    {
+        Bracket b(h, 4);
+        if (dmax_variant(h) == 0) k_chain_factor<16><<<C, 32, smem, h->stream>>>(h->P, h->S, init);
+        else k_chain_factor<32><<<C, 32, smem, h->stream>>>(h->P, h->S, init);
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+int launch_solve(rmhmc_handle* h, int is_last) {
+    const unsigned C = (unsigned)h->n_chains;
+    size_t smem = (size_t)h->dim * (h->dim | 1) * 8;
+    {
+        Bracket b(h, 4);
+        if (dmax_variant(h) == 0) k_chain_solve<16><<<C, 32, smem, h->stream>>>(h->P, h->S, is_last);
+        else k_chain_solve<32><<<C, 32, smem, h->stream>>>(h->P, h->S, is_last);
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+int launch_seam_factor(rmhmc_handle* h, const EngineParams& P, int64_t C, const double* gp, const double* tp, double* L,
+                       double* Ginv, double* logdet, double* trace) {
+    size_t smem = seam_smem_bytes(h->dim, h->p3p, tp != nullptr);
+    if (h->dim <= 16 && h->p2 <= 128)
+        k_seam_factor<16, 4><<<(unsigned)C, 32, smem, h->stream>>>(P, gp, tp, L, Ginv, logdet, trace);
+    else if (h->p2 <= 352)
+        k_seam_factor<32, 11><<<(unsigned)C, 32, smem, h->stream>>>(P, gp, tp, L, Ginv, logdet, trace);
+    else
+        k_seam_factor<32, 17><<<(unsigned)C, 32, smem, h->stream>>>(P, gp, tp, L, Ginv, logdet, trace);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+// The builds of one RMHMC round (rmhmc.py:113-156 for every chain): F-1 position iterates, each a
+// metric build + per-chain solve, then the closing metric build, the partials build and the
+// per-chain factorisation of the new metric.  The
+// per-chain halves around them (k_chain_turn) are launched by the callers.
+int rmhmc_round_builds(rmhmc_handle* h) {
+    const int64_t C = h->n_chains;
+    ChainArrays& S = h->S;
     for (int fi = 2; fi <= h->P.n_fixed; ++fi) {
         MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, nullptr, nullptr, nullptr);
         int rc = launch_metric<0>(h, a);
         if (rc) return rc;
-        {
-            Bracket b(h, 3);
-            k_chain_solve<<<(unsigned)C, 32, chain_smem(h, false), h->stream>>>(h->P, S, fi == h->P.n_fixed ? 1 : 0);
-        }
-        h->launches += 1;
+        rc = launch_solve(h, fi == h->P.n_fixed ? 1 : 0);
+        if (rc) return rc;
     }
     MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, S.grad_tmp, S.loglik_tmp, S.cbuf);
     int rc = launch_metric<1>(h, a);
     if (rc) return rc;
     rc = launch_tbuild(h, C, S.cbuf, S.tpack, S.cur, 1, h->P.slot_t);
     if (rc) return rc;
-    {
-        Bracket b(h, 3);
-        k_chain_back<<<(unsigned)C, 32, chain_smem(h, true), h->stream>>>(h->P, S, 0);
+    return launch_factor(h, 0);
+}
+
+// n_rounds rounds: front | builds | back+front | builds | ... | back
+int rmhmc_rounds(rmhmc_handle* h, int64_t n_rounds) {
+    if (n_rounds <= 0) return RMHMC_OK;
+    int rc = launch_turn(h, 0, 1, 0);
+    for (int64_t r = 0; r < n_rounds && !rc; ++r) {
+        rc = rmhmc_round_builds(h);
+        if (!rc) rc = launch_turn(h, 1, r + 1 < n_rounds ? 1 : 0, 0);
     }
-    h->launches += 1;
-    CUDA_TRY(h, cudaGetLastError());
-    return RMHMC_OK;
+    return rc;
 }
 
 int hmc_round(rmhmc_handle* h) {
@@ -426,8 +504,13 @@ int run_until(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done, bool hmc) 
         if (rem <= 0) break;
         // every unfinished iteration needs at least one round; keep the host a bounded distance ahead
         int64_t chunk = rem < 512 ? rem : 512;
-        for (int64_t r = 0; r < chunk; ++r) {
-            int rc = hmc ? hmc_round(h) : rmhmc_round(h);
+        if (hmc) {
+            for (int64_t r = 0; r < chunk; ++r) {
+                int rc = hmc_round(h);
+                if (rc) return rc;
+            }
+        } else {
+            int rc = rmhmc_rounds(h, chunk);
             if (rc) return rc;
         }
         total += chunk;
@@ -495,9 +578,9 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
         for (int j = i; j < dim; ++j)
             for (int k = j; k < dim; ++k)
                 tri_tab[triple_index(i, j, k, dim)] = make_uchar4((unsigned char)i, (unsigned char)j, (unsigned char)k, 0);
-    std::vector<unsigned short> qidx((size_t)h->p2 * 32, 0);
-    for (int pr = 0; pr < h->p2; ++pr)
-        for (int d = 0; d < dim; ++d) qidx[(size_t)pr * 32 + d] = (unsigned short)triple_index_any(pa[pr], pb[pr], d, dim);
+    std::vector<unsigned short> tidx((size_t)dim * h->p2, 0);
+    for (int d = 0; d < dim; ++d)
+        for (int pr = 0; pr < h->p2; ++pr) tidx[(size_t)d * h->p2 + pr] = (unsigned short)triple_index_any(pa[pr], pb[pr], d, dim);
     if (h->p3p > 65535) {
         h->err = "packed triple index exceeds 16 bits";
         return bail(RMHMC_E_UNSUPPORTED);
@@ -514,13 +597,13 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
     CREATE_TRY(cudaMalloc((void**)&h->x_pad, (size_t)h->n_rows_pad * h->xs * 8));
     CREATE_TRY(cudaMalloc((void**)&h->pair_tab, pair_tab.size() * sizeof(uchar2)));
     CREATE_TRY(cudaMalloc((void**)&h->tri_tab, tri_tab.size() * sizeof(uchar4)));
-    CREATE_TRY(cudaMalloc((void**)&h->qidx, qidx.size() * sizeof(unsigned short)));
+    CREATE_TRY(cudaMalloc((void**)&h->tidx, tidx.size() * sizeof(unsigned short)));
     CREATE_TRY(cudaMalloc((void**)&h->pair_a, pa.size()));
     CREATE_TRY(cudaMalloc((void**)&h->pair_b, pb.size()));
     CREATE_TRY(cudaMalloc((void**)&h->d_remaining, sizeof(long long)));
     CREATE_TRY(cudaMemcpy(h->pair_tab, pair_tab.data(), pair_tab.size() * sizeof(uchar2), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(h->tri_tab, tri_tab.data(), tri_tab.size() * sizeof(uchar4), cudaMemcpyHostToDevice));
-    CREATE_TRY(cudaMemcpy(h->qidx, qidx.data(), qidx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(h->tidx, tidx.data(), tidx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(h->pair_a, pa.data(), pa.size(), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(h->pair_b, pb.data(), pb.size(), cudaMemcpyHostToDevice));
     int64_t total = (int64_t)h->n_rows_pad * h->xs;
@@ -539,7 +622,7 @@ void rmhmc_destroy(rmhmc_handle* h) {
     cudaSetDevice(h->device);
     drain_profile(h);
     free_chains(h);
-    cudaFree(h->x_pad); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->qidx);
+    cudaFree(h->x_pad); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx);
     cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
     delete h;
 }
@@ -595,9 +678,9 @@ int rmhmc_metric_partials(rmhmc_handle* h, int64_t C, const double* theta, doubl
         if (trace) {
             EngineParams P = h->P;
             P.n_chains = (int)C; P.dim = h->dim; P.ds = h->dim | 1; P.p2 = h->p2; P.p2p = h->p2p; P.p3 = h->p3;
-            P.p3p = h->p3p; P.qidx = h->qidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
+            P.p3p = h->p3p; P.tidx = h->tidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
             rc = set_chain_smem_attrs(h);
-            if (!rc) k_seam_factor<<<(unsigned)C, 32, chain_smem(h, true), h->stream>>>(P, gp, tp, nullptr, nullptr, nullptr, trace);
+            if (!rc) rc = launch_seam_factor(h, P, C, gp, tp, nullptr, nullptr, nullptr, trace);
         }
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e == cudaSuccess) e = cudaGetLastError();
@@ -617,9 +700,9 @@ int rmhmc_chol_logdet(rmhmc_handle* h, int64_t C, const double* G, double* L, do
         k_pack_g<<<blocks_for(C * h->p2p, 256), 256, 0, h->stream>>>(G, gp, C, h->dim, h->p2, h->p2p, h->pair_a, h->pair_b);
         EngineParams P = h->P;
         P.n_chains = (int)C; P.dim = h->dim; P.ds = h->dim | 1; P.p2 = h->p2; P.p2p = h->p2p; P.p3 = h->p3;
-        P.p3p = h->p3p; P.qidx = h->qidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
+        P.p3p = h->p3p; P.tidx = h->tidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
         rc = set_chain_smem_attrs(h);
-        if (!rc) k_seam_factor<<<(unsigned)C, 32, chain_smem(h, false), h->stream>>>(P, gp, nullptr, L, Ginv, logdet, nullptr);
+        if (!rc) rc = launch_seam_factor(h, P, C, gp, nullptr, L, Ginv, logdet, nullptr);
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) { h->err = std::string("rmhmc_chol_logdet: ") + cudaGetErrorString(e); rc = RMHMC_E_CUDA; }
@@ -657,7 +740,10 @@ static int chains_init_common(rmhmc_handle* h, int64_t C, const double* theta0, 
         if (rc) return rc;
         rc = launch_tbuild(h, C, S.cbuf, S.tpack, S.cur, 0, h->P.slot_t);
         if (rc) return rc;
-        k_chain_back<<<(unsigned)C, 32, chain_smem(h, true), h->stream>>>(h->P, S, 1);
+        rc = launch_factor(h, 1);
+        if (rc) return rc;
+        rc = launch_turn(h, 1, 0, 1);
+        if (rc) return rc;
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -729,11 +815,7 @@ int rmhmc_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop) {
     if (!h->configured || !h->rng_set) return fail(h, RMHMC_E_STATE, "rmhmc_advance: configure and set a tape / philox seed first");
     CUDA_TRY(h, cudaSetDevice(h->device));
     h->P.it_stop = it_stop;
-    for (int64_t r = 0; r < n_rounds; ++r) {
-        int rc = rmhmc_round(h);
-        if (rc) return rc;
-    }
-    return RMHMC_OK;
+    return rmhmc_rounds(h, n_rounds);
 }
 
 int rmhmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done) {
@@ -776,7 +858,7 @@ int rmhmc_profile_enable(rmhmc_handle* h, int enable) {
     return RMHMC_OK;
 }
 int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches) {
-    if (!h || kind < 0 || kind > 3) return RMHMC_E_INVALID;
+    if (!h || kind < 0 || kind > 4) return RMHMC_E_INVALID;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     drain_profile(h);
     if (ms) *ms = h->prof[kind].ms;

@@ -41,18 +41,13 @@ struct EngineParams {
     double* tr_hprop;                  // [C][TI]
     int* tr_flags;                     // [C][TI] bit0 accepted, bit1 uniform consumed, bits 8.. nsteps, bit 4 dir>0
     long long tr_iters;                // TI
-    const unsigned short* qidx;        // [P2][32]: packed-triple index of (pair, lane d)
+    const unsigned short* tidx;        // [D][P2]: packed-triple index of (d, pair)
     const unsigned char* pair_a;       // [P2]
     const unsigned char* pair_b;       // [P2]
-    size_t slot_theta, slot_scalar, slot_gp, slot_invg, slot_t;   // doubles between slot 0 and slot 1
+    size_t slot_theta, slot_scalar, slot_invg, slot_t;   // doubles between slot 0 and slot 1
 };
 
-__host__ inline size_t chain_smem_bytes(int dim, int p2, int p3p, bool with_t) {
-    int ds = dim | 1;
-    size_t b = (size_t)2 * dim * ds * 8 + (size_t)p2 * 8 + 4 * 32 * 8 + 8;   // +8: T is 16-byte aligned
-    if (with_t) b += (size_t)p3p * 8;
-    return b;
-}
+__host__ inline size_t factor_smem_bytes(int dim) { return (size_t)2 * dim * (dim | 1) * 8; }
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- Philox4x32-10
@@ -83,135 +78,196 @@ __device__ __forceinline__ double philox_normal(const EngineParams& P, long long
 }
 
 // ---------------------------------------------------------------- warp linear algebra (D <= 32)
-// dense symmetric matrix from the packed upper triangle
-__device__ __forceinline__ void unpack_sym(const double* __restrict__ gp, double* A, int D, int DS, int lane) {
-    for (int idx = lane; idx < D * D; idx += 32) {
-        int i = idx / D, j = idx - i * D;
-        int lo = i < j ? i : j, hi = i < j ? j : i;
-        A[i * DS + j] = gp[pair_index(lo, hi, D)];
+// One lane owns one row.  Matrices live in registers (statically indexed, loops unrolled to DMAX
+// with warp-uniform guards on the runtime D) and are mirrored in shared memory where another lane's
+// column is needed.  Cross-lane traffic is warp shuffles; no __syncthreads anywhere.
+constexpr unsigned kFull = 0xffffffffu;
+
+// row[j] = G[lane][j], j <= lane, from the packed upper triangle (coalesced: consecutive lanes read
+// consecutive packed entries for a fixed j)
+template <int DMAX>
+__device__ __forceinline__ void load_packed_rows(const double* __restrict__ gp, double (&row)[DMAX], int D, int lane) {
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+        row[j] = (j < D && lane >= j && lane < D) ? gp[j * D - j * (j - 1) / 2 + (lane - j)] : 0.0;
+}
+
+// In-register lower Cholesky factor (row[j] = L[lane][j], j <= lane).  Returns
+// sum_k log L_kk = 0.5 log|G| (rmhmc.py:171,175); dinv = 1 / L[lane][lane].  A non-PD matrix yields
+// NaNs, which the accept test then rejects (the reference would raise LinAlgError; it cannot happen
+// since G >= I/alpha).
+template <int DMAX>
+__device__ __forceinline__ double chol_regs(double (&row)[DMAX], int D, int lane, double& dinv) {
+    double diag = 1.0;
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) {
+        if (k < D) {
+            double lkk = sqrt(__shfl_sync(kFull, row[k], k));
+            double inv = 1.0 / lkk;
+            double lik = (lane == k) ? lkk : row[k] * inv;
+            if (lane == k) diag = lkk;
+            row[k] = lik;
+#pragma unroll
+            for (int j = k + 1; j < DMAX; ++j) {
+                if (j < D) {
+                    double ljk = __shfl_sync(kFull, lik, j);
+                    if (lane >= j) row[j] = fma(-lik, ljk, row[j]);
+                }
+            }
+        }
     }
+    dinv = 1.0 / diag;
+    return warp_sum(lane < D ? log(diag) : 0.0);
+}
+
+template <int DMAX>
+__device__ __forceinline__ void store_rows(double* Lsm, const double (&row)[DMAX], int D, int DS, int lane) {
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+        if (j < D && lane < D) Lsm[lane * DS + j] = (j <= lane) ? row[j] : 0.0;
     __syncwarp();
 }
 
-// In-place lower Cholesky factor (A = L L^T; strict upper part left untouched).  Returns
-// sum_k log L_kk = 0.5 log|A| (rmhmc.py:171,175).  A non-PD matrix yields NaNs, which the accept
-// test then rejects (the reference would raise LinAlgError; it never happens since G >= I/alpha).
-__device__ __forceinline__ double chol_warp(double* A, int D, int DS, int lane) {
-    for (int k = 0; k < D; ++k) {
-        double lkk = sqrt(A[k * DS + k]);
-        double lik = 0.0;
-        bool below = lane > k && lane < D;
-        if (below) lik = A[lane * DS + k] / lkk;
-        __syncwarp();
-        if (lane == k) A[k * DS + k] = lkk;
-        if (below) A[lane * DS + k] = lik;
-        __syncwarp();
-        if (below)
-            for (int j = k + 1; j <= lane; ++j) A[lane * DS + j] -= lik * A[j * DS + k];
-        __syncwarp();
+// Solve L L^T x = b; lane i holds b_i on entry and x_i on exit (rmhmc.py:113,121).
+template <int DMAX>
+__device__ __forceinline__ double chol_solve_regs(const double (&row)[DMAX], const double* Lsm, double dinv, int D,
+                                                  int DS, int lane, double b) {
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) {                    // forward: L y = b
+        if (k < D) {
+            double yk = __shfl_sync(kFull, b, k) * __shfl_sync(kFull, dinv, k);
+            if (lane == k) b = yk;
+            else if (lane > k) b = fma(-row[k], yk, b);
+        }
     }
-    double l = lane < D ? log(A[lane * DS + lane]) : 0.0;
-    return warp_sum(l);
-}
-
-// Solve L L^T x = b; lane i holds b_i on entry and x_i on exit.
-__device__ __forceinline__ double chol_solve_warp(const double* L, int D, int DS, int lane, double b) {
-    double dinv = lane < D ? 1.0 / L[lane * DS + lane] : 0.0;
-    for (int k = 0; k < D; ++k) {                       // forward: L y = b
-        double yk = __shfl_sync(0xffffffffu, b, k) * __shfl_sync(0xffffffffu, dinv, k);
-        if (lane == k) b = yk;
-        if (lane > k && lane < D) b -= L[lane * DS + k] * yk;
-    }
-    for (int k = D - 1; k >= 0; --k) {                  // backward: L^T x = y
-        double xk = __shfl_sync(0xffffffffu, b, k) * __shfl_sync(0xffffffffu, dinv, k);
-        if (lane == k) b = xk;
-        if (lane < k) b -= L[k * DS + lane] * xk;
+#pragma unroll
+    for (int k = DMAX - 1; k >= 0; --k) {               // backward: L^T x = y
+        if (k < D) {
+            double xk = __shfl_sync(kFull, b, k) * __shfl_sync(kFull, dinv, k);
+            double lkj = lane < k ? Lsm[k * DS + lane] : 0.0;
+            if (lane == k) b = xk;
+            else if (lane < k) b = fma(-lkj, xk, b);
+        }
     }
     return b;
 }
 
-// B = (L L^T)^-1, one right-hand side (column) per lane.
-__device__ __forceinline__ void chol_inverse_warp(const double* L, double* B, int D, int DS, int lane) {
-    const int j = lane < D ? lane : 0;      // idle lanes shadow column 0 without storing
-    const bool live = lane < D;
-    for (int i = 0; i < D; ++i) {           // forward sweep: L Y = I
-        double s = (i == j) ? 1.0 : 0.0;
-        for (int k = 0; k < i; ++k) s -= L[i * DS + k] * B[k * DS + j];
-        s /= L[i * DS + i];
-        __syncwarp();
-        if (live) B[i * DS + j] = s;
-        __syncwarp();
+// ig[b] = (L L^T)^-1 [lane][b].  Lane j first builds column j of M = L^-1 (Msm mirrors it), then
+// G^-1 = M^T M.
+template <int DMAX>
+__device__ __forceinline__ void chol_inverse_regs(const double* Lsm, double* Msm, double dinv, double (&ig)[DMAX],
+                                                  int D, int DS, int lane) {
+    double m[DMAX];
+#pragma unroll
+    for (int i = 0; i < DMAX; ++i) {
+        m[i] = 0.0;
+        if (i < D) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) {
+                if (k & 1) s1 = fma(Lsm[i * DS + k], m[k], s1);
+                else s0 = fma(Lsm[i * DS + k], m[k], s0);
+            }
+            double di = __shfl_sync(kFull, dinv, i);
+            m[i] = (i == lane) ? di : (i > lane ? -(s0 + s1) * di : 0.0);
+        }
     }
-    for (int i = D - 1; i >= 0; --i) {      // backward sweep: L^T X = Y
-        double s = B[i * DS + j];
-        for (int k = i + 1; k < D; ++k) s -= L[k * DS + i] * B[k * DS + j];
-        s /= L[i * DS + i];
-        __syncwarp();
-        if (live) B[i * DS + j] = s;
-        __syncwarp();
-    }
-}
-
-// y_i = sum_j M[i][j] x_j, x given per lane (staged through xv in smem)
-__device__ __forceinline__ double matvec_warp(const double* M, double* xv, int D, int DS, int lane, double x) {
+#pragma unroll
+    for (int i = 0; i < DMAX; ++i)
+        if (i < D && lane < D) Msm[i * DS + lane] = m[i];
     __syncwarp();
-    if (lane < D) xv[lane] = x;
-    __syncwarp();
-    double y = 0.0;
-    if (lane < D)
-        for (int j = 0; j < D; ++j) y += M[lane * DS + j] * xv[j];
-    return y;
-}
-
-// out_d = sum_{a<=b} Q[(a,b)] T[d,a,b] for lane d, T packed in smem, Q packed weights (off-diagonal
-// pairs already carry their factor 2).
-__device__ __forceinline__ double tensor_contract(const double* Tsm, const double* Q, const unsigned short* __restrict__ qidx,
-                                                  int P2, int lane) {
-    double s0 = 0.0, s1 = 0.0;
-    int pr = 0;
-    for (; pr + 1 < P2; pr += 2) {
-        s0 += Q[pr] * Tsm[__ldg(qidx + pr * 32 + lane)];
-        s1 += Q[pr + 1] * Tsm[__ldg(qidx + (pr + 1) * 32 + lane)];
-    }
-    if (pr < P2) s0 += Q[pr] * Tsm[__ldg(qidx + pr * 32 + lane)];
-    return s0 + s1;
-}
-
-// LastTerm_d = 0.5 u^T dG_d u (rmhmc.py:105-107 with u = G^-1 p; G^-1 symmetric)
-__device__ __forceinline__ double last_term(const EngineParams& P, const double* Tsm, double* Q, double* uv,
-                                            int lane, double u) {
-    __syncwarp();
-    if (lane < P.dim) uv[lane] = u;
-    __syncwarp();
-    for (int pr = lane; pr < P.p2; pr += 32) {
-        int pa = P.pair_a[pr], pb = P.pair_b[pr];
-        double w = uv[pa] * uv[pb];
-        Q[pr] = pa == pb ? w : 2.0 * w;
+#pragma unroll
+    for (int b = 0; b < DMAX; ++b) {
+        double s0 = 0.0, s1 = 0.0;
+        if (b < D) {
+#pragma unroll
+            for (int k = b; k < DMAX; ++k) {
+                if (k < D) {
+                    if (k & 1) s1 = fma(m[k], Msm[k * DS + b], s1);
+                    else s0 = fma(m[k], Msm[k * DS + b], s0);
+                }
+            }
+        }
+        ig[b] = s0 + s1;
     }
     __syncwarp();
-    return 0.5 * tensor_contract(Tsm, Q, P.qidx, P.p2, lane);
 }
 
-struct ChainSmem {
-    double *A, *B, *Q, *v0, *v1, *v2, *v3, *T;
+template <int DMAX>
+__device__ __forceinline__ double matvec_regs(const double (&ig)[DMAX], int D, double x) {
+    double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+    for (int b = 0; b < DMAX; ++b) {
+        if (b < D) {
+            double xb = __shfl_sync(kFull, x, b);
+            if (b & 1) y1 = fma(ig[b], xb, y1);
+            else y0 = fma(ig[b], xb, y0);
+        }
+    }
+    return y0 + y1;
+}
+
+// (pair a, pair b, weight) of the packed pairs this lane owns in the tensor contractions
+template <int NCH>
+struct PairRegs {
+    int pa[NCH], pb[NCH];
+    double w[NCH];
 };
-__device__ __forceinline__ ChainSmem carve_chain_smem(unsigned char* raw, const EngineParams& P, bool with_t) {
-    ChainSmem s;
-    double* p = reinterpret_cast<double*>(raw);
-    s.A = p; p += P.dim * P.ds;
-    s.B = p; p += P.dim * P.ds;
-    s.Q = p; p += P.p2;
-    s.v0 = p; p += 32; s.v1 = p; p += 32; s.v2 = p; p += 32; s.v3 = p; p += 32;
-    if ((p - reinterpret_cast<double*>(raw)) & 1) ++p;      // double2 loads into T
-    s.T = with_t ? p : nullptr;
-    return s;
+template <int NCH>
+__device__ __forceinline__ void load_pairs(const EngineParams& P, PairRegs<NCH>& pr, int lane) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        int p = lane + 32 * ch;
+        bool ok = p < P.p2;
+        pr.pa[ch] = ok ? P.pair_a[p] : 0;
+        pr.pb[ch] = ok ? P.pair_b[p] : 0;
+        pr.w[ch] = ok ? (pr.pa[ch] == pr.pb[ch] ? 1.0 : 2.0) : 0.0;
+    }
 }
 
-__device__ __forceinline__ void load_t_smem(double* Tsm, const double* __restrict__ src, int p3p, int lane) {
-    const double2* s2 = reinterpret_cast<const double2*>(src);
-    double2* d2 = reinterpret_cast<double2*>(Tsm);
-    for (int i = lane; i < p3p / 2; i += 32) d2[i] = s2[i];
-    __syncwarp();
+// out[d] = sum over packed pairs p of q[p] * T[d, a_p, b_p], for every d.  Lanes run over pairs (so a
+// warp's reads of the packed T are mostly consecutive), the CTA's warps split the d range, and each
+// per-d sum is reduced with a fixed xor butterfly.  q[ch] belongs to pair lane + 32 ch and already
+// carries the factor 2 of off-diagonal pairs.  Ends with a CTA barrier.
+template <int NCH>
+__device__ __forceinline__ void tensor_contract(const double* Tsm, const double (&q)[NCH],
+                                                const unsigned short* __restrict__ tidx, double* out, int D, int P2,
+                                                int warp, int n_warps, int lane) {
+    for (int d = warp; d < D; d += n_warps) {
+        const unsigned short* row = tidx + d * P2 + lane;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            if (lane + 32 * ch < P2) {
+                double t = Tsm[__ldg(row + 32 * ch)];
+                if (ch & 1) a1 = fma(q[ch], t, a1);
+                else a0 = fma(q[ch], t, a0);
+            }
+        }
+        double acc = warp_sum(a0 + a1);
+        if (lane == 0) out[d] = acc;
+    }
+    __syncthreads();
+}
+
+// out_d = u^T dG_d u (caller halves it: LastTerm, rmhmc.py:105-107 with u = G^-1 p; G^-1 symmetric)
+template <int NCH>
+__device__ __forceinline__ void quad_terms(const EngineParams& P, const PairRegs<NCH>& pr, const double* Tsm,
+                                           const double* u, double* out, int warp, int n_warps, int lane) {
+    double q[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) q[ch] = pr.w[ch] * u[pr.pa[ch]] * u[pr.pb[ch]];
+    tensor_contract<NCH>(Tsm, q, P.tidx, out, P.dim, P.p2, warp, n_warps, lane);
+}
+
+// out_d = tr(G^-1 dG_d) = <G^-1, dG_d> (rmhmc.py:76-77,155-156)
+template <int NCH>
+__device__ __forceinline__ void trace_terms(const EngineParams& P, const PairRegs<NCH>& pr, const double* Tsm,
+                                            const double* IGsm, double* out, int warp, int n_warps, int lane) {
+    double q[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) q[ch] = pr.w[ch] * IGsm[pr.pa[ch] * P.ds + pr.pb[ch]];
+    tensor_contract<NCH>(Tsm, q, P.tidx, out, P.dim, P.p2, warp, n_warps, lane);
 }
 
 __device__ __forceinline__ double clamp_position(double w, int lane, int dim, int* counter) {
@@ -225,238 +281,319 @@ __device__ __forceinline__ double clamp_position(double w, int lane, int dim, in
     return w;
 }
 
-// ---------------------------------------------------------------- round stage 1
-// [new iteration: momentum draw, H_current] + implicit momentum half-step + first position iterate
-__global__ void __launch_bounds__(32) k_chain_front(EngineParams P, ChainArrays S) {
+// ---------------------------------------------------------------- factor kernel (one warp per chain)
+// Cholesky factor, inverse and log-det of the metric built at theta_w (rmhmc.py:138,171 / :58-60).
+// Writes L, G^-1 and 0.5 log|G| of the proposal slot (of slot `cur` when init != 0).
+template <int DMAX>
+__global__ void __launch_bounds__(32) k_chain_factor(EngineParams P, ChainArrays S, int init) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = blockIdx.x, lane = threadIdx.x, D = P.dim, DS = P.ds;
     if (c >= P.n_chains) return;
-    long long it = S.iter[c];
-    if (it >= P.it_stop) return;
-    ChainSmem sm = carve_chain_smem(smem_raw, P, true);
-    const int cur = S.cur[c];
-    int step = S.step[c];
-    const bool live = lane < D;
-    double p = 0.0;
-    int sgn, nsteps;
+    if (!init && (S.iter[c] >= P.it_stop || S.nsteps[c] <= 0)) return;
+    double* Lsm = reinterpret_cast<double*>(smem_raw);
+    double* Msm = Lsm + D * DS;
+    const int out = init ? S.cur[c] : 1 - S.cur[c];
+    double dinv, ig[DMAX];
+    {
+        double lrow[DMAX];
+        load_packed_rows<DMAX>(S.g_tmp + (size_t)c * P.p2p, lrow, D, lane);
+        double logdet = chol_regs<DMAX>(lrow, D, lane, dinv);
+        store_rows<DMAX>(Lsm, lrow, D, DS, lane);
+        if (lane == 0) S.logdet[out * P.slot_scalar + c] = logdet;
+    }
+    double* ld = S.lfac + out * P.slot_invg + (size_t)c * D * D;
+    for (int idx = lane; idx < D * D; idx += 32) ld[idx] = Lsm[(idx / D) * DS + (idx % D)];
+    chol_inverse_regs<DMAX>(Lsm, Msm, dinv, ig, D, DS, lane);
+    double* igd = S.invg + out * P.slot_invg + (size_t)c * D * D;
+#pragma unroll
+    for (int b = 0; b < DMAX; ++b)
+        if (b < D && lane < D) igd[lane * D + b] = ig[b];
+}
 
+// ---------------------------------------------------------------- the per-round chain kernel
+// One CTA of kTurnThreads threads per chain.
+// do_back : finish the leapfrog step whose closing builds (metric at theta_w -> grad_tmp/loglik_tmp,
+//           partials -> T[out], k_chain_factor -> L/G^-1/log-det[out]) have just run: traces, gradient,
+//           log joint, explicit momentum half-step (R12-R14); if the trajectory is complete:
+//           Hamiltonian, accept/reject, sample store (R15-R18).  init != 0: only fill slot `cur`.
+// do_front: start the next leapfrog step: [new iteration: momentum draw, H_current (R2-R6)],
+//           implicit momentum half-step (R7-R8), u0 and the first position iterate (R9-R10).
+// Both halves run back to back in the same CTA so that T and G^-1 of the step's end point -- which
+// is the next step's start point unless the proposal was rejected -- stay in shared memory.
+constexpr int kTurnThreads = 128;
+
+__host__ inline size_t turn_smem_bytes(int dim, int p3p) {
+    return ((size_t)dim * (dim | 1) + 8 * 32) * 8 + 8 + (size_t)p3p * 8;
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(kTurnThreads) k_chain_turn(EngineParams P, ChainArrays S, int do_back, int do_front,
+                                                             int init) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = kTurnThreads / 32;
+    const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, D = P.dim, DS = P.ds;
+    if (c >= P.n_chains) return;
+    long long it = S.iter[c];
+    if (!init && it >= P.it_stop) return;
+    double* IG = reinterpret_cast<double*>(smem_raw);
+    double* v_p = IG + D * DS;        // momentum
+    double* v_u = v_p + 32;           // G^-1 x
+    double* v_out = v_u + 32;         // contraction results
+    double* v_grad = v_out + 32;
+    double* v_tr = v_grad + 32;
+    double* v_th = v_tr + 32;
+    double* v_x = v_th + 32;          // scratch vector (z, fixed-point iterate)
+    double* v_y = v_x + 32;
+    double* Tsm = v_y + 32;
+    if ((Tsm - IG) & 1) ++Tsm;
+    const bool live = tid < D;
+    PairRegs<NCH> pr;
+    load_pairs<NCH>(P, pr, lane);
+
+    int cur = S.cur[c];
+    int step = init ? 0 : S.step[c];
+    int have_slot = -1;               // slot whose T / G^-1 / grad / trace / theta are in shared memory
+
+    auto load_slot_mats = [&](int slot) {
+        const double2* ts = reinterpret_cast<const double2*>(S.tpack + slot * P.slot_t + (size_t)c * P.p3p);
+        double2* td = reinterpret_cast<double2*>(Tsm);
+        for (int i = tid; i < P.p3p / 2; i += kTurnThreads) td[i] = ts[i];
+        const double* ig = S.invg + slot * P.slot_invg + (size_t)c * D * D;
+        for (int idx = tid; idx < D * D; idx += kTurnThreads) IG[(idx / D) * DS + (idx % D)] = ig[idx];
+    };
+    // y = G^-1 x for vectors in shared memory; ends with a CTA barrier
+    auto matvec = [&](const double* x, double* y) {
+        if (live) {
+            double y0 = 0.0, y1 = 0.0;
+            const double* r = IG + tid * DS;
+            int b = 0;
+            for (; b + 1 < D; b += 2) { y0 = fma(r[b], x[b], y0); y1 = fma(r[b + 1], x[b + 1], y1); }
+            if (b < D) y0 = fma(r[b], x[b], y0);
+            y[tid] = y0 + y1;
+        }
+        __syncthreads();
+    };
+    auto dot = [&](const double* x, const double* y) {     // every thread gets the same value
+        double s = 0.0;
+        for (int b = 0; b < D; ++b) s = fma(x[b], y[b], s);
+        return s;
+    };
+
+    if (do_back) {
+        const int nsteps = init ? 1 : S.nsteps[c];
+        const int out = init ? cur : 1 - cur;
+        const int sgn = init ? 1 : S.dir[c];
+        double hprop;
+        bool finished = true;
+        if (nsteps > 0) {
+            // ---- R12/R13: traces with the freshly factored metric; R7': gradient; log joint
+            load_slot_mats(out);
+            if (live) {
+                double th = S.theta_w[(size_t)c * D + tid];
+                v_th[tid] = th;
+                v_grad[tid] = S.grad_tmp[(size_t)c * D + tid] - th / P.alpha;                    // rmhmc.py:140
+                v_p[tid] = init ? 0.0 : S.mom[(size_t)c * D + tid];
+            }
+            __syncthreads();
+            trace_terms<NCH>(P, pr, Tsm, IG, v_tr, warp, NW, lane);
+            double lp = 0.0;
+            for (int b = 0; b < D; ++b)
+                lp += -0.5 * log(2.0 * 3.14159265358979323846 * P.alpha) - v_th[b] * v_th[b] / (2.0 * P.alpha);
+            const double ljl = S.loglik_tmp[c] + lp;                        // rmhmc.py:166-169, tools.py:10-14
+            const double logdet = S.logdet[out * P.slot_scalar + c];
+            if (live) {
+                S.theta[out * P.slot_theta + (size_t)c * D + tid] = v_th[tid];
+                S.grad[out * P.slot_theta + (size_t)c * D + tid] = v_grad[tid];
+                S.trace[out * P.slot_theta + (size_t)c * D + tid] = v_tr[tid];
+            }
+            if (tid == 0) S.logjoint[out * P.slot_scalar + c] = ljl;
+            if (init) return;
+            have_slot = out;
+
+            // ---- R14: explicit closing momentum half-step
+            matvec(v_p, v_u);
+            quad_terms<NCH>(P, pr, Tsm, v_u, v_out, warp, NW, lane);
+            if (live) {
+                double p = v_p[tid] + (sgn * P.step_size / 2) * (v_grad[tid] - 0.5 * v_tr[tid] + 0.5 * v_out[tid]);
+                v_p[tid] = p;
+                S.mom[(size_t)c * D + tid] = p;
+                if (P.tr_theta_steps && it < P.tr_iters)
+                    P.tr_theta_steps[(((size_t)c * P.tr_iters + it) * P.n_leapfrog + step) * D + tid] = v_th[tid];
+            }
+            __syncthreads();
+            ++step;
+            if (tid == 0) ++S.leapfrogs[c];
+            if (step < nsteps) {
+                if (tid == 0) S.step[c] = step;
+                finished = false;
+            } else {
+                // ---- R15: proposed Hamiltonian
+                matvec(v_p, v_u);
+                hprop = -ljl + logdet + 0.5 * dot(v_p, v_u);
+            }
+        } else {
+            // empty trajectory (RandomStep = 0): the proposal is the current state
+            hprop = S.hcur[c];
+            if (live) v_p[tid] = S.mom[(size_t)c * D + tid];
+            __syncthreads();
+        }
+        if (finished) {
+            // ---- R16/R17: accept / reject.  The uniform is consumed only when Ratio > 0 is false.
+            double ratio = S.hcur[c] - hprop;
+            bool take = ratio > 0.0, used_u = false;
+            if (!take) {
+                used_u = true;
+                double ua = P.rng_mode == 0 ? P.tape_u_acc[(size_t)(it - P.tape_base) * P.n_chains + c]
+                                            : philox_pair(P, c, it, 34u).u0;
+                take = ratio > log(ua);
+            }
+            const int fin = (take && nsteps > 0) ? out : cur;
+            if (P.tr_mom_end && it < P.tr_iters) {
+                size_t o = ((size_t)c * P.tr_iters + it) * D + tid;
+                if (live) {
+                    P.tr_mom_end[o] = v_p[tid];
+                    P.tr_theta_end[o] = S.theta[(nsteps > 0 ? out : cur) * P.slot_theta + (size_t)c * D + tid];
+                }
+                if (tid == 0) {
+                    P.tr_hprop[(size_t)c * P.tr_iters + it] = hprop;
+                    P.tr_flags[(size_t)c * P.tr_iters + it] =
+                        (take ? 1 : 0) | (used_u ? 2 : 0) | (sgn > 0 ? 16 : 0) | (nsteps << 8);
+                }
+            }
+            // ---- R18: store (row it - burn_in, only for it > burn_in)
+            if (P.samples && it > P.burn_in && it - P.burn_in < P.sample_cap && live)
+                P.samples[((size_t)c * P.sample_cap + (it - P.burn_in)) * D + tid] =
+                    S.theta[fin * P.slot_theta + (size_t)c * D + tid];
+            __syncthreads();       // everyone has read the pre-update state
+            if (tid == 0) {
+                S.cur[c] = fin;
+                if (take) ++S.accepted[c];
+                S.step[c] = 0;
+                S.iter[c] = it + 1;
+            }
+            cur = fin;
+            step = 0;
+            it += 1;
+        }
+    }
+
+    if (!do_front || it >= P.it_stop) return;
+    const int in_slot = step == 0 ? cur : 1 - cur;
+    if (have_slot != in_slot) {
+        load_slot_mats(in_slot);
+        if (live) {
+            v_grad[tid] = S.grad[in_slot * P.slot_theta + (size_t)c * D + tid];
+            v_tr[tid] = S.trace[in_slot * P.slot_theta + (size_t)c * D + tid];
+            v_th[tid] = S.theta[in_slot * P.slot_theta + (size_t)c * D + tid];
+        }
+        __syncthreads();
+    }
+    int sgn, nsteps;
     if (step == 0) {
-        // ---- R2/R4-R6: factor G at the current position, draw p = L^T z, H_current
-        unpack_sym(S.gp + cur * P.slot_gp + (size_t)c * P.p2p, sm.A, D, DS, lane);
-        chol_warp(sm.A, D, DS, lane);
+        // ---- R4-R6: p = L^T z with the current position's Cholesky factor, H_current
         double z = 0.0, u_step, z_dir;
         if (P.rng_mode == 0) {
             size_t row = (size_t)(it - P.tape_base) * P.n_chains + c;
-            if (live) z = P.tape_z[row * D + lane];
+            if (live) z = P.tape_z[row * D + tid];
             u_step = P.tape_u_step[row];
             z_dir = P.tape_z_dir[row];
         } else {
-            if (live) z = philox_normal(P, c, it, (uint32_t)lane);
+            if (live) z = philox_normal(P, c, it, (uint32_t)tid);
             u_step = philox_pair(P, c, it, 32u).u0;
             z_dir = philox_normal(P, c, it, 33u);
         }
-        __syncwarp();
-        if (live) sm.v0[lane] = z;
-        __syncwarp();
-        if (live)
-            for (int i = lane; i < D; ++i) p += sm.A[i * DS + lane] * sm.v0[i];   // (z L)^T = L^T z, rmhmc.py:80
-        double nrm = sqrt(warp_sum(p * p));
+        if (live) v_x[tid] = z;
+        __syncthreads();
+        if (live) {
+            const double* lf = S.lfac + in_slot * P.slot_invg + (size_t)c * D * D;
+            double p = 0.0;
+            for (int i = tid; i < D; ++i) p = fma(lf[i * D + tid], v_x[i], p);     // (z L)^T = L^T z, rmhmc.py:80
+            v_p[tid] = p;
+        }
+        __syncthreads();
+        double nrm = sqrt(dot(v_p, v_p));
         if (nrm > 100.0) {                                                          // rmhmc.py:81-85
-            p /= nrm * 25.0;
-            if (lane == 0) ++S.renorm_mom[c];
+            __syncthreads();
+            if (live) v_p[tid] /= nrm * 25.0;
+            if (tid == 0) ++S.renorm_mom[c];
+            __syncthreads();
         }
         nsteps = (int)ceil(u_step * (double)P.n_leapfrog);                          // rmhmc.py:89
         sgn = z_dir > 0.5 ? 1 : -1;                                                 // rmhmc.py:90-93
-        // InvG of the current slot -> B
-        const double* ig = S.invg + cur * P.slot_invg + (size_t)c * D * D;
-        for (int idx = lane; idx < D * D; idx += 32) sm.B[(idx / D) * DS + (idx % D)] = ig[idx];
-        __syncwarp();
-        double u = matvec_warp(sm.B, sm.v1, D, DS, lane, p);
-        double kin = 0.5 * warp_sum(live ? p * u : 0.0);
-        double hcur = -S.logjoint[cur * P.slot_scalar + c] + S.logdet[cur * P.slot_scalar + c] + kin;  // rmhmc.py:175-176
-        if (lane == 0) {
+        matvec(v_p, v_u);
+        double hcur = -S.logjoint[in_slot * P.slot_scalar + c] + S.logdet[in_slot * P.slot_scalar + c] +
+                      0.5 * dot(v_p, v_u);                                          // rmhmc.py:175-176
+        if (tid == 0) {
             S.hcur[c] = hcur;
             S.nsteps[c] = nsteps;
             S.dir[c] = sgn;
         }
-        if (P.tr_mom0 && it < P.tr_iters && live) P.tr_mom0[((size_t)c * P.tr_iters + it) * D + lane] = p;
-        if (P.tr_hcur && it < P.tr_iters && lane == 0) P.tr_hcur[(size_t)c * P.tr_iters + it] = hcur;
-        if (nsteps <= 0) {            // u_step == 0: empty trajectory; k_chain_back finishes the iteration
-            if (live) S.mom[(size_t)c * D + lane] = p;
+        if (P.tr_mom0 && it < P.tr_iters && live) P.tr_mom0[((size_t)c * P.tr_iters + it) * D + tid] = v_p[tid];
+        if (P.tr_hcur && it < P.tr_iters && tid == 0) P.tr_hcur[(size_t)c * P.tr_iters + it] = hcur;
+        if (nsteps <= 0) {        // u_step == 0: empty trajectory; the next back half finishes the iteration
+            if (live) S.mom[(size_t)c * D + tid] = v_p[tid];
             return;
         }
     } else {
         nsteps = S.nsteps[c];
         sgn = S.dir[c];
-        if (live) p = S.mom[(size_t)c * D + lane];
+        if (live) v_p[tid] = S.mom[(size_t)c * D + tid];
+        __syncthreads();
     }
 
     // ---- R7/R8: implicit momentum half-step with the metric quantities of the step's start point
-    const int in_slot = step == 0 ? cur : 1 - cur;
-    if (step != 0) {
-        const double* ig = S.invg + in_slot * P.slot_invg + (size_t)c * D * D;
-        for (int idx = lane; idx < D * D; idx += 32) sm.B[(idx / D) * DS + (idx % D)] = ig[idx];
-        __syncwarp();
-    }
-    load_t_smem(sm.T, S.tpack + in_slot * P.slot_t + (size_t)c * P.p3p, P.p3p, lane);
-    double grad = 0.0, tr = 0.0, w = 0.0;
-    if (live) {
-        grad = S.grad[in_slot * P.slot_theta + (size_t)c * D + lane];
-        tr = S.trace[in_slot * P.slot_theta + (size_t)c * D + lane];
-        w = S.theta[in_slot * P.slot_theta + (size_t)c * D + lane];
-    }
     const double h = sgn * P.step_size / 2;
-    const double base = grad - 0.5 * tr;
-    double pm = p;
+    if (live) v_x[tid] = v_p[tid];                  // v_x: fixed-point iterate PM
+    __syncthreads();
     for (int fi = 0; fi < P.n_fixed; ++fi) {
-        double u = matvec_warp(sm.B, sm.v1, D, DS, lane, pm);
-        double last = last_term(P, sm.T, sm.Q, sm.v2, lane, u);
-        pm = p + h * (base + last);
+        matvec(v_x, v_u);
+        quad_terms<NCH>(P, pr, Tsm, v_u, v_out, warp, NW, lane);
+        if (live) v_x[tid] = v_p[tid] + h * (v_grad[tid] - 0.5 * v_tr[tid] + 0.5 * v_out[tid]);
+        __syncthreads();
     }
-    p = pm;
     // ---- R9 and the first position iterate (its metric is the one we already hold)
-    double u0 = matvec_warp(sm.B, sm.v1, D, DS, lane, p);
-    double pw = w + h * (u0 + u0);
-    if (P.n_fixed <= 1) {
-        if (P.n_fixed == 0) pw = w;
-        pw = clamp_position(pw, lane, D, &S.renorm_pos[c]);
-    }
-    if (live) {
-        S.mom[(size_t)c * D + lane] = p;
-        S.u0[(size_t)c * D + lane] = u0;
-        S.theta_w[(size_t)c * D + lane] = pw;
+    matvec(v_x, v_u);
+    if (warp == 0) {
+        double u0 = live ? v_u[tid] : 0.0;
+        double th = live ? v_th[tid] : 0.0;
+        double pw = th + h * (u0 + u0);
+        if (P.n_fixed <= 1) {
+            if (P.n_fixed == 0) pw = th;
+            pw = clamp_position(pw, lane, D, &S.renorm_pos[c]);
+        }
+        if (live) {
+            S.mom[(size_t)c * D + tid] = v_x[tid];
+            S.u0[(size_t)c * D + tid] = u0;
+            S.theta_w[(size_t)c * D + tid] = pw;
+        }
     }
 }
 
-// ---------------------------------------------------------------- round stage 2 (x (F-1))
-// position fixed-point iterate: solve G(theta_w) u = p, theta_w <- theta + s eps/2 (u0 + u)
+// ---------------------------------------------------------------- position fixed-point iterate (x (F-1))
+// solve G(theta_w) u = p, theta_w <- theta + s eps/2 (u0 + u)   (rmhmc.py:116-122)
+template <int DMAX>
 __global__ void __launch_bounds__(32) k_chain_solve(EngineParams P, ChainArrays S, int is_last) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = blockIdx.x, lane = threadIdx.x, D = P.dim, DS = P.ds;
     if (c >= P.n_chains) return;
     if (S.iter[c] >= P.it_stop || S.nsteps[c] <= 0) return;
-    ChainSmem sm = carve_chain_smem(smem_raw, P, false);
+    double* Lsm = reinterpret_cast<double*>(smem_raw);
     const bool live = lane < D;
     const int cur = S.cur[c];
     const int in_slot = S.step[c] == 0 ? cur : 1 - cur;
-    unpack_sym(S.g_tmp + (size_t)c * P.p2p, sm.A, D, DS, lane);
-    chol_warp(sm.A, D, DS, lane);
+    double lrow[DMAX], dinv;
+    load_packed_rows<DMAX>(S.g_tmp + (size_t)c * P.p2p, lrow, D, lane);
     double p = live ? S.mom[(size_t)c * D + lane] : 0.0;
-    double u = chol_solve_warp(sm.A, D, DS, lane, p);                   // rmhmc.py:121
     double w = live ? S.theta[in_slot * P.slot_theta + (size_t)c * D + lane] : 0.0;
     double u0 = live ? S.u0[(size_t)c * D + lane] : 0.0;
-    double pw = w + (S.dir[c] * P.step_size / 2) * (u0 + u);            // rmhmc.py:122
+    chol_regs<DMAX>(lrow, D, lane, dinv);
+    store_rows<DMAX>(Lsm, lrow, D, DS, lane);
+    double u = chol_solve_regs<DMAX>(lrow, Lsm, dinv, D, DS, lane, p);             // rmhmc.py:121
+    double pw = w + (S.dir[c] * P.step_size / 2) * (u0 + u);                        // rmhmc.py:122
     if (is_last) pw = clamp_position(pw, lane, D, &S.renorm_pos[c]);
     if (live) S.theta_w[(size_t)c * D + lane] = pw;
 }
 
-// ---------------------------------------------------------------- round stage 3
-// metric quantities at the new position, explicit closing momentum half-step, and -- when the
-// trajectory is complete -- Hamiltonian, accept/reject, sample store.  With init != 0 it only
-// fills slot `cur` from the builds at theta_w (sampler start-up).
-__global__ void __launch_bounds__(32) k_chain_back(EngineParams P, ChainArrays S, int init) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int c = blockIdx.x, lane = threadIdx.x, D = P.dim, DS = P.ds;
-    if (c >= P.n_chains) return;
-    long long it = S.iter[c];
-    if (!init && it >= P.it_stop) return;
-    ChainSmem sm = carve_chain_smem(smem_raw, P, true);
-    const bool live = lane < D;
-    const int cur = S.cur[c];
-    const int nsteps = init ? 1 : S.nsteps[c];
-    const int out = init ? cur : 1 - cur;
-    double hprop = 0.0, p = 0.0;
-    int step = init ? 0 : S.step[c];
-
-    if (nsteps > 0) {
-        // ---- R12/R13: factor G(theta_w), inverse, log-det, traces; R7': gradient; log joint
-        const double* gsrc = S.g_tmp + (size_t)c * P.p2p;
-        double* gdst = S.gp + out * P.slot_gp + (size_t)c * P.p2p;
-        for (int i = lane; i < P.p2p; i += 32) gdst[i] = gsrc[i];
-        unpack_sym(gsrc, sm.A, D, DS, lane);
-        double logdet = chol_warp(sm.A, D, DS, lane);
-        chol_inverse_warp(sm.A, sm.B, D, DS, lane);
-        double* ig = S.invg + out * P.slot_invg + (size_t)c * D * D;
-        for (int idx = lane; idx < D * D; idx += 32) ig[idx] = sm.B[(idx / D) * DS + (idx % D)];
-        load_t_smem(sm.T, S.tpack + out * P.slot_t + (size_t)c * P.p3p, P.p3p, lane);
-        for (int pr = lane; pr < P.p2; pr += 32) {
-            int pa = P.pair_a[pr], pb = P.pair_b[pr];
-            double w = sm.B[pa * DS + pb];
-            sm.Q[pr] = pa == pb ? w : 2.0 * w;
-        }
-        __syncwarp();
-        double tr = tensor_contract(sm.T, sm.Q, P.qidx, P.p2, lane);    // tr(G^-1 dG_d), rmhmc.py:156
-        double th = live ? S.theta_w[(size_t)c * D + lane] : 0.0;
-        double grad = live ? S.grad_tmp[(size_t)c * D + lane] - th / P.alpha : 0.0;   // rmhmc.py:140
-        double lp = live ? -0.5 * log(2.0 * 3.14159265358979323846 * P.alpha) - th * th / (2.0 * P.alpha) : 0.0;
-        double ljl = S.loglik_tmp[c] + warp_sum(lp);                    // rmhmc.py:166-169, tools.py:10-14
-        if (live) {
-            S.theta[out * P.slot_theta + (size_t)c * D + lane] = th;
-            S.grad[out * P.slot_theta + (size_t)c * D + lane] = grad;
-            S.trace[out * P.slot_theta + (size_t)c * D + lane] = tr;
-        }
-        if (lane == 0) {
-            S.logjoint[out * P.slot_scalar + c] = ljl;
-            S.logdet[out * P.slot_scalar + c] = logdet;
-        }
-        if (init) return;
-
-        // ---- R14: explicit closing momentum half-step
-        p = live ? S.mom[(size_t)c * D + lane] : 0.0;
-        double u = matvec_warp(sm.B, sm.v1, D, DS, lane, p);
-        double last = last_term(P, sm.T, sm.Q, sm.v2, lane, u);
-        p += (S.dir[c] * P.step_size / 2) * (grad - 0.5 * tr + last);
-        if (live) S.mom[(size_t)c * D + lane] = p;
-        if (P.tr_theta_steps && it < P.tr_iters && live)
-            P.tr_theta_steps[(((size_t)c * P.tr_iters + it) * P.n_leapfrog + step) * D + lane] = th;
-        ++step;
-        if (lane == 0) ++S.leapfrogs[c];
-        if (step < nsteps) {
-            if (lane == 0) S.step[c] = step;
-            return;
-        }
-        // ---- R15: proposed Hamiltonian
-        double u2 = matvec_warp(sm.B, sm.v1, D, DS, lane, p);
-        hprop = -ljl + logdet + 0.5 * warp_sum(live ? p * u2 : 0.0);
-    } else {
-        // empty trajectory (RandomStep = 0): the proposal is the current state
-        hprop = S.hcur[c];
-        p = live ? S.mom[(size_t)c * D + lane] : 0.0;
-    }
-
-    // ---- R16/R17: accept / reject.  The uniform is consumed only when Ratio > 0 is false.
-    double ratio = S.hcur[c] - hprop;
-    bool take = ratio > 0.0, used_u = false;
-    if (!take) {
-        used_u = true;
-        double ua = P.rng_mode == 0 ? P.tape_u_acc[(size_t)(it - P.tape_base) * P.n_chains + c]
-                                    : philox_pair(P, c, it, 34u).u0;
-        take = ratio > log(ua);
-    }
-    const int fin = (take && nsteps > 0) ? out : cur;
-    if (P.tr_mom_end && it < P.tr_iters) {
-        size_t o = ((size_t)c * P.tr_iters + it) * D + lane;
-        if (live) {
-            P.tr_mom_end[o] = p;
-            P.tr_theta_end[o] = S.theta[(nsteps > 0 ? out : cur) * P.slot_theta + (size_t)c * D + lane];
-        }
-        if (lane == 0) {
-            P.tr_hprop[(size_t)c * P.tr_iters + it] = hprop;
-            P.tr_flags[(size_t)c * P.tr_iters + it] =
-                (take ? 1 : 0) | (used_u ? 2 : 0) | (S.dir[c] > 0 ? 16 : 0) | (nsteps << 8);
-        }
-    }
-    // ---- R18: store (row it - burn_in, only for it > burn_in)
-    if (P.samples && it > P.burn_in && it - P.burn_in < P.sample_cap && live)
-        P.samples[((size_t)c * P.sample_cap + (it - P.burn_in)) * D + lane] =
-            S.theta[fin * P.slot_theta + (size_t)c * D + lane];
-    if (lane == 0) {
-        S.cur[c] = fin;
-        if (take) ++S.accepted[c];
-        S.step[c] = 0;
-        S.iter[c] = it + 1;
-    }
-}
 #endif  // __CUDACC__
 
 }  // namespace rmhmc

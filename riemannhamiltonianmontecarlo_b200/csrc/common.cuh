@@ -113,7 +113,7 @@ struct ChainArrays {
     // slot-indexed: ptr + slot * slot_stride
     double* theta;     // [2][C][D]     position
     double* logjoint;  // [2][C]        log-likelihood + log-prior at theta
-    double* gp;        // [2][C][P2]    packed metric G(theta)
+    double* lfac;      // [2][C][D*D]   lower Cholesky factor of G(theta) (dense, row-major)
     double* invg;      // [2][C][D*D]   G^-1 (dense, symmetric)
     double* logdet;    // [2][C]        sum log diag chol(G) = 0.5 log|G|
     double* tpack;     // [2][C][P3p]   packed partials tensor T(theta)

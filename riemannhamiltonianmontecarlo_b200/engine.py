@@ -206,8 +206,8 @@ class RMHMCSampler(_SamplerBase):
         _capi.check(self._lib.rmhmc_profile_enable(self.h, 1 if enable else 0), self.h, "profile_enable")
 
     def profile_read(self):
-        """{kind: (milliseconds, launches)} for metric_fp, metric_closing, partials, chain stages."""
-        names = ["metric_fp", "metric_closing", "partials", "chain"]
+        """{kind: (milliseconds, launches)} per kernel class."""
+        names = ["metric_fp", "metric_closing", "partials", "chain_turn", "chain_solve"]
         out = {}
         for k, nm in enumerate(names):
             ms, n = ctypes.c_double(0), c_int64(0)
