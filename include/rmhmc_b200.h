@@ -46,6 +46,9 @@ const char* rmhmc_version(void);
 int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double alpha,
                  const double* xx_dev, const double* t_dev);
 void rmhmc_destroy(rmhmc_handle* h);
+/* Re-upload XX / t of the same shape into the handle (chains keep their state); enqueued on the
+ * handle's stream.  This is what a caller that owns host buffers does before each batch of rounds. */
+int rmhmc_update_data(rmhmc_handle* h, const double* xx_dev, const double* t_dev);
 const char* rmhmc_last_error(const rmhmc_handle* h);
 /* cudaStream_t to enqueue on (0 = legacy default stream). */
 int rmhmc_set_stream(rmhmc_handle* h, void* cuda_stream);
@@ -143,6 +146,12 @@ int hmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
 int blr_ess_batched(int device, void* cuda_stream, const double* samples, int64_t n_chains,
                     int64_t n_samples, int dim, int64_t chain_stride, int64_t row_stride,
                     int64_t max_lag, double* ess);
+
+/* Ragged variant for free-running chains: chain c uses rows [starts[c], starts[c] + counts[c]) of its
+ * block (int64 device arrays) with max_lag = counts[c] - 1; max_samples bounds counts[c]. */
+int blr_ess_ragged(int device, void* cuda_stream, const double* samples, int64_t n_chains,
+                   int64_t max_samples, int dim, int64_t chain_stride, int64_t row_stride,
+                   const int64_t* starts, const int64_t* counts, double* ess);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,7 @@ SIGNATURES = {
     "rmhmc_create": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int, c_double, c_void_p, c_void_p]),
     "rmhmc_destroy": (None, [c_void_p]),
     "rmhmc_last_error": (c_char_p, [c_void_p]),
+    "rmhmc_update_data": (c_int, [c_void_p, c_void_p, c_void_p]),
     "rmhmc_set_stream": (c_int, [c_void_p, c_void_p]),
     "rmhmc_metric": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rmhmc_metric_partials": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -41,6 +42,7 @@ SIGNATURES = {
     "hmc_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "hmc_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     "blr_ess_batched": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p]),
+    "blr_ess_ragged": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 
 

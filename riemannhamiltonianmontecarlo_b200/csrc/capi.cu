@@ -627,6 +627,16 @@ void rmhmc_destroy(rmhmc_handle* h) {
     delete h;
 }
 
+int rmhmc_update_data(rmhmc_handle* h, const double* xx_dev, const double* t_dev) {
+    if (!h || !xx_dev || !t_dev) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_update_data: bad arguments") : RMHMC_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int64_t total = (int64_t)h->n_rows_pad * h->xs;
+    k_pad_design<<<blocks_for(total, 256), 256, 0, h->stream>>>(xx_dev, t_dev, h->x_pad, h->n_rows, h->dim, h->xs, h->n_rows_pad);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
 int rmhmc_set_stream(rmhmc_handle* h, void* cuda_stream) {
     if (!h) return RMHMC_E_INVALID;
     h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
@@ -879,7 +889,22 @@ int blr_ess_batched(int device, void* cuda_stream, const double* samples, int64_
     if (cudaFuncSetAttribute(k_ess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return RMHMC_E_CUDA;
     dim3 grid((unsigned)n_chains, (unsigned)dim);
     k_ess<<<grid, kEssThreads, smem, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
-        samples, (size_t)chain_stride, (size_t)row_stride, (int)n_samples, (int)max_lag, n_fft, ess, dim);
+        samples, (size_t)chain_stride, (size_t)row_stride, (int)n_samples, (int)max_lag, n_fft, ess, dim, nullptr, nullptr);
+    return cudaGetLastError() == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
+}
+
+int blr_ess_ragged(int device, void* cuda_stream, const double* samples, int64_t n_chains, int64_t max_samples,
+                   int dim, int64_t chain_stride, int64_t row_stride, const int64_t* starts, const int64_t* counts,
+                   double* ess) {
+    if (!samples || !ess || !starts || !counts || n_chains <= 0 || max_samples < 2 || dim <= 0) return RMHMC_E_INVALID;
+    if (max_samples > 24000 || dim > 65535) return RMHMC_E_UNSUPPORTED;
+    if (cudaSetDevice(device) != cudaSuccess) return RMHMC_E_CUDA;
+    size_t smem = (size_t)max_samples * 8;
+    if (cudaFuncSetAttribute(k_ess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return RMHMC_E_CUDA;
+    dim3 grid((unsigned)n_chains, (unsigned)dim);
+    k_ess<<<grid, kEssThreads, smem, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+        samples, (size_t)chain_stride, (size_t)row_stride, (int)max_samples, 0, 0, ess, dim,
+        reinterpret_cast<const long long*>(starts), reinterpret_cast<const long long*>(counts));
     return cudaGetLastError() == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
 }
 

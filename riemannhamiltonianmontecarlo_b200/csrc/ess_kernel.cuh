@@ -29,14 +29,32 @@ __device__ __forceinline__ double lin_lag(const double* y, int S, int lag, doubl
 }
 
 // samples: series (c, d) element s at samples[c*chain_stride + s*row_stride + d]
+// With starts/counts (ragged mode) chain c uses rows [starts[c], starts[c] + counts[c]) with
+// max_lag = count - 1; S then is only the shared-memory capacity.
 __global__ void __launch_bounds__(kEssThreads) k_ess(const double* __restrict__ samples, size_t chain_stride,
                                                       size_t row_stride, int S, int max_lag, int n_fft,
-                                                      double* __restrict__ ess_out, int D) {
+                                                      double* __restrict__ ess_out, int D,
+                                                      const long long* __restrict__ starts,
+                                                      const long long* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* y = reinterpret_cast<double*>(smem_raw);
     __shared__ double scratch[4];
     const int c = blockIdx.x, d = blockIdx.y;
     const double* src = samples + (size_t)c * chain_stride + d;
+    if (counts) {
+        long long n = counts[c];
+        if (n > S) n = S;
+        if (n < 2) {
+            if (threadIdx.x == 0) ess_out[(size_t)c * D + d] = 0.0;
+            return;
+        }
+        src += (size_t)starts[c] * row_stride;
+        S = (int)n;
+        max_lag = S - 1;
+        n_fft = 1;
+        while (n_fft < S) n_fft *= 2;
+        n_fft += 1;
+    }
     double s = 0.0;
     for (int t = threadIdx.x; t < S; t += kEssThreads) {
         double v = src[(size_t)t * row_stride];

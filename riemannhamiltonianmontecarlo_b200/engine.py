@@ -49,6 +49,11 @@ class LogisticData:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _capi.check(self._lib.rmhmc_set_stream(self.handle, c_void_p(stream)), self.handle, "rmhmc_set_stream")
 
+    def update(self, xx_dev, t_dev):
+        """Re-upload the design matrix / labels from device tensors of the bound shape."""
+        assert xx_dev.shape == (self.n_rows, self.dim) and t_dev.numel() == self.n_rows
+        _capi.check(self._lib.rmhmc_update_data(self.handle, _ptr(xx_dev), _ptr(t_dev)), self.handle, "rmhmc_update_data")
+
     def close(self):
         if getattr(self, "handle", None):
             self._lib.rmhmc_destroy(self.handle)
@@ -251,7 +256,7 @@ def ess_batched(samples, max_lag: int | None = None):
     lib = _capi.load()
     if isinstance(samples, np.ndarray):
         samples = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)).cuda()
-    assert samples.dim() == 3 and samples.dtype == torch.float64
+    assert samples.dim() == 3 and samples.dtype == torch.float64 and samples.stride(2) == 1
     c, s, d = samples.shape
     if max_lag is None:
         max_lag = s - 1
@@ -261,4 +266,28 @@ def ess_batched(samples, max_lag: int | None = None):
                              samples.stride(0), samples.stride(1), int(max_lag), _ptr(out))
     if rc != 0:
         raise _capi.RmhmcError(f"blr_ess_batched failed (code {rc})")
+    return out
+
+
+def ess_ragged(samples, starts, counts):
+    """ESS per (chain, parameter) over per-chain row windows of a device array (C, S, D).
+
+    ``starts`` / ``counts`` are int64 device tensors (C,): chain c uses rows
+    [starts[c], starts[c]+counts[c]).  Returns a device tensor (C, D).
+    """
+    torch = _capi.require_cuda()
+    lib = _capi.load()
+    c, s, d = samples.shape
+    assert samples.dtype == torch.float64 and samples.stride(2) == 1
+    starts = starts.to(torch.int64).contiguous()
+    counts = counts.to(torch.int64).contiguous()
+    max_s = int(counts.max().item())
+    out = torch.zeros(c, d, dtype=torch.float64, device=samples.device)
+    if max_s < 2:
+        return out
+    stream = torch.cuda.current_stream(samples.device).cuda_stream
+    rc = lib.blr_ess_ragged(samples.device.index or 0, c_void_p(stream), _ptr(samples), c, max_s, d,
+                            samples.stride(0), samples.stride(1), _ptr(starts), _ptr(counts), _ptr(out))
+    if rc != 0:
+        raise _capi.RmhmcError(f"blr_ess_ragged failed (code {rc})")
     return out

@@ -1,0 +1,141 @@
+"""CPU tests of the host side: the C-ABI library builds, loads and exports every symbol the header
+declares; host helpers; loud failure without a GPU; the bench CPU arm; multi-rank plumbing (gloo)."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "rmhmc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:rmhmc|hmc|blr)_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol(built_library):
+    from riemannhamiltonianmontecarlo_b200 import _capi
+    lib = _capi.load()
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in include/rmhmc_b200.h but not exported"
+        assert name in _capi.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_capi.SIGNATURES) == set(syms)
+    assert b"sm_100a" in lib.rmhmc_version()
+
+
+def test_library_is_sm100a_only(built_library):
+    out = subprocess.run(["cuobjdump", "-lelf", built_library], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu(built_library):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import riemannhamiltonianmontecarlo_b200 as r
+    from riemannhamiltonianmontecarlo_b200._capi import RmhmcError
+    xx, t = r.datasets.shaped("australian")
+    with pytest.raises(RmhmcError):
+        r.RMHMC(xx, t, 10, 2)
+    with pytest.raises(RmhmcError):
+        r.HMC(xx, t, 10, 2)
+    with pytest.raises(RmhmcError):
+        r.CalculateESS(np.zeros((10, 2)), 9)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "riemannhamiltonianmontecarlo_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), fn
+
+
+def test_host_helpers_match_reference_semantics(golden):
+    import riemannhamiltonianmontecarlo_b200 as r
+    fx = golden("tools_ess")
+    assert abs(r.LogNormPDF(np.zeros((1, 15)), fx["lnp_w"], 100) - float(fx["lnp"])) < 1e-12
+    assert abs(r.LogNormPDF(np.zeros((15, 1)), fx["lnp_w"], 100) - float(fx["lnp"])) < 1e-12
+    for i, v in fx["nextpow2"]:
+        assert r.nextpow2(int(i)) == int(v)
+    for j in range(3):
+        assert np.abs(r.ac(fx["x"][:, j], 200) - fx["ac_200"][:, j]).max() < 1e-10
+
+
+def test_csv_preprocessing_matches_main_py(tmp_path):
+    from riemannhamiltonianmontecarlo_b200 import datasets
+    rng = np.random.default_rng(1)
+    raw = np.hstack([rng.normal(3, 2, (40, 4)), rng.integers(1, 3, (40, 1))])
+    p = tmp_path / "toy.csv"
+    np.savetxt(p, raw, delimiter=",")
+    xx, t = datasets.load_csv(str(p), relabel_12=True)
+    x = raw[:, :-1]
+    expect = np.hstack([np.ones((40, 1)), (x - x.mean(0)) / x.std(0)])      # main.py:34-41 (ddof=0)
+    assert np.allclose(xx, expect) and set(np.unique(t)) <= {0.0, 1.0} and t.shape == (40, 1)
+
+
+def test_packed_index_tables_roundtrip():
+    # python mirror of csrc/common.cuh index math: packed triples enumerate i<=j<=k exactly once
+    def tri(n): return n * (n + 1) * (n + 2) // 6
+    def triple_index(i, j, k, d):
+        n, jj, kk = d - i, j - i, k - i
+        return tri(d) - tri(d - i) + jj * n - jj * (jj - 1) // 2 + (kk - jj)
+    for d in (3, 15, 25, 32):
+        seen = [triple_index(i, j, k, d) for i in range(d) for j in range(i, d) for k in range(j, d)]
+        assert seen == list(range(tri(d)))
+
+
+def test_bench_reference_arm_prints_contract_json():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--ref-iters-per-step", "4"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "min_ess_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # chain sharding: contiguous blocks, Philox streams keyed by the global chain id
+    c_local = 6
+    offset = rank * c_local
+    ids = torch.arange(offset, offset + c_local, dtype=torch.float64)
+    ess_local = torch.stack([ids + 1.0, 2.0 * ids + 1.0], dim=1)          # stand-in per-chain ESS (C, D)
+    ess_sum = ess_local.sum(dim=0)
+    dist.all_reduce(ess_sum, op=dist.ReduceOp.SUM)
+    tmax = torch.tensor([1.0 + rank], dtype=torch.float64)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    gathered = [torch.zeros_like(ess_local) for _ in range(world)]
+    dist.all_gather(gathered, ess_local)
+    q.put((rank, ess_sum.tolist(), float(tmax.item()), torch.cat(gathered).shape[0]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_statistics_gather_over_gloo():
+    """The N>1 reduction the bench does over NCCL (sum of per-chain ESS, max of time), on gloo."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    ids = np.arange(12.0)
+    for rank, ess_sum, tmax, n in res:
+        assert ess_sum == [float((ids + 1).sum()), float((2 * ids + 1).sum())]
+        assert tmax == 2.0 and n == 12
