@@ -30,7 +30,7 @@ struct rmhmc_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     int64_t n_rows = 0;
-    int dim = 0, xs = 0, n_rows_pad = 0, p2 = 0, p2p = 0, p3 = 0, p3p = 0, nt = 0;
+    int dim = 0, xs = 0, n_rows_pad = 0, p2 = 0, p2p = 0, p3 = 0, p3p = 0, nt = 0, extra_tile = -1;
     double alpha = 100.0;
     // data set
     double* x_pad = nullptr;
@@ -260,7 +260,7 @@ int launch_metric(rmhmc_handle* h, const MetricArgs& a) {
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         Bracket b(h, MODE == 0 ? 0 : 1);
-        kern<<<grid, kMetricWarps * 32, smem, h->stream>>>(a);
+        kern<<<grid, kMetricThreads, smem, h->stream>>>(a);
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -271,7 +271,7 @@ MetricArgs metric_args(rmhmc_handle* h, int64_t C, const double* theta, double* 
                        double* loglik_out, double* cbuf) {
     MetricArgs a{};
     a.x = h->x_pad; a.pair_tab = h->pair_tab; a.theta = theta;
-    a.g_out = g_out; a.grad_out = grad_out; a.loglik_out = loglik_out; a.cbuf = cbuf; a.skip = nullptr;
+    a.g_out = g_out; a.grad_out = grad_out; a.loglik_out = loglik_out; a.cbuf = cbuf; a.extra_tile = h->extra_tile;
     a.n_chains = (int)C; a.n_rows = (int)h->n_rows; a.n_rows_pad = h->n_rows_pad;
     a.dim = h->dim; a.xs = h->xs; a.p2 = h->p2; a.p2p = h->p2p; a.alpha_inv = 1.0 / h->alpha;
     return a;
@@ -562,7 +562,13 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
     h->n_rows_pad = pad_up((int)n_rows, 32);
     h->p2 = num_pairs(dim); h->p2p = pad_up(h->p2, 8);
     h->p3 = num_triples(dim); h->p3p = pad_up(h->p3, 8);
-    h->nt = (h->p2p / 8 + kMetricWarps - 1) / kMetricWarps;
+    {
+        // packed-column tiles per G-warp; a single left-over tile is split over chain tiles instead
+        int tiles = h->p2p / 8;
+        if (tiles % 4 == 1 && tiles > 1) { h->extra_tile = tiles - 1; tiles -= 1; }
+        else h->extra_tile = -1;
+        h->nt = (tiles + kMetricGWarps - 1) / kMetricGWarps;
+    }
 
     // index tables
     std::vector<uchar2> pair_tab(h->p2p, make_uchar2(0, 0));

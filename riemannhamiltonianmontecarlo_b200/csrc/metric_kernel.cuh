@@ -19,8 +19,10 @@ namespace rmhmc {
 
 constexpr int kMetricChains = 32;    // chains per CTA
 constexpr int kMetricRows = 32;      // design-matrix rows per staged block
-constexpr int kMetricWarps = 8;
-constexpr int kMetricStages = 3;
+constexpr int kMetricGWarps = 8;     // warps accumulating G (and X^T r); 16 was measured slower (more A-fragment traffic)
+constexpr int kMetricFWarps = 4;     // warps producing f = X theta and the logistic terms one block ahead
+constexpr int kMetricThreads = (kMetricGWarps + kMetricFWarps) * 32;
+constexpr int kMetricStages = 4;     // X ring depth
 constexpr int kMetricVS = kMetricRows + 4;   // smem stride of the V/R tiles (4*odd)
 
 struct MetricArgs {
@@ -31,53 +33,95 @@ struct MetricArgs {
     double* grad_out;         // [C][D]    (closing) X^T (t - p)
     double* loglik_out;       // [C]       (closing)
     double* cbuf;             // [C][Np]   (closing)
-    const unsigned char* skip;// [C] or null: chains whose outputs nobody will read
     int n_chains, n_rows, n_rows_pad, dim, xs, p2, p2p;
+    int extra_tile;           // n-tile split over the chain tiles of G-warps 0..3, or -1
     double alpha_inv;
 };
 
 __host__ inline size_t metric_smem_bytes(int xs) {
     size_t b = 0;
     b += (size_t)kMetricStages * kMetricRows * xs * 8;  // X ring
+    b += 4 * (size_t)kMetricChains * kMetricVS * 8;     // V and R tiles, double buffered
     b += (size_t)kMetricChains * xs * 8;                // Theta tile
-    b += 2 * (size_t)kMetricChains * kMetricVS * 8;     // V and R tiles
-    b += (size_t)kMetricWarps * 8 * 8;                  // loglik partials
-    b += 64;                                            // mbarriers
+    b += (size_t)kMetricFWarps * 32 * 8;                // loglik partials
+    b += 256 * 8;                                       // exp table
+    b += 16 * 8;                                        // mbarriers
     return b;
 }
 
 #ifdef __CUDACC__
-// Logistic terms of one (chain, row) pair.  One exp; p and 1-p are both formed without
-// cancellation.  Overflow quirk of the reference kept: exp(f) overflows for f > ~709.78, which
-// makes its gradient NaN (inf/inf, rmhmc.py:100) and its log-likelihood -inf (rmhmc.py:168).
-__device__ __forceinline__ void logistic_terms(double f, double& v, double& om_minus_p, double& p_out,
-                                               double& e_out) {
-    double e = exp(-fabs(f));
-    double q = 1.0 / (1.0 + e);
-    double eq = e * q;
-    bool pos = f >= 0.0;
-    double p = pos ? q : eq;
-    double om = pos ? eq : q;     // 1 - p
-    v = eq * q;                   // p (1-p)
-    om_minus_p = om - p;          // 1 - 2p
-    p_out = p;
-    e_out = e;
+// ---------------------------------------------------------------- fast FP64 exp / reciprocal
+// The F-warps share the FP64 pipe with the DMMAs, so the logistic terms are kept short:
+//   exp(x), x <= 0:  x = (256 k + j) ln2/256 + r, |r| <= ln2/512;  e^x = 2^k * 2^(j/256) * P5(r)
+//                    (256-entry table in shared memory, degree-5 Taylor: truncation < 1e-20, ~1 ulp)
+//   1/y, y in [1,2]: rcp.approx.ftz.f64 (20-bit seed) + two Newton steps (~1 ulp)
+// instead of the libdevice exp() and IEEE division (~4x fewer FP64 instructions).
+__device__ __forceinline__ double exp_table_entry(int j) { return exp2((double)j * (1.0 / 256.0)); }
+
+__device__ __forceinline__ double fast_exp_nonpos(double x, const double* __restrict__ tab) {
+    const double kInv = 369.3299304675746271;           // 256 / ln 2
+    const double kHi = 0.00270760617331689;              // ln2/256, upper 32 bits (n * kHi is exact)
+    const double kLo = 7.453964567463233e-13;            // ln2/256 - kHi
+    const double kMagic = 6755399441055744.0;            // 1.5 * 2^52
+    double t = fma(x, kInv, kMagic);
+    int n = __double2loint(t);
+    double nf = t - kMagic;
+    double r = fma(nf, -kHi, x);
+    r = fma(nf, -kLo, r);
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    int k = n >> 8;
+    double y = p * tab[n & 255];
+    // y in [1, 4); scale by 2^k through the exponent field; below the normal range flush to zero
+    double out = __hiloint2double(__double2hiint(y) + (k << 20), __double2loint(y));
+    return (k < -1020 || !(x == x)) ? (x == x ? 0.0 : x) : out;
+}
+
+__device__ __forceinline__ double fast_rcp_1to2(double y) {
+    double q;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(y));
+    double e = fma(-y, q, 1.0);
+    q = fma(q, e, q);
+    e = fma(-y, q, 1.0);
+    q = fma(q, e, q);
+    return q;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
 // MODE 0: G only (position fixed-point iterates); 1: closing build (G, gradient, log-likelihood,
 // cbuf); 2: gradient and log-likelihood only (Euclidean HMC, hmc.py:52-53,60-61,65-66).
+//
+// Warp-specialised: 4 F-warps (one 8-row tile each, all 32 chains) compute f^T = Theta X^T on the
+// tensor cores, the logistic terms, and publish V (and R) for row block rb+1 while the 8 G-warps
+// accumulate G += V . KR2(X) for row block rb.  Everything is handed over through mbarriers
+// (X ring full/empty, V double buffer full/empty); there is no CTA-wide barrier in the main loop.
+// NT = packed-column tiles (8 columns) per G-warp (tile t belongs to warp t mod GW); when the tile
+// count is 1 mod 4 the last tile is split over the four chain tiles of G-warps 0..3 (a.extra_tile)
+// so that all four SM sub-partitions issue the same number of DMMAs.
 template <int NT, int MODE>
-__global__ void __launch_bounds__(kMetricWarps * 32, 1) k_metric(MetricArgs a) {
+__global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a) {
     constexpr bool CLOSING = MODE >= 1, WITH_G = MODE <= 1, WITH_C = MODE == 1;
     constexpr int MC = kMetricChains, NB = kMetricRows, VS = kMetricVS, ST = kMetricStages;
+    constexpr int GW = kMetricGWarps, FW = kMetricFWarps;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int xs = a.xs;
     double* xs_ring = reinterpret_cast<double*>(smem_raw);
-    double* th = xs_ring + (size_t)ST * NB * xs;
-    double* vs = th + (size_t)MC * xs;
-    double* rs = vs + (size_t)MC * VS;
-    double* ll_s = rs + (size_t)MC * VS;
-    uint64_t* full = reinterpret_cast<uint64_t*>(ll_s + kMetricWarps * 8);
+    double* v_buf = xs_ring + (size_t)ST * NB * xs;           // [2][MC][VS]
+    double* r_buf = v_buf + 2 * (size_t)MC * VS;              // [2][MC][VS]
+    double* ll_s = r_buf + 2 * (size_t)MC * VS;               // [FW][32]
+    double* exp_tab = ll_s + FW * 32;                         // [256] 2^(j/256)
+    double* th = exp_tab + 256;                               // [MC][xs] Theta tile, zero padded
+    uint64_t* bars = reinterpret_cast<uint64_t*>(th + (size_t)MC * xs);
+    uint64_t* x_full = bars;            // [ST]
+    uint64_t* x_empty = bars + ST;      // [ST]
+    uint64_t* v_full = bars + 2 * ST;   // [2]
+    uint64_t* v_empty = v_full + 2;     // [2]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int chain0 = blockIdx.x * MC;
@@ -86,170 +130,236 @@ __global__ void __launch_bounds__(kMetricWarps * 32, 1) k_metric(MetricArgs a) {
     const uint32_t stage_bytes = (uint32_t)(NB * xs * 8);
 
     if (tid == 0) {
-        for (int s = 0; s < ST; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < ST; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], GW + FW); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&v_full[s], FW); mbar_init(&v_empty[s], GW); }
         mbar_fence_init();
     }
-    // Theta tile, zero padded (pad columns multiply the staged label column by zero)
-    for (int i = tid; i < MC * xs; i += blockDim.x) {
+    if (tid < 256) exp_tab[tid] = exp_table_entry(tid);
+    // Theta tile, zero padded (pad columns meet the staged label column and must contribute 0)
+    for (int i = tid; i < MC * xs; i += kMetricThreads) {
         int m = i / xs, d = i - m * xs, c = chain0 + m;
         th[i] = (c < a.n_chains && d < a.dim) ? a.theta[(size_t)c * a.dim + d] : 0.0;
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int s = 0; s < ST && s < n_blocks; ++s) {
-            mbar_expect_tx(&full[s], stage_bytes);
-            tma_bulk_g2s(xs_ring + (size_t)s * NB * xs, a.x + (size_t)s * NB * xs, stage_bytes, &full[s]);
-        }
-    }
 
-    // columns owned by this warp: n-tiles warp, warp+8, ...
-    const int n_tiles = a.p2p / 8;
-    int col_a[NT], col_b[NT];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        int nt = warp + j * kMetricWarps;
-        uchar2 ab = make_uchar2(0, 0);
-        if (nt < n_tiles) ab = a.pair_tab[nt * 8 + g];
-        col_a[j] = ab.x; col_b[j] = ab.y;
-    }
-    double acc[NT][4][2];
-#pragma unroll
-    for (int j = 0; j < NT; ++j)
-#pragma unroll
-        for (int m = 0; m < 4; ++m) acc[j][m][0] = acc[j][m][1] = 0.0;
-    // closing: gradient tiles (mt, dt) = flattened index warp, warp+8 over 4 x ceil(D/8)
-    const int d_tiles = (a.dim + 7) / 8;
-    double gacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-    double ll_acc = 0.0;
-
-    const int mt1 = warp & 3;                // chain tile of this warp's f tiles
-    const int k_steps_f = (a.dim + 3) / 4;
-    const int tcol = xs - 1;                 // label column
-
-    for (int rb = 0; rb < n_blocks; ++rb) {
-        const int stage = rb % ST;
-        const uint32_t parity = (uint32_t)((rb / ST) & 1);
-        mbar_wait(&full[stage], parity);
-        const double* xb = xs_ring + (size_t)stage * NB * xs;
-
-        // ---- phase 1: f^T tiles and the logistic terms
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int rt = (warp >> 2) + 2 * h;          // row tile 0..3
-            double f0 = 0.0, f1 = 0.0;
-            const double* ta = th + (size_t)(mt1 * 8 + g) * xs + q;
-            const double* xb_ = xb + (size_t)(rt * 8 + g) * xs + q;
-            for (int ks = 0; ks < k_steps_f; ++ks) dmma884(f0, f1, ta[ks * 4], xb_[ks * 4]);
-            const int r_local = rt * 8 + 2 * q;
-            double vv[2], rr[2], cc[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                double f = j ? f1 : f0;
-                double v, omp, p, e;
-                logistic_terms(f, v, omp, p, e);
-                vv[j] = v;
-                if (CLOSING) {
-                    double t = xb[(size_t)(r_local + j) * xs + tcol];
-                    bool ovf = f > 709.782712893384;
-                    rr[j] = ovf ? __longlong_as_double(0x7ff8000000000000LL) : t - p;
-                    cc[j] = WITH_C ? v * omp : 0.0;
-                    int row = rb * NB + r_local + j;
-                    if (row < a.n_rows) {
-                        double l1pe = ovf ? __longlong_as_double(0x7ff0000000000000LL) : fmax(f, 0.0) + log1p(e);
-                        ll_acc += t * f - l1pe;
-                    }
-                }
-            }
-            const int m_local = mt1 * 8 + g;
-            if (WITH_G)
-                *reinterpret_cast<double2*>(vs + (size_t)m_local * VS + r_local) = make_double2(vv[0], vv[1]);
-            if (CLOSING)
-                *reinterpret_cast<double2*>(rs + (size_t)m_local * VS + r_local) = make_double2(rr[0], rr[1]);
-            if (WITH_C) {
-                int c = chain0 + m_local;
-                if (c < a.n_chains)
-                    *reinterpret_cast<double2*>(a.cbuf + (size_t)c * a.n_rows_pad + rb * NB + r_local) =
-                        make_double2(cc[0], cc[1]);
+    if (warp >= GW) {
+        // =================================================================== F-warps
+        const int fw = warp - GW;               // row tile of this warp inside every block
+        if (fw == 0 && lane == 0) {
+            for (int s = 0; s < ST && s < n_blocks; ++s) {
+                mbar_expect_tx(&x_full[s], stage_bytes);
+                tma_bulk_g2s(xs_ring + (size_t)s * NB * xs, a.x + (size_t)s * NB * xs, stage_bytes, &x_full[s]);
             }
         }
-        __syncthreads();
-
-        // ---- phase 2: G += V . KR2(X) (and X^T r) over the 32 staged rows
-#pragma unroll 2
-        for (int ks = 0; ks < NB / 4; ++ks) {
-            const double* xr = xb + (size_t)(ks * 4 + q) * xs;
-            if (WITH_G) {
-                double af[4];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) af[m] = vs[(size_t)(m * 8 + g) * VS + ks * 4 + q];
-#pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    double b = xr[col_a[j]] * xr[col_b[j]];
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) dmma884(acc[j][m][0], acc[j][m][1], af[m], b);
-                }
+        const int k_steps_f = (a.dim + 3) / 4;
+        double ll_acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const int tcol = xs - 1;
+        for (int rb = 0; rb < n_blocks; ++rb) {
+            const int stage = rb % ST, buf = rb & 1;
+            // refill the stage freed two blocks ago (the G-warps have released it: see v_empty below)
+            if (rb >= 2) mbar_wait(&v_empty[buf], (uint32_t)(((rb - 2) >> 1) & 1));
+            if (fw == 0 && lane == 0 && rb >= 2 && rb + ST - 2 < n_blocks) {
+                const int nb = rb + ST - 2, ns = nb % ST;
+                mbar_wait(&x_empty[ns], (uint32_t)(((nb / ST) - 1) & 1));
+                mbar_expect_tx(&x_full[ns], stage_bytes);
+                tma_bulk_g2s(xs_ring + (size_t)ns * NB * xs, a.x + (size_t)nb * NB * xs, stage_bytes, &x_full[ns]);
             }
+            mbar_wait(&x_full[stage], (uint32_t)((rb / ST) & 1));
+            const double* xb = xs_ring + (size_t)stage * NB * xs;
+            double f[4][2];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) f[m][0] = f[m][1] = 0.0;
+            const double* xrow = xb + (size_t)(fw * 8 + g) * xs + q;
+            const double* trow = th + (size_t)g * xs + q;
+            for (int ks = 0; ks < k_steps_f; ++ks) {
+                double bx = xrow[ks * 4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) dmma884(f[m][0], f[m][1], trow[(size_t)m * 8 * xs + ks * 4], bx);
+            }
+            const int r_local = fw * 8 + 2 * q;
+            double t0 = 0.0, t1 = 0.0;
             if (CLOSING) {
+                t0 = xb[(size_t)r_local * xs + tcol];
+                t1 = xb[(size_t)(r_local + 1) * xs + tcol];
+            }
+            double* vdst = v_buf + (size_t)buf * MC * VS;
+            double* rdst = r_buf + (size_t)buf * MC * VS;
+            // the 8 (chain, row) pairs of this lane, evaluated in lock-step for instruction-level parallelism
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    int tix = warp + h * kMetricWarps;
-                    int mt = tix & 3, dt = tix >> 2;
-                    if (dt < d_tiles) {
-                        double ar = rs[(size_t)(mt * 8 + g) * VS + ks * 4 + q];
-                        int dcol = dt * 8 + g;
-                        double b = dcol < a.dim ? xr[dcol] : 0.0;
-                        dmma884(gacc[h][0], gacc[h][1], ar, b);
+            for (int half = 0; half < 2; ++half) {
+            double ev[4], eq[4], qq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ev[i] = fast_exp_nonpos(-fabs(f[2 * half + (i >> 1)][i & 1]), exp_tab);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qq[i] = fast_rcp_1to2(1.0 + ev[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) eq[i] = ev[i] * qq[i];
+#pragma unroll
+            for (int mm = 0; mm < 2; ++mm) {
+                const int m = 2 * half + mm;
+                double vv[2], rr[2], cc[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int i = 2 * mm + j;
+                    double fv = f[m][j];
+                    bool pos = fv >= 0.0;
+                    double p = pos ? qq[i] : eq[i];
+                    double om = pos ? eq[i] : qq[i];          // 1 - p
+                    vv[j] = eq[i] * qq[i];                    // p (1 - p)
+                    if (CLOSING) {
+                        double t = j ? t1 : t0;
+                        bool ovf = fv > 709.782712893384;
+                        rr[j] = ovf ? __longlong_as_double(0x7ff8000000000000LL) : t - p;
+                        cc[j] = WITH_C ? vv[j] * (om - p) : 0.0;
+                        int row = rb * NB + r_local + j;
+                        if (row < a.n_rows) {
+                            double l1pe = ovf ? __longlong_as_double(0x7ff0000000000000LL) : fmax(fv, 0.0) + log1p(ev[i]);
+                            ll_acc[m] += t * fv - l1pe;
+                        }
+                    }
+                }
+                const int m_local = m * 8 + g;
+                if (WITH_G) *reinterpret_cast<double2*>(vdst + (size_t)m_local * VS + r_local) = make_double2(vv[0], vv[1]);
+                if (CLOSING) *reinterpret_cast<double2*>(rdst + (size_t)m_local * VS + r_local) = make_double2(rr[0], rr[1]);
+                if (WITH_C) {
+                    int c = chain0 + m_local;
+                    if (c < a.n_chains)
+                        *reinterpret_cast<double2*>(a.cbuf + (size_t)c * a.n_rows_pad + rb * NB + r_local) =
+                            make_double2(cc[0], cc[1]);
+                }
+            }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&v_full[buf]);
+                mbar_arrive(&x_empty[stage]);
+            }
+        }
+        if (CLOSING) {
+            // log-likelihood: fixed-order reduction (q lanes, then the four F-warps)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                double v = ll_acc[m];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (q == 0) ll_s[fw * 32 + m * 8 + g] = v;
+            }
+        }
+    } else {
+        // =================================================================== G-warps
+        const int gw = warp;
+        const int n_tiles = a.p2p / 8;
+        int col_a[NT], col_b[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            int nt = gw + j * GW;
+            uchar2 ab = make_uchar2(0, 0);
+            if (nt < n_tiles && nt != a.extra_tile) ab = a.pair_tab[nt * 8 + g];
+            col_a[j] = ab.x; col_b[j] = ab.y;
+        }
+        const bool has_extra = WITH_G && a.extra_tile >= 0 && gw < 4;
+        int ex_a = 0, ex_b = 0;
+        if (has_extra) { uchar2 ab = a.pair_tab[a.extra_tile * 8 + g]; ex_a = ab.x; ex_b = ab.y; }
+        double acc[NT][4][2];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[j][m][0] = acc[j][m][1] = 0.0;
+        double eacc[2] = {0.0, 0.0};
+        // closing: gradient tiles (chain tile mt, parameter tile dt) = flattened index gw, gw + GW, ...
+        constexpr int GT = 16 / GW;
+        const int d_tiles = (a.dim + 7) / 8;
+        double gacc[GT][2];
+#pragma unroll
+        for (int h = 0; h < GT; ++h) gacc[h][0] = gacc[h][1] = 0.0;
+
+        for (int rb = 0; rb < n_blocks; ++rb) {
+            const int stage = rb % ST, buf = rb & 1;
+            mbar_wait(&x_full[stage], (uint32_t)((rb / ST) & 1));
+            mbar_wait(&v_full[buf], (uint32_t)((rb >> 1) & 1));
+            const double* xb = xs_ring + (size_t)stage * NB * xs;
+            const double* vs = v_buf + (size_t)buf * MC * VS;
+            const double* rs = r_buf + (size_t)buf * MC * VS;
+#pragma unroll 2
+            for (int ks = 0; ks < NB / 4; ++ks) {
+                const double* xr = xb + (size_t)(ks * 4 + q) * xs;
+                if (WITH_G) {
+                    double af[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) af[m] = vs[(size_t)(m * 8 + g) * VS + ks * 4 + q];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        double b = xr[col_a[j]] * xr[col_b[j]];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) dmma884(acc[j][m][0], acc[j][m][1], af[m], b);
+                    }
+                    if (has_extra) {
+                        double b = xr[ex_a] * xr[ex_b];
+                        double asel = gw == 0 ? af[0] : (gw == 1 ? af[1] : (gw == 2 ? af[2] : af[3]));
+                        dmma884(eacc[0], eacc[1], asel, b);
+                    }
+                }
+                if (CLOSING) {
+#pragma unroll
+                    for (int h = 0; h < GT; ++h) {
+                        int tix = gw + h * GW;
+                        int mt = tix & 3, dt = tix >> 2;
+                        if (dt < d_tiles) {
+                            double ar = rs[(size_t)(mt * 8 + g) * VS + ks * 4 + q];
+                            int dcol = dt * 8 + g;
+                            double b = dcol < a.dim ? xr[dcol] : 0.0;
+                            dmma884(gacc[h][0], gacc[h][1], ar, b);
+                        }
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&v_empty[buf]);
+                mbar_arrive(&x_empty[stage]);
+            }
         }
-        __syncthreads();
-        if (tid == 0 && rb + ST < n_blocks) {
-            mbar_expect_tx(&full[stage], stage_bytes);
-            tma_bulk_g2s(xs_ring + (size_t)stage * NB * xs, a.x + (size_t)(rb + ST) * NB * xs, stage_bytes,
-                         &full[stage]);
-        }
-    }
 
-    // ---- epilogue: packed G (+ I/alpha on the diagonal pairs)
-#pragma unroll
-    for (int j = 0; j < (WITH_G ? NT : 0); ++j) {
-        int nt = warp + j * kMetricWarps;
-        if (nt >= n_tiles) continue;
-        int col = nt * 8 + 2 * q;
-        uchar2 ab0 = a.pair_tab[col], ab1 = a.pair_tab[col + 1];
-        double d0 = (col < a.p2 && ab0.x == ab0.y) ? a.alpha_inv : 0.0;
-        double d1 = (col + 1 < a.p2 && ab1.x == ab1.y) ? a.alpha_inv : 0.0;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
+        // ---- epilogue: packed G (+ I/alpha on the diagonal pairs)
+        auto store_tile = [&](int nt, int m, double o0, double o1) {
+            int col = nt * 8 + 2 * q;
+            uchar2 ab0 = a.pair_tab[col], ab1 = a.pair_tab[col + 1];
+            double d0 = (col < a.p2 && ab0.x == ab0.y) ? a.alpha_inv : 0.0;
+            double d1 = (col + 1 < a.p2 && ab1.x == ab1.y) ? a.alpha_inv : 0.0;
             int c = chain0 + m * 8 + g;
-            if (c < a.n_chains) {
-                double o0 = col < a.p2 ? acc[j][m][0] + d0 : 0.0;
-                double o1 = col + 1 < a.p2 ? acc[j][m][1] + d1 : 0.0;
-                *reinterpret_cast<double2*>(a.g_out + (size_t)c * a.p2p + col) = make_double2(o0, o1);
+            if (c < a.n_chains)
+                *reinterpret_cast<double2*>(a.g_out + (size_t)c * a.p2p + col) =
+                    make_double2(col < a.p2 ? o0 + d0 : 0.0, col + 1 < a.p2 ? o1 + d1 : 0.0);
+        };
+        if (WITH_G) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                int nt = gw + j * GW;
+                if (nt >= n_tiles || nt == a.extra_tile) continue;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) store_tile(nt, m, acc[j][m][0], acc[j][m][1]);
+            }
+            if (has_extra) store_tile(a.extra_tile, gw, eacc[0], eacc[1]);
+        }
+        if (CLOSING) {
+#pragma unroll
+            for (int h = 0; h < GT; ++h) {
+                int tix = gw + h * GW;
+                int mt = tix & 3, dt = tix >> 2;
+                int c = chain0 + mt * 8 + g;
+                if (dt < d_tiles && c < a.n_chains) {
+                    int dcol = dt * 8 + 2 * q;
+                    if (dcol < a.dim) a.grad_out[(size_t)c * a.dim + dcol] = gacc[h][0];
+                    if (dcol + 1 < a.dim) a.grad_out[(size_t)c * a.dim + dcol + 1] = gacc[h][1];
+                }
             }
         }
     }
     if (CLOSING) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int tix = warp + h * kMetricWarps;
-            int mt = tix & 3, dt = tix >> 2;
-            int c = chain0 + mt * 8 + g;
-            if (dt < d_tiles && c < a.n_chains) {
-                int dcol = dt * 8 + 2 * q;
-                if (dcol < a.dim) a.grad_out[(size_t)c * a.dim + dcol] = gacc[h][0];
-                if (dcol + 1 < a.dim) a.grad_out[(size_t)c * a.dim + dcol + 1] = gacc[h][1];
-            }
-        }
-        // log-likelihood: fixed-order reduction (q lanes, then the two warps sharing a chain tile)
-        ll_acc += __shfl_xor_sync(0xffffffffu, ll_acc, 1);
-        ll_acc += __shfl_xor_sync(0xffffffffu, ll_acc, 2);
-        if (q == 0) ll_s[warp * 8 + g] = ll_acc;
         __syncthreads();
         if (tid < MC) {
-            int mt = tid >> 3, gg = tid & 7, c = chain0 + tid;
-            if (c < a.n_chains) a.loglik_out[c] = ll_s[mt * 8 + gg] + ll_s[(mt + 4) * 8 + gg];
+            int c = chain0 + tid;
+            if (c < a.n_chains) a.loglik_out[c] = (ll_s[tid] + ll_s[32 + tid]) + (ll_s[64 + tid] + ll_s[96 + tid]);
         }
     }
 }
