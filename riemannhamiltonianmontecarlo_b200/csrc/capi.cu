@@ -48,6 +48,7 @@ struct rmhmc_handle {
     bool configured = false, rng_set = false;
     int64_t launches = 0;
     bool profiling = false;
+    bool fuse_epilogues = false;
     ProfSlot prof[5];
     mutable std::string err;
 };
@@ -239,11 +240,23 @@ void drain_profile(rmhmc_handle* h) {
 }
 
 // ------------------------------------------------------------------ kernel launch helpers
+FuseArgs fuse_args(rmhmc_handle* h, int mode, int is_last, int init) {
+    FuseArgs f{};
+    f.mode = mode; f.is_last = is_last; f.init = init;
+    f.step_size = h->P.step_size; f.it_stop = h->P.it_stop;
+    const ChainArrays& S = h->S;
+    f.mom = S.mom; f.theta = S.theta; f.u0 = S.u0; f.theta_w = S.theta_w; f.dir = S.dir; f.step = S.step;
+    f.cur = S.cur; f.iter = S.iter; f.nsteps = S.nsteps; f.renorm_pos = S.renorm_pos;
+    f.lfac = S.lfac; f.invg = S.invg; f.logdet = S.logdet;
+    f.slot_theta = h->P.slot_theta; f.slot_invg = h->P.slot_invg; f.slot_scalar = h->P.slot_scalar;
+    return f;
+}
+
 template <int MODE>
-int launch_metric(rmhmc_handle* h, const MetricArgs& a) {
-    size_t smem = metric_smem_bytes(h->xs);
+int launch_metric(rmhmc_handle* h, const MetricArgs& a, const FuseArgs& fz = FuseArgs{}) {
+    size_t smem = metric_smem_bytes(h->xs, h->p2p, fz.mode != kFuseNone);
     unsigned grid = blocks_for(a.n_chains, kMetricChains);
-    void (*kern)(MetricArgs) = nullptr;
+    void (*kern)(MetricArgs, FuseArgs) = nullptr;
     int nt = MODE == 2 ? 1 : h->nt;
     switch (nt) {
         case 1: kern = k_metric<1, MODE>; break;
@@ -260,7 +273,7 @@ int launch_metric(rmhmc_handle* h, const MetricArgs& a) {
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         Bracket b(h, MODE == 0 ? 0 : 1);
-        kern<<<grid, kMetricThreads, smem, h->stream>>>(a);
+        kern<<<grid, kMetricThreads, smem, h->stream>>>(a, fz);
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -445,18 +458,26 @@ int launch_seam_factor(rmhmc_handle* h, const EngineParams& P, int64_t C, const 
 int rmhmc_round_builds(rmhmc_handle* h) {
     const int64_t C = h->n_chains;
     ChainArrays& S = h->S;
+    // h->fuse_epilogues: do the per-chain solve / factorisation in the metric kernels' epilogues.  Measured
+    // SLOWER on B200 (metric 1.78 -> 2.95 ms per launch vs 0.62 ms for the stand-alone solve kernel at
+    // 65536 chains: 12 warps per SM of straight-line code are instruction-fetch bound while the tensor
+    // pipe idles), so it is off by default and kept for small chain counts / experiments.
+    const bool fuse = h->fuse_epilogues;
     for (int fi = 2; fi <= h->P.n_fixed; ++fi) {
+        const int last = fi == h->P.n_fixed ? 1 : 0;
         MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, nullptr, nullptr, nullptr);
-        int rc = launch_metric<0>(h, a);
+        int rc = fuse ? launch_metric<0>(h, a, fuse_args(h, kFuseSolve, last, 0)) : launch_metric<0>(h, a);
         if (rc) return rc;
-        rc = launch_solve(h, fi == h->P.n_fixed ? 1 : 0);
-        if (rc) return rc;
+        if (!fuse) {
+            rc = launch_solve(h, last);
+            if (rc) return rc;
+        }
     }
     MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, S.grad_tmp, S.loglik_tmp, S.cbuf);
-    int rc = launch_metric<1>(h, a);
+    int rc = fuse ? launch_metric<1>(h, a, fuse_args(h, kFuseFactor, 0, 0)) : launch_metric<1>(h, a);
     if (rc) return rc;
     rc = launch_tbuild(h, C, S.cbuf, S.tpack, S.cur, 1, h->P.slot_t);
-    if (rc) return rc;
+    if (rc || fuse) return rc;
     return launch_factor(h, 0);
 }
 

@@ -193,6 +193,84 @@ __device__ __forceinline__ void chol_inverse_regs(const double* Lsm, double* Msm
     __syncwarp();
 }
 
+// ---- variants working on a PACKED lower factor in shared memory (L[i][j], j <= i, stored at
+// pair_index(j, i)): used by the epilogues fused into the metric kernel, where the chain's packed
+// metric tile is overwritten in place by its factor.
+template <int DMAX>
+__device__ __forceinline__ void store_rows_packed(double* Lp, const double (&row)[DMAX], int D, int lane) {
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+        if (j < D && lane < D && j <= lane) Lp[pair_index(j, lane, D)] = row[j];
+    __syncwarp();
+}
+
+template <int DMAX>
+__device__ __forceinline__ double chol_solve_packed(const double (&row)[DMAX], const double* Lp, double dinv, int D,
+                                                    int lane, double b) {
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) {                    // forward: L y = b
+        if (k < D) {
+            double yk = __shfl_sync(kFull, b, k) * __shfl_sync(kFull, dinv, k);
+            if (lane == k) b = yk;
+            else if (lane > k) b = fma(-row[k], yk, b);
+        }
+    }
+    const int lbase = lane * D - lane * (lane - 1) / 2 - lane;      // pair_index(lane, k) = lbase + k
+#pragma unroll
+    for (int k = DMAX - 1; k >= 0; --k) {               // backward: L^T x = y
+        if (k < D) {
+            double xk = __shfl_sync(kFull, b, k) * __shfl_sync(kFull, dinv, k);
+            double lkj = lane < k ? Lp[lbase + k] : 0.0;
+            if (lane == k) b = xk;
+            else if (lane < k) b = fma(-lkj, xk, b);
+        }
+    }
+    return b;
+}
+
+// ig[b] = (L L^T)^-1 [lane][b] with L packed in Lp; Mp is a packed scratch of the same size.
+template <int DMAX>
+__device__ __forceinline__ void chol_inverse_packed(const double* Lp, double* Mp, double dinv, double (&ig)[DMAX],
+                                                    int D, int lane) {
+    double m[DMAX];
+#pragma unroll
+    for (int i = 0; i < DMAX; ++i) {
+        m[i] = 0.0;
+        if (i < D) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) {
+                double lik = Lp[k * D - k * (k - 1) / 2 + (i - k)];      // L[i][k], same address for all lanes
+                if (k & 1) s1 = fma(lik, m[k], s1);
+                else s0 = fma(lik, m[k], s0);
+            }
+            double di = __shfl_sync(kFull, dinv, i);
+            m[i] = (i == lane) ? di : (i > lane ? -(s0 + s1) * di : 0.0);
+        }
+    }
+    const int lbase = lane * D - lane * (lane - 1) / 2 - lane;
+#pragma unroll
+    for (int i = 0; i < DMAX; ++i)
+        if (i < D && lane < D && i >= lane) Mp[lbase + i] = m[i];          // M[i][lane]
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < DMAX; ++b) {
+        double s0 = 0.0, s1 = 0.0;
+        if (b < D) {
+            const int bbase = b * D - b * (b - 1) / 2 - b;
+#pragma unroll
+            for (int k = b; k < DMAX; ++k) {
+                if (k < D) {
+                    if (k & 1) s1 = fma(m[k], Mp[bbase + k], s1);          // M[k][b]
+                    else s0 = fma(m[k], Mp[bbase + k], s0);
+                }
+            }
+        }
+        ig[b] = s0 + s1;
+    }
+    __syncwarp();
+}
+
 template <int DMAX>
 __device__ __forceinline__ double matvec_regs(const double (&ig)[DMAX], int D, double x) {
     double y0 = 0.0, y1 = 0.0;

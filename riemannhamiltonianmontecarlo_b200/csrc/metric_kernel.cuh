@@ -13,6 +13,7 @@
 // element from two staged X values.  X row blocks arrive by 1-D bulk TMA (UBLKCP) into a
 // 3-stage mbarrier ring; V never leaves the SM.
 #pragma once
+#include "chain_kernels.cuh"
 #include "common.cuh"
 
 namespace rmhmc {
@@ -45,7 +46,33 @@ __host__ inline size_t metric_smem_bytes(int xs) {
     b += (size_t)kMetricChains * xs * 8;                // Theta tile
     b += (size_t)kMetricFWarps * 32 * 8;                // loglik partials
     b += 256 * 8;                                       // exp table
+    b += 256 * 8;                                       // log table (1/c_j, log c_j)
     b += 16 * 8;                                        // mbarriers
+    return b;
+}
+
+// Per-chain work fused into the kernel's epilogue (the chain tile's packed metric stays in shared
+// memory and is factored there by the CTA's 12 warps, one chain per warp at a time):
+//   kFuseSolve  (MODE 0): Cholesky solve G(theta_w) u = p and the position fixed-point update
+//                         theta_w <- theta + s eps/2 (u0 + u) (+ the ||theta|| > 10 hack on the last
+//                         iterate)                                            rmhmc.py:121-130
+//   kFuseFactor (MODE 1): L = chol(G), G^-1, 0.5 log|G| of the new position into the proposal slot
+//                         (slot `cur` when init)                              rmhmc.py:138,171
+enum { kFuseNone = 0, kFuseSolve = 1, kFuseFactor = 2 };
+struct FuseArgs {
+    int mode, is_last, init;
+    double step_size;
+    long long it_stop;
+    const double* mom; const double* theta; const double* u0; double* theta_w;
+    const int* dir; const int* step; const int* cur; const long long* iter; const int* nsteps;
+    int* renorm_pos;
+    double* lfac; double* invg; double* logdet;
+    size_t slot_theta, slot_invg, slot_scalar;
+};
+
+__host__ inline size_t metric_smem_bytes(int xs, int p2p, bool fused) {
+    size_t b = metric_smem_bytes(xs);
+    if (fused) b += (size_t)kMetricChains * p2p * 8;     // the chain tile's packed metric / factor
     return b;
 }
 
@@ -90,6 +117,28 @@ __device__ __forceinline__ double fast_rcp_1to2(double y) {
     return q;
 }
 
+// log(1 + e), e in [0, 1]:  y = 1 + e = c_j (1 + r), c_j = 1 + (j + 0.5)/128 from the top 7 mantissa
+// bits, |r| < 2^-8;  log y = log c_j + (r - r^2/2 + ... + r^7/7)   (truncation < 1e-20; absolute
+// error ~1e-16, the same as the reference's log(1 + exp(f)) which also rounds 1 + e first).
+__device__ __forceinline__ void log_table_entry(int j, double& inv_c, double& log_c) {
+    double c = 1.0 + ((double)j + 0.5) * (1.0 / 128.0);
+    inv_c = 1.0 / c;
+    log_c = log(c);
+}
+__device__ __forceinline__ double fast_log1p_01(double e, const double* __restrict__ tab) {
+    double y = 1.0 + e;
+    int j = (__double2hiint(y) >> 13) & 127;
+    if (y >= 2.0) j = 127;
+    double r = fma(y, tab[2 * j], -1.0);
+    double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = fma(p, r, 0.2);
+    p = fma(p, r, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    p = fma(p, r, 1.0);
+    return fma(p, r, tab[2 * j + 1]);
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -105,7 +154,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // count is 1 mod 4 the last tile is split over the four chain tiles of G-warps 0..3 (a.extra_tile)
 // so that all four SM sub-partitions issue the same number of DMMAs.
 template <int NT, int MODE>
-__global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a) {
+__global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, FuseArgs fz) {
     constexpr bool CLOSING = MODE >= 1, WITH_G = MODE <= 1, WITH_C = MODE == 1;
     constexpr int MC = kMetricChains, NB = kMetricRows, VS = kMetricVS, ST = kMetricStages;
     constexpr int GW = kMetricGWarps, FW = kMetricFWarps;
@@ -116,12 +165,14 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a) {
     double* r_buf = v_buf + 2 * (size_t)MC * VS;              // [2][MC][VS]
     double* ll_s = r_buf + 2 * (size_t)MC * VS;               // [FW][32]
     double* exp_tab = ll_s + FW * 32;                         // [256] 2^(j/256)
-    double* th = exp_tab + 256;                               // [MC][xs] Theta tile, zero padded
+    double* log_tab = exp_tab + 256;                          // [128][2] 1/c_j, log c_j
+    double* th = log_tab + 256;                               // [MC][xs] Theta tile, zero padded
     uint64_t* bars = reinterpret_cast<uint64_t*>(th + (size_t)MC * xs);
     uint64_t* x_full = bars;            // [ST]
     uint64_t* x_empty = bars + ST;      // [ST]
     uint64_t* v_full = bars + 2 * ST;   // [2]
     uint64_t* v_empty = v_full + 2;     // [2]
+    double* g_s = reinterpret_cast<double*>(bars + 16);   // [MC][P2p] packed metric tile (fused epilogues only)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int chain0 = blockIdx.x * MC;
@@ -135,6 +186,7 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a) {
         mbar_fence_init();
     }
     if (tid < 256) exp_tab[tid] = exp_table_entry(tid);
+    if (CLOSING && tid < 128) log_table_entry(tid, log_tab[2 * tid], log_tab[2 * tid + 1]);
     // Theta tile, zero padded (pad columns meet the staged label column and must contribute 0)
     for (int i = tid; i < MC * xs; i += kMetricThreads) {
         int m = i / xs, d = i - m * xs, c = chain0 + m;
@@ -213,7 +265,7 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a) {
                         cc[j] = WITH_C ? vv[j] * (om - p) : 0.0;
                         int row = rb * NB + r_local + j;
                         if (row < a.n_rows) {
-                            double l1pe = ovf ? __longlong_as_double(0x7ff0000000000000LL) : fmax(fv, 0.0) + log1p(ev[i]);
+                            double l1pe = ovf ? __longlong_as_double(0x7ff0000000000000LL) : fmax(fv, 0.0) + fast_log1p_01(ev[i], log_tab);
                             ll_acc[m] += t * fv - l1pe;
                         }
                     }
@@ -327,9 +379,11 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a) {
             double d0 = (col < a.p2 && ab0.x == ab0.y) ? a.alpha_inv : 0.0;
             double d1 = (col + 1 < a.p2 && ab1.x == ab1.y) ? a.alpha_inv : 0.0;
             int c = chain0 + m * 8 + g;
-            if (c < a.n_chains)
-                *reinterpret_cast<double2*>(a.g_out + (size_t)c * a.p2p + col) =
-                    make_double2(col < a.p2 ? o0 + d0 : 0.0, col + 1 < a.p2 ? o1 + d1 : 0.0);
+            double2 val = make_double2(col < a.p2 ? o0 + d0 : 0.0, col + 1 < a.p2 ? o1 + d1 : 0.0);
+            if (fz.mode != kFuseNone)
+                *reinterpret_cast<double2*>(g_s + (size_t)(m * 8 + g) * a.p2p + col) = val;
+            else if (c < a.n_chains)
+                *reinterpret_cast<double2*>(a.g_out + (size_t)c * a.p2p + col) = val;
         };
         if (WITH_G) {
 #pragma unroll
@@ -355,11 +409,51 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a) {
             }
         }
     }
-    if (CLOSING) {
-        __syncthreads();
-        if (tid < MC) {
-            int c = chain0 + tid;
-            if (c < a.n_chains) a.loglik_out[c] = (ll_s[tid] + ll_s[32 + tid]) + (ll_s[64 + tid] + ll_s[96 + tid]);
+    if (CLOSING || (WITH_G && fz.mode != kFuseNone)) __syncthreads();
+    if (CLOSING && tid < MC) {
+        int c = chain0 + tid;
+        if (c < a.n_chains) a.loglik_out[c] = (ll_s[tid] + ll_s[32 + tid]) + (ll_s[64 + tid] + ll_s[96 + tid]);
+    }
+    if (WITH_G && fz.mode != kFuseNone) {
+        // ---- fused per-chain epilogue: every warp takes chains warp, warp + 12, ... of the tile
+        constexpr int DMAX = NT <= 2 ? 16 : 32;          // NT <= 2  <=>  at most 16 parameters
+        const int D = a.dim;
+        double* m_scratch = xs_ring + (size_t)warp * a.p2p;      // X ring / V buffers are dead by now
+        for (int ci = warp; ci < MC; ci += GW + FW) {
+            const int c = chain0 + ci;
+            if (c >= a.n_chains) continue;
+            if (!fz.init && (fz.iter[c] >= fz.it_stop || fz.nsteps[c] <= 0)) continue;
+            double* gp = g_s + (size_t)ci * a.p2p;
+            double lrow[DMAX], dinv;
+            load_packed_rows<DMAX>(gp, lrow, D, lane);
+            __syncwarp();
+            double logdet = chol_regs<DMAX>(lrow, D, lane, dinv);
+            store_rows_packed<DMAX>(gp, lrow, D, lane);
+            const bool live = lane < D;
+            if (fz.mode == kFuseSolve) {
+                const int cur = fz.cur[c];
+                const int in_slot = fz.step[c] == 0 ? cur : 1 - cur;
+                double p = live ? fz.mom[(size_t)c * D + lane] : 0.0;
+                double w = live ? fz.theta[in_slot * fz.slot_theta + (size_t)c * D + lane] : 0.0;
+                double u0 = live ? fz.u0[(size_t)c * D + lane] : 0.0;
+                double u = chol_solve_packed<DMAX>(lrow, gp, dinv, D, lane, p);          // rmhmc.py:121
+                double pw = w + (fz.dir[c] * fz.step_size / 2) * (u0 + u);                 // rmhmc.py:122
+                if (fz.is_last) pw = clamp_position(pw, lane, D, &fz.renorm_pos[c]);
+                if (live) fz.theta_w[(size_t)c * D + lane] = pw;
+            } else {
+                const int out = fz.init ? fz.cur[c] : 1 - fz.cur[c];
+                if (lane == 0) fz.logdet[out * fz.slot_scalar + c] = logdet;
+                double* ld = fz.lfac + out * fz.slot_invg + (size_t)c * D * D;
+#pragma unroll
+                for (int j = 0; j < DMAX; ++j)
+                    if (j < D && live) ld[lane * D + j] = j <= lane ? lrow[j] : 0.0;
+                double ig[DMAX];
+                chol_inverse_packed<DMAX>(gp, m_scratch, dinv, ig, D, lane);
+                double* igd = fz.invg + out * fz.slot_invg + (size_t)c * D * D;
+#pragma unroll
+                for (int b = 0; b < DMAX; ++b)
+                    if (b < D && live) igd[lane * D + b] = ig[b];
+            }
         }
     }
 }
