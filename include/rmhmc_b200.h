@@ -15,7 +15,8 @@
  *     call returns without synchronising unless stated;
  *   - one handle per (device, stream); a handle is not re-entrant, different handles may be used
  *     from different host threads;
- *   - D (number of parameters incl. intercept) must be <= 32 in this version.
+ *   - D (number of parameters incl. intercept) must be <= 128: D <= 32 runs the warp-per-chain
+ *     kernels the benchmark configurations use, 32 < D <= 128 a CTA-per-chain path.
  *
  * Library: librmhmc_b200.so, built for sm_100a only.  There is no CPU fallback.
  */

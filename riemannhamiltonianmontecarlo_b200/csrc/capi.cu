@@ -2,6 +2,7 @@
 // Host side only orchestrates; all arithmetic is in the kernels of this directory.
 #include "../../include/rmhmc_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -31,12 +32,14 @@ struct rmhmc_handle {
     cudaStream_t stream = nullptr;
     int64_t n_rows = 0;
     int dim = 0, xs = 0, n_rows_pad = 0, p2 = 0, p2p = 0, p3 = 0, p3p = 0, nt = 0, extra_tile = -1;
+    int main_tiles = 0, col_ctas = 1;      // metric kernel: tiles spread over G-warps, column CTAs per chain tile
     double alpha = 100.0;
     // data set
     double* x_pad = nullptr;
     uchar2* pair_tab = nullptr;
     uchar4* tri_tab = nullptr;
     unsigned short* tidx = nullptr;
+    unsigned int* tidx32 = nullptr;
     unsigned char *pair_a = nullptr, *pair_b = nullptr;
     // chains
     int64_t n_chains = 0, c_pad = 0;
@@ -178,6 +181,37 @@ __global__ void __launch_bounds__(32) k_seam_factor(EngineParams P, const double
     }
 }
 
+// D > 32 variant: one CTA per chain
+__global__ void __launch_bounds__(kBigThreads) k_seam_factor_big(EngineParams P, const double* __restrict__ gp,
+                                                                 const double* __restrict__ tp, double* L, double* Ginv,
+                                                                 double* logdet, double* trace) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int c = blockIdx.x, tid = threadIdx.x, D = P.dim, DS = P.ds;
+    double* A = reinterpret_cast<double*>(smem_raw);
+    double* B = A + D * DS;
+    double* outv = B + D * DS;
+    double* q = outv + kMaxDimBig;
+    unpack_sym_cta(gp + (size_t)c * P.p2p, A, D, DS);
+    double ld = chol_cta(A, D, DS);
+    if (logdet && tid == 0) logdet[c] = ld;
+    if (L)
+        for (int idx = tid; idx < D * D; idx += kBigThreads) L[(size_t)c * D * D + idx] = A[(idx / D) * DS + (idx % D)];
+    if (Ginv || trace) {
+        chol_inverse_cta(A, B, D, DS);
+        if (Ginv)
+            for (int idx = tid; idx < D * D; idx += kBigThreads) Ginv[(size_t)c * D * D + idx] = B[(idx / D) * DS + (idx % D)];
+    }
+    if (trace) {
+        for (int p = tid; p < P.p2; p += kBigThreads) {
+            int pa = P.pair_a[p], pb = P.pair_b[p];
+            q[p] = (pa == pb ? 1.0 : 2.0) * B[pa * DS + pb];
+        }
+        __syncthreads();
+        tensor_contract_big(tp + (size_t)c * P.p3p, q, P.tidx32, outv, D, P.p2);
+        if (tid < D) trace[(size_t)c * D + tid] = outv[tid];
+    }
+}
+
 __global__ void k_remaining(const long long* __restrict__ iter, int64_t C, long long it_stop, long long* out) {
     long long m = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < C; i += (int64_t)gridDim.x * blockDim.x) {
@@ -255,7 +289,8 @@ FuseArgs fuse_args(rmhmc_handle* h, int mode, int is_last, int init) {
 template <int MODE>
 int launch_metric(rmhmc_handle* h, const MetricArgs& a, const FuseArgs& fz = FuseArgs{}) {
     size_t smem = metric_smem_bytes(h->xs, h->p2p, fz.mode != kFuseNone);
-    unsigned grid = blocks_for(a.n_chains, kMetricChains);
+    dim3 grid(blocks_for(a.n_chains, kMetricChains), MODE == 2 ? (unsigned)((h->dim + 31) / 32) : (unsigned)h->col_ctas);
+    if (fz.mode != kFuseNone && grid.y != 1) return fail(h, RMHMC_E_UNSUPPORTED, "fused epilogues need a single column CTA");
     void (*kern)(MetricArgs, FuseArgs) = nullptr;
     int nt = MODE == 2 ? 1 : h->nt;
     switch (nt) {
@@ -285,6 +320,7 @@ MetricArgs metric_args(rmhmc_handle* h, int64_t C, const double* theta, double* 
     MetricArgs a{};
     a.x = h->x_pad; a.pair_tab = h->pair_tab; a.theta = theta;
     a.g_out = g_out; a.grad_out = grad_out; a.loglik_out = loglik_out; a.cbuf = cbuf; a.extra_tile = h->extra_tile;
+    a.tiles_per_cta = kMetricGWarps * h->nt; a.n_main_tiles = h->main_tiles;
     a.n_chains = (int)C; a.n_rows = (int)h->n_rows; a.n_rows_pad = h->n_rows_pad;
     a.dim = h->dim; a.xs = h->xs; a.p2 = h->p2; a.p2p = h->p2p; a.alpha_inv = 1.0 / h->alpha;
     return a;
@@ -329,7 +365,7 @@ void fill_engine_params(rmhmc_handle* h) {
     EngineParams& P = h->P;
     P.n_chains = (int)h->n_chains; P.dim = h->dim; P.ds = h->dim | 1;
     P.p2 = h->p2; P.p2p = h->p2p; P.p3 = h->p3; P.p3p = h->p3p; P.n_rows_pad = h->n_rows_pad;
-    P.alpha = h->alpha; P.tidx = h->tidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
+    P.alpha = h->alpha; P.tidx = h->tidx; P.tidx32 = h->tidx32; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
     size_t C = (size_t)h->n_chains;
     P.slot_theta = C * h->dim; P.slot_scalar = C;
     P.slot_invg = C * h->dim * h->dim; P.slot_t = C * h->p3p;
@@ -381,12 +417,23 @@ int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
 int dmax_variant(const rmhmc_handle* h) { return h->dim <= 16 ? 0 : 1; }
 int nch_variant(const rmhmc_handle* h) { return h->p2 <= 128 ? 0 : (h->p2 <= 352 ? 1 : 2); }
 
+bool is_big(const rmhmc_handle* h) { return h->dim > kMaxDimWarp; }
+
 int set_chain_smem_attrs(rmhmc_handle* h) {
-    int turn = (int)turn_smem_bytes(h->dim, h->p3p), seam = (int)seam_smem_bytes(h->dim, h->p3p, true);
+    if (is_big(h)) {
+        int turn = (int)turn_smem_bytes(h->dim, h->p2, h->p3p, true);
+        int seam = (int)(big_mat_smem_bytes(h->dim, 2) + (size_t)h->p2 * 8);
+        CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
+        CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor_big, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
+        CUDA_TRY(h, cudaFuncSetAttribute(k_chain_factor_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_mat_smem_bytes(h->dim, 2)));
+        CUDA_TRY(h, cudaFuncSetAttribute(k_chain_solve_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_mat_smem_bytes(h->dim, 1)));
+        return RMHMC_OK;
+    }
+    int turn = (int)turn_smem_bytes(h->dim, h->p2, h->p3p, false), seam = (int)seam_smem_bytes(h->dim, h->p3p, true);
     int fac = (int)factor_smem_bytes(h->dim);
-    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<17, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
     CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
     CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<32, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
     CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<32, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
@@ -397,13 +444,15 @@ int set_chain_smem_attrs(rmhmc_handle* h) {
 
 int launch_turn(rmhmc_handle* h, int do_back, int do_front, int init) {
     const unsigned C = (unsigned)h->n_chains;
-    size_t smem = turn_smem_bytes(h->dim, h->p3p);
+    const bool big = is_big(h);
+    size_t smem = turn_smem_bytes(h->dim, h->p2, h->p3p, big);
     {
         Bracket b(h, 3);
-        switch (nch_variant(h)) {
-            case 0: k_chain_turn<4><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init); break;
-            case 1: k_chain_turn<11><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init); break;
-            default: k_chain_turn<17><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init);
+        if (big) k_chain_turn<1, true><<<C, kBigThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init);
+        else switch (nch_variant(h)) {
+            case 0: k_chain_turn<4, false><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init); break;
+            case 1: k_chain_turn<11, false><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init); break;
+            default: k_chain_turn<17, false><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init);
         }
     }
     h->launches += 1;
@@ -413,11 +462,11 @@ int launch_turn(rmhmc_handle* h, int do_back, int do_front, int init) {
 
 int launch_factor(rmhmc_handle* h, int init) {
     const unsigned C = (unsigned)h->n_chains;
-    size_t smem = factor_smem_bytes(h->dim);
     {
         Bracket b(h, 4);
-        if (dmax_variant(h) == 0) k_chain_factor<16><<<C, 32, smem, h->stream>>>(h->P, h->S, init);
-        else k_chain_factor<32><<<C, 32, smem, h->stream>>>(h->P, h->S, init);
+        if (is_big(h)) k_chain_factor_big<<<C, kBigThreads, big_mat_smem_bytes(h->dim, 2), h->stream>>>(h->P, h->S, init);
+        else if (dmax_variant(h) == 0) k_chain_factor<16><<<C, 32, factor_smem_bytes(h->dim), h->stream>>>(h->P, h->S, init);
+        else k_chain_factor<32><<<C, 32, factor_smem_bytes(h->dim), h->stream>>>(h->P, h->S, init);
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -429,7 +478,8 @@ int launch_solve(rmhmc_handle* h, int is_last) {
     size_t smem = (size_t)h->dim * (h->dim | 1) * 8;
     {
         Bracket b(h, 4);
-        if (dmax_variant(h) == 0) k_chain_solve<16><<<C, 32, smem, h->stream>>>(h->P, h->S, is_last);
+        if (is_big(h)) k_chain_solve_big<<<C, kBigThreads, big_mat_smem_bytes(h->dim, 1), h->stream>>>(h->P, h->S, is_last);
+        else if (dmax_variant(h) == 0) k_chain_solve<16><<<C, 32, smem, h->stream>>>(h->P, h->S, is_last);
         else k_chain_solve<32><<<C, 32, smem, h->stream>>>(h->P, h->S, is_last);
     }
     h->launches += 1;
@@ -439,13 +489,18 @@ int launch_solve(rmhmc_handle* h, int is_last) {
 
 int launch_seam_factor(rmhmc_handle* h, const EngineParams& P, int64_t C, const double* gp, const double* tp, double* L,
                        double* Ginv, double* logdet, double* trace) {
-    size_t smem = seam_smem_bytes(h->dim, h->p3p, tp != nullptr);
-    if (h->dim <= 16 && h->p2 <= 128)
-        k_seam_factor<16, 4><<<(unsigned)C, 32, smem, h->stream>>>(P, gp, tp, L, Ginv, logdet, trace);
-    else if (h->p2 <= 352)
-        k_seam_factor<32, 11><<<(unsigned)C, 32, smem, h->stream>>>(P, gp, tp, L, Ginv, logdet, trace);
-    else
-        k_seam_factor<32, 17><<<(unsigned)C, 32, smem, h->stream>>>(P, gp, tp, L, Ginv, logdet, trace);
+    if (is_big(h)) {
+        size_t smem = big_mat_smem_bytes(h->dim, 2) + (size_t)h->p2 * 8;
+        k_seam_factor_big<<<(unsigned)C, kBigThreads, smem, h->stream>>>(P, gp, tp, L, Ginv, logdet, trace);
+    } else {
+        size_t smem = seam_smem_bytes(h->dim, h->p3p, tp != nullptr);
+        if (h->dim <= 16 && h->p2 <= 128)
+            k_seam_factor<16, 4><<<(unsigned)C, 32, smem, h->stream>>>(P, gp, tp, L, Ginv, logdet, trace);
+        else if (h->p2 <= 352)
+            k_seam_factor<32, 11><<<(unsigned)C, 32, smem, h->stream>>>(P, gp, tp, L, Ginv, logdet, trace);
+        else
+            k_seam_factor<32, 17><<<(unsigned)C, 32, smem, h->stream>>>(P, gp, tp, L, Ginv, logdet, trace);
+    }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
     return RMHMC_OK;
@@ -557,8 +612,8 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
         g_create_error = "rmhmc_create: bad arguments";
         return RMHMC_E_INVALID;
     }
-    if (dim > kMaxDimWarp) {
-        g_create_error = "rmhmc_create: dim > 32 is not supported by this version";
+    if (dim > kMaxDimBig) {
+        g_create_error = "rmhmc_create: dim > 128 is not supported by this version";
         return RMHMC_E_UNSUPPORTED;
     }
     auto* h = new rmhmc_handle();
@@ -586,9 +641,13 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
     {
         // packed-column tiles per G-warp; a single left-over tile is split over chain tiles instead
         int tiles = h->p2p / 8;
-        if (tiles % 4 == 1 && tiles > 1) { h->extra_tile = tiles - 1; tiles -= 1; }
+        const int max_nt = 6;                     // accumulator tiles per G-warp that fit the register file
+        if (tiles % 4 == 1 && tiles > 1 && tiles <= kMetricGWarps * max_nt + 1) { h->extra_tile = tiles - 1; tiles -= 1; }
         else h->extra_tile = -1;
-        h->nt = (tiles + kMetricGWarps - 1) / kMetricGWarps;
+        h->main_tiles = tiles;
+        h->nt = std::min(max_nt, (tiles + kMetricGWarps - 1) / kMetricGWarps);
+        int d_tiles = (dim + 7) / 8;
+        h->col_ctas = std::max((tiles + kMetricGWarps * h->nt - 1) / (kMetricGWarps * h->nt), (d_tiles + 3) / 4);
     }
 
     // index tables
@@ -605,13 +664,15 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
         for (int j = i; j < dim; ++j)
             for (int k = j; k < dim; ++k)
                 tri_tab[triple_index(i, j, k, dim)] = make_uchar4((unsigned char)i, (unsigned char)j, (unsigned char)k, 0);
-    std::vector<unsigned short> tidx((size_t)dim * h->p2, 0);
+    const bool big = dim > kMaxDimWarp;
+    std::vector<unsigned short> tidx(big ? 1 : (size_t)dim * h->p2, 0);
+    std::vector<unsigned int> tidx32(big ? (size_t)dim * h->p2 : 1, 0);
     for (int d = 0; d < dim; ++d)
-        for (int pr = 0; pr < h->p2; ++pr) tidx[(size_t)d * h->p2 + pr] = (unsigned short)triple_index_any(pa[pr], pb[pr], d, dim);
-    if (h->p3p > 65535) {
-        h->err = "packed triple index exceeds 16 bits";
-        return bail(RMHMC_E_UNSUPPORTED);
-    }
+        for (int pr = 0; pr < h->p2; ++pr) {
+            int ti = triple_index_any(pa[pr], pb[pr], d, dim);
+            if (big) tidx32[(size_t)d * h->p2 + pr] = (unsigned int)ti;
+            else tidx[(size_t)d * h->p2 + pr] = (unsigned short)ti;
+        }
 
 #define CREATE_TRY(expr)                                                          \
     do {                                                                          \
@@ -625,12 +686,14 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
     CREATE_TRY(cudaMalloc((void**)&h->pair_tab, pair_tab.size() * sizeof(uchar2)));
     CREATE_TRY(cudaMalloc((void**)&h->tri_tab, tri_tab.size() * sizeof(uchar4)));
     CREATE_TRY(cudaMalloc((void**)&h->tidx, tidx.size() * sizeof(unsigned short)));
+    CREATE_TRY(cudaMalloc((void**)&h->tidx32, tidx32.size() * sizeof(unsigned int)));
     CREATE_TRY(cudaMalloc((void**)&h->pair_a, pa.size()));
     CREATE_TRY(cudaMalloc((void**)&h->pair_b, pb.size()));
     CREATE_TRY(cudaMalloc((void**)&h->d_remaining, sizeof(long long)));
     CREATE_TRY(cudaMemcpy(h->pair_tab, pair_tab.data(), pair_tab.size() * sizeof(uchar2), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(h->tri_tab, tri_tab.data(), tri_tab.size() * sizeof(uchar4), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(h->tidx, tidx.data(), tidx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(h->tidx32, tidx32.data(), tidx32.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(h->pair_a, pa.data(), pa.size(), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(h->pair_b, pb.data(), pb.size(), cudaMemcpyHostToDevice));
     int64_t total = (int64_t)h->n_rows_pad * h->xs;
@@ -649,7 +712,7 @@ void rmhmc_destroy(rmhmc_handle* h) {
     cudaSetDevice(h->device);
     drain_profile(h);
     free_chains(h);
-    cudaFree(h->x_pad); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx);
+    cudaFree(h->x_pad); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
     cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
     delete h;
 }
@@ -715,7 +778,7 @@ int rmhmc_metric_partials(rmhmc_handle* h, int64_t C, const double* theta, doubl
         if (trace) {
             EngineParams P = h->P;
             P.n_chains = (int)C; P.dim = h->dim; P.ds = h->dim | 1; P.p2 = h->p2; P.p2p = h->p2p; P.p3 = h->p3;
-            P.p3p = h->p3p; P.tidx = h->tidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
+            P.p3p = h->p3p; P.tidx = h->tidx; P.tidx32 = h->tidx32; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
             rc = set_chain_smem_attrs(h);
             if (!rc) rc = launch_seam_factor(h, P, C, gp, tp, nullptr, nullptr, nullptr, trace);
         }
@@ -737,7 +800,7 @@ int rmhmc_chol_logdet(rmhmc_handle* h, int64_t C, const double* G, double* L, do
         k_pack_g<<<blocks_for(C * h->p2p, 256), 256, 0, h->stream>>>(G, gp, C, h->dim, h->p2, h->p2p, h->pair_a, h->pair_b);
         EngineParams P = h->P;
         P.n_chains = (int)C; P.dim = h->dim; P.ds = h->dim | 1; P.p2 = h->p2; P.p2p = h->p2p; P.p3 = h->p3;
-        P.p3p = h->p3p; P.tidx = h->tidx; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
+        P.p3p = h->p3p; P.tidx = h->tidx; P.tidx32 = h->tidx32; P.pair_a = h->pair_a; P.pair_b = h->pair_b;
         rc = set_chain_smem_attrs(h);
         if (!rc) rc = launch_seam_factor(h, P, C, gp, nullptr, L, Ginv, logdet, nullptr);
         cudaError_t e = cudaStreamSynchronize(h->stream);

@@ -10,6 +10,7 @@
 // beginning of the following one.  No lock-step over iterations, no compaction, every round is a
 // full batch.
 #pragma once
+#include "chain_big.cuh"
 #include "common.cuh"
 
 namespace rmhmc {
@@ -41,7 +42,8 @@ struct EngineParams {
     double* tr_hprop;                  // [C][TI]
     int* tr_flags;                     // [C][TI] bit0 accepted, bit1 uniform consumed, bits 8.. nsteps, bit 4 dir>0
     long long tr_iters;                // TI
-    const unsigned short* tidx;        // [D][P2]: packed-triple index of (d, pair)
+    const unsigned short* tidx;        // [D][P2]: packed-triple index of (d, pair) (D <= 32)
+    const unsigned int* tidx32;        // same, 32-bit (D > 32)
     const unsigned char* pair_a;       // [P2]
     const unsigned char* pair_b;       // [P2]
     size_t slot_theta, slot_scalar, slot_invg, slot_t;   // doubles between slot 0 and slot 1
@@ -398,46 +400,81 @@ __global__ void __launch_bounds__(32) k_chain_factor(EngineParams P, ChainArrays
 //           implicit momentum half-step (R7-R8), u0 and the first position iterate (R9-R10).
 // Both halves run back to back in the same CTA so that T and G^-1 of the step's end point -- which
 // is the next step's start point unless the proposal was rejected -- stay in shared memory.
+// BIG (32 < D <= 128): 256 threads, T is read from global memory through 32-bit indices and the pair
+// weights live in shared memory instead of registers.
 constexpr int kTurnThreads = 128;
 
-__host__ inline size_t turn_smem_bytes(int dim, int p3p) {
-    return ((size_t)dim * (dim | 1) + 8 * 32) * 8 + 8 + (size_t)p3p * 8;
+__host__ inline size_t turn_smem_bytes(int dim, int p2, int p3p, bool big) {
+    size_t vec = big ? kMaxDimBig : 32;
+    return ((size_t)dim * (dim | 1) + 8 * vec) * 8 + 8 + (big ? (size_t)p2 : (size_t)p3p) * 8;
 }
 
-template <int NCH>
-__global__ void __launch_bounds__(kTurnThreads) k_chain_turn(EngineParams P, ChainArrays S, int do_back, int do_front,
-                                                             int init) {
+template <int NCH, bool BIG>
+__global__ void __launch_bounds__(BIG ? kBigThreads : kTurnThreads)
+k_chain_turn(EngineParams P, ChainArrays S, int do_back, int do_front, int init) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NW = kTurnThreads / 32;
+    constexpr int NTHR = BIG ? kBigThreads : kTurnThreads;
+    constexpr int NW = NTHR / 32;
+    constexpr int VEC = BIG ? kMaxDimBig : 32;
     const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, D = P.dim, DS = P.ds;
     if (c >= P.n_chains) return;
     long long it = S.iter[c];
     if (!init && it >= P.it_stop) return;
     double* IG = reinterpret_cast<double*>(smem_raw);
     double* v_p = IG + D * DS;        // momentum
-    double* v_u = v_p + 32;           // G^-1 x
-    double* v_out = v_u + 32;         // contraction results
-    double* v_grad = v_out + 32;
-    double* v_tr = v_grad + 32;
-    double* v_th = v_tr + 32;
-    double* v_x = v_th + 32;          // scratch vector (z, fixed-point iterate)
-    double* v_y = v_x + 32;
-    double* Tsm = v_y + 32;
+    double* v_u = v_p + VEC;          // G^-1 x
+    double* v_out = v_u + VEC;        // contraction results
+    double* v_grad = v_out + VEC;
+    double* v_tr = v_grad + VEC;
+    double* v_th = v_tr + VEC;
+    double* v_x = v_th + VEC;         // scratch vector (z, fixed-point iterate)
+    double* v_y = v_x + VEC;
+    double* Tsm = v_y + VEC;          // packed T (D <= 32) or the pair weights q (BIG)
     if ((Tsm - IG) & 1) ++Tsm;
+    const double* Tg = nullptr;       // BIG: packed T of the loaded slot, in global memory
     const bool live = tid < D;
     PairRegs<NCH> pr;
-    load_pairs<NCH>(P, pr, lane);
+    if (!BIG) load_pairs<NCH>(P, pr, lane);
 
     int cur = S.cur[c];
     int step = init ? 0 : S.step[c];
     int have_slot = -1;               // slot whose T / G^-1 / grad / trace / theta are in shared memory
 
     auto load_slot_mats = [&](int slot) {
-        const double2* ts = reinterpret_cast<const double2*>(S.tpack + slot * P.slot_t + (size_t)c * P.p3p);
-        double2* td = reinterpret_cast<double2*>(Tsm);
-        for (int i = tid; i < P.p3p / 2; i += kTurnThreads) td[i] = ts[i];
+        if (BIG) {
+            Tg = S.tpack + slot * P.slot_t + (size_t)c * P.p3p;
+        } else {
+            const double2* ts = reinterpret_cast<const double2*>(S.tpack + slot * P.slot_t + (size_t)c * P.p3p);
+            double2* td = reinterpret_cast<double2*>(Tsm);
+            for (int i = tid; i < P.p3p / 2; i += NTHR) td[i] = ts[i];
+        }
         const double* ig = S.invg + slot * P.slot_invg + (size_t)c * D * D;
-        for (int idx = tid; idx < D * D; idx += kTurnThreads) IG[(idx / D) * DS + (idx % D)] = ig[idx];
+        for (int idx = tid; idx < D * D; idx += NTHR) IG[(idx / D) * DS + (idx % D)] = ig[idx];
+    };
+    // out_d = u^T dG_d u  /  out_d = tr(G^-1 dG_d); both end with a CTA barrier
+    auto quad = [&](const double* u, double* out) {
+        if (BIG) {
+            for (int p = tid; p < P.p2; p += NTHR) {
+                int pa = P.pair_a[p], pb = P.pair_b[p];
+                Tsm[p] = (pa == pb ? 1.0 : 2.0) * u[pa] * u[pb];
+            }
+            __syncthreads();
+            tensor_contract_big(Tg, Tsm, P.tidx32, out, D, P.p2);
+        } else {
+            quad_terms<NCH>(P, pr, Tsm, u, out, warp, NW, lane);
+        }
+    };
+    auto trace = [&](double* out) {
+        if (BIG) {
+            for (int p = tid; p < P.p2; p += NTHR) {
+                int pa = P.pair_a[p], pb = P.pair_b[p];
+                Tsm[p] = (pa == pb ? 1.0 : 2.0) * IG[pa * DS + pb];
+            }
+            __syncthreads();
+            tensor_contract_big(Tg, Tsm, P.tidx32, out, D, P.p2);
+        } else {
+            trace_terms<NCH>(P, pr, Tsm, IG, out, warp, NW, lane);
+        }
     };
     // y = G^-1 x for vectors in shared memory; ends with a CTA barrier
     auto matvec = [&](const double* x, double* y) {
@@ -473,7 +510,7 @@ __global__ void __launch_bounds__(kTurnThreads) k_chain_turn(EngineParams P, Cha
                 v_p[tid] = init ? 0.0 : S.mom[(size_t)c * D + tid];
             }
             __syncthreads();
-            trace_terms<NCH>(P, pr, Tsm, IG, v_tr, warp, NW, lane);
+            trace(v_tr);
             double lp = 0.0;
             for (int b = 0; b < D; ++b)
                 lp += -0.5 * log(2.0 * 3.14159265358979323846 * P.alpha) - v_th[b] * v_th[b] / (2.0 * P.alpha);
@@ -490,7 +527,7 @@ __global__ void __launch_bounds__(kTurnThreads) k_chain_turn(EngineParams P, Cha
 
             // ---- R14: explicit closing momentum half-step
             matvec(v_p, v_u);
-            quad_terms<NCH>(P, pr, Tsm, v_u, v_out, warp, NW, lane);
+            quad(v_u, v_out);
             if (live) {
                 double p = v_p[tid] + (sgn * P.step_size / 2) * (v_grad[tid] - 0.5 * v_tr[tid] + 0.5 * v_out[tid]);
                 v_p[tid] = p;
@@ -522,7 +559,7 @@ __global__ void __launch_bounds__(kTurnThreads) k_chain_turn(EngineParams P, Cha
             if (!take) {
                 used_u = true;
                 double ua = P.rng_mode == 0 ? P.tape_u_acc[(size_t)(it - P.tape_base) * P.n_chains + c]
-                                            : philox_pair(P, c, it, 34u).u0;
+                                            : philox_pair(P, c, it, 0x102u).u0;
                 take = ratio > log(ua);
             }
             const int fin = (take && nsteps > 0) ? out : cur;
@@ -577,8 +614,8 @@ __global__ void __launch_bounds__(kTurnThreads) k_chain_turn(EngineParams P, Cha
             z_dir = P.tape_z_dir[row];
         } else {
             if (live) z = philox_normal(P, c, it, (uint32_t)tid);
-            u_step = philox_pair(P, c, it, 32u).u0;
-            z_dir = philox_normal(P, c, it, 33u);
+            u_step = philox_pair(P, c, it, 0x100u).u0;
+            z_dir = philox_normal(P, c, it, 0x101u);
         }
         if (live) v_x[tid] = z;
         __syncthreads();
@@ -625,25 +662,29 @@ __global__ void __launch_bounds__(kTurnThreads) k_chain_turn(EngineParams P, Cha
     __syncthreads();
     for (int fi = 0; fi < P.n_fixed; ++fi) {
         matvec(v_x, v_u);
-        quad_terms<NCH>(P, pr, Tsm, v_u, v_out, warp, NW, lane);
+        quad(v_u, v_out);
         if (live) v_x[tid] = v_p[tid] + h * (v_grad[tid] - 0.5 * v_tr[tid] + 0.5 * v_out[tid]);
         __syncthreads();
     }
     // ---- R9 and the first position iterate (its metric is the one we already hold)
     matvec(v_x, v_u);
-    if (warp == 0) {
-        double u0 = live ? v_u[tid] : 0.0;
-        double th = live ? v_th[tid] : 0.0;
-        double pw = th + h * (u0 + u0);
-        if (P.n_fixed <= 1) {
-            if (P.n_fixed == 0) pw = th;
-            pw = clamp_position(pw, lane, D, &S.renorm_pos[c]);
+    if (live) {
+        double u0 = v_u[tid];
+        v_y[tid] = P.n_fixed == 0 ? v_th[tid] : v_th[tid] + h * (u0 + u0);
+    }
+    __syncthreads();
+    double div = 1.0;
+    if (P.n_fixed <= 1) {                       // this iterate is already the step's final position
+        double nrm = sqrt(dot(v_y, v_y));       // rmhmc.py:125-130
+        if (nrm > 10.0) {
+            div = nrm * 3.0;
+            if (tid == 0) ++S.renorm_pos[c];
         }
-        if (live) {
-            S.mom[(size_t)c * D + tid] = v_x[tid];
-            S.u0[(size_t)c * D + tid] = u0;
-            S.theta_w[(size_t)c * D + tid] = pw;
-        }
+    }
+    if (live) {
+        S.mom[(size_t)c * D + tid] = v_x[tid];
+        S.u0[(size_t)c * D + tid] = v_u[tid];
+        S.theta_w[(size_t)c * D + tid] = div == 1.0 ? v_y[tid] : v_y[tid] / div;
     }
 }
 
@@ -670,6 +711,60 @@ __global__ void __launch_bounds__(32) k_chain_solve(EngineParams P, ChainArrays 
     double pw = w + (S.dir[c] * P.step_size / 2) * (u0 + u);                        // rmhmc.py:122
     if (is_last) pw = clamp_position(pw, lane, D, &S.renorm_pos[c]);
     if (live) S.theta_w[(size_t)c * D + lane] = pw;
+}
+
+// ---------------------------------------------------------------- D > 32: CTA-per-chain variants
+__host__ inline size_t big_mat_smem_bytes(int dim, int n_mats) { return ((size_t)n_mats * dim * (dim | 1) + kMaxDimBig) * 8; }
+
+__global__ void __launch_bounds__(kBigThreads) k_chain_factor_big(EngineParams P, ChainArrays S, int init) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int c = blockIdx.x, tid = threadIdx.x, D = P.dim, DS = P.ds;
+    if (c >= P.n_chains) return;
+    if (!init && (S.iter[c] >= P.it_stop || S.nsteps[c] <= 0)) return;
+    double* A = reinterpret_cast<double*>(smem_raw);
+    double* B = A + D * DS;
+    const int out = init ? S.cur[c] : 1 - S.cur[c];
+    unpack_sym_cta(S.g_tmp + (size_t)c * P.p2p, A, D, DS);
+    double logdet = chol_cta(A, D, DS);
+    if (tid == 0) S.logdet[out * P.slot_scalar + c] = logdet;
+    double* ld = S.lfac + out * P.slot_invg + (size_t)c * D * D;
+    for (int idx = tid; idx < D * D; idx += kBigThreads) ld[idx] = A[(idx / D) * DS + (idx % D)];
+    chol_inverse_cta(A, B, D, DS);
+    double* igd = S.invg + out * P.slot_invg + (size_t)c * D * D;
+    for (int idx = tid; idx < D * D; idx += kBigThreads) igd[idx] = B[(idx / D) * DS + (idx % D)];
+}
+
+__global__ void __launch_bounds__(kBigThreads) k_chain_solve_big(EngineParams P, ChainArrays S, int is_last) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int c = blockIdx.x, tid = threadIdx.x, D = P.dim, DS = P.ds;
+    if (c >= P.n_chains) return;
+    if (S.iter[c] >= P.it_stop || S.nsteps[c] <= 0) return;
+    double* A = reinterpret_cast<double*>(smem_raw);
+    double* b = A + D * DS;
+    const int cur = S.cur[c];
+    const int in_slot = S.step[c] == 0 ? cur : 1 - cur;
+    if (tid < D) b[tid] = S.mom[(size_t)c * D + tid];
+    unpack_sym_cta(S.g_tmp + (size_t)c * P.p2p, A, D, DS);
+    chol_cta(A, D, DS);
+    chol_solve_cta(A, b, D, DS);                                                     // rmhmc.py:121
+    double pw = 0.0;
+    if (tid < D) {
+        double w = S.theta[in_slot * P.slot_theta + (size_t)c * D + tid];
+        pw = w + (S.dir[c] * P.step_size / 2) * (S.u0[(size_t)c * D + tid] + b[tid]);    // rmhmc.py:122
+    }
+    __syncthreads();
+    if (tid < D) b[tid] = pw;
+    __syncthreads();
+    if (is_last) {                                                                   // rmhmc.py:125-130
+        double n2 = 0.0;
+        for (int d = 0; d < D; ++d) n2 = fma(b[d], b[d], n2);
+        double nrm = sqrt(n2);
+        if (nrm > 10.0) {
+            pw /= nrm * 3.0;
+            if (tid == 0) ++S.renorm_pos[c];
+        }
+    }
+    if (tid < D) S.theta_w[(size_t)c * D + tid] = pw;
 }
 
 #endif  // __CUDACC__

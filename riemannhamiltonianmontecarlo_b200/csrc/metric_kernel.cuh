@@ -36,6 +36,8 @@ struct MetricArgs {
     double* cbuf;             // [C][Np]   (closing)
     int n_chains, n_rows, n_rows_pad, dim, xs, p2, p2p;
     int extra_tile;           // n-tile split over the chain tiles of G-warps 0..3, or -1
+    int tiles_per_cta;        // packed-column tiles owned by one CTA (blockIdx.y selects the range)
+    int n_main_tiles;         // tiles distributed over the G-warps (all tiles except extra_tile)
     double alpha_inv;
 };
 
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
                 const int m_local = m * 8 + g;
                 if (WITH_G) *reinterpret_cast<double2*>(vdst + (size_t)m_local * VS + r_local) = make_double2(vv[0], vv[1]);
                 if (CLOSING) *reinterpret_cast<double2*>(rdst + (size_t)m_local * VS + r_local) = make_double2(rr[0], rr[1]);
-                if (WITH_C) {
+                if (WITH_C && blockIdx.y == 0) {
                     int c = chain0 + m_local;
                     if (c < a.n_chains)
                         *reinterpret_cast<double2*>(a.cbuf + (size_t)c * a.n_rows_pad + rb * NB + r_local) =
@@ -300,16 +302,18 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
     } else {
         // =================================================================== G-warps
         const int gw = warp;
-        const int n_tiles = a.p2p / 8;
+        // this CTA's packed-column tiles: [tile0, tile_end), tile t of the range belongs to warp t mod GW
+        const int tile0 = blockIdx.y * a.tiles_per_cta;
+        const int tile_end = min(tile0 + a.tiles_per_cta, a.n_main_tiles);
         int col_a[NT], col_b[NT];
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-            int nt = gw + j * GW;
+            int nt = tile0 + gw + j * GW;
             uchar2 ab = make_uchar2(0, 0);
-            if (nt < n_tiles && nt != a.extra_tile) ab = a.pair_tab[nt * 8 + g];
+            if (nt < tile_end) ab = a.pair_tab[nt * 8 + g];
             col_a[j] = ab.x; col_b[j] = ab.y;
         }
-        const bool has_extra = WITH_G && a.extra_tile >= 0 && gw < 4;
+        const bool has_extra = WITH_G && a.extra_tile >= 0 && gw < 4 && blockIdx.y == 0;
         int ex_a = 0, ex_b = 0;
         if (has_extra) { uchar2 ab = a.pair_tab[a.extra_tile * 8 + g]; ex_a = ab.x; ex_b = ab.y; }
         double acc[NT][4][2];
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
 #pragma unroll
                     for (int h = 0; h < GT; ++h) {
                         int tix = gw + h * GW;
-                        int mt = tix & 3, dt = tix >> 2;
+                        int mt = tix & 3, dt = (tix >> 2) + 4 * blockIdx.y;
                         if (dt < d_tiles) {
                             double ar = rs[(size_t)(mt * 8 + g) * VS + ks * 4 + q];
                             int dcol = dt * 8 + g;
@@ -388,8 +392,8 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
         if (WITH_G) {
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                int nt = gw + j * GW;
-                if (nt >= n_tiles || nt == a.extra_tile) continue;
+                int nt = tile0 + gw + j * GW;
+                if (nt >= tile_end) continue;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) store_tile(nt, m, acc[j][m][0], acc[j][m][1]);
             }
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
 #pragma unroll
             for (int h = 0; h < GT; ++h) {
                 int tix = gw + h * GW;
-                int mt = tix & 3, dt = tix >> 2;
+                int mt = tix & 3, dt = (tix >> 2) + 4 * blockIdx.y;
                 int c = chain0 + mt * 8 + g;
                 if (dt < d_tiles && c < a.n_chains) {
                     int dcol = dt * 8 + 2 * q;
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
         }
     }
     if (CLOSING || (WITH_G && fz.mode != kFuseNone)) __syncthreads();
-    if (CLOSING && tid < MC) {
+    if (CLOSING && tid < MC && blockIdx.y == 0) {
         int c = chain0 + tid;
         if (c < a.n_chains) a.loglik_out[c] = (ll_s[tid] + ll_s[32 + tid]) + (ll_s[64 + tid] + ll_s[96 + tid]);
     }

@@ -238,3 +238,50 @@ def test_philox_chains_reach_the_reference_posterior(pkg, golden):
     assert np.all(np.abs(s.var(axis=0) / ref_var - 1) < 0.15)
     acc = info["accepted"].sum() / info["iters"].sum()
     assert 0.8 < acc < 0.99
+
+
+# ------------------------------------------------------------------ 32 < D <= 128 (CTA-per-chain path)
+@pytest.mark.parametrize("dim,n_rows", [(40, 500), (64, 700), (100, 450)])
+def test_large_dim_seams_match_oracle(pkg, dim, n_rows):
+    xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 4000 + dim)
+    thetas = _thetas(dim, 5, 21) * 0.3
+    data = pkg.LogisticData(xx, t)
+    g, grad, lj = data.metric(thetas)
+    dg, tr = data.metric_partials(thetas[:2])
+    l, gi, ld = data.chol_logdet(g)
+    for c in range(thetas.shape[0]):
+        w = thetas[c].reshape(-1, 1)
+        _, p, v, g_ref = bo.fisher_metric(xx, w)
+        assert rel_err(g[c], g_ref) < 1e-12
+        assert rel_err(grad[c], bo.likelihood_gradient(xx, t, w)[:, 0]) < 1e-11
+        assert abs(lj[c] - bo._scalar(bo.log_joint(xx, t, w))) < 1e-11 * abs(lj[c])
+        assert rel_err(l[c], np.linalg.cholesky(g[c])) < 1e-12
+        assert rel_err(gi[c], np.linalg.inv(g[c])) < 1e-11
+        if c < 2:
+            assert rel_err(dg[c], bo.metric_tensor(xx, w)) < 1e-12
+            _, tr_ref = bo.metric_partials(xx, p, v, np.linalg.inv(g_ref))
+            assert rel_err(tr[c], tr_ref[:, 0]) < 1e-10
+    data.close()
+
+
+@pytest.mark.parametrize("dim,n_rows", [(40, 500), (64, 700)])
+def test_large_dim_rmhmc_matches_oracle(pkg, dim, n_rows):
+    xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 4100 + dim)
+    n_iter, burn, c = 5, 1, 3
+    tapes = [bo.make_tape(n_iter, dim, 9100 + i) for i in range(c)]
+    ref, infos = bo.rmhmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=4, step_size=0.3, n_fixed=4)
+    out, _, info = pkg.rmhmc_batched(xx, t, c, n_iter, burn, 4, 0.3, 4, draws=bo.stack_tapes(tapes))
+    assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
+    assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
+
+
+def test_large_dim_hmc_matches_oracle(pkg):
+    dim, n_rows = 48, 600
+    xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 4248)
+    n_iter, burn, c = 8, 2, 3
+    tapes = [bo.make_tape(n_iter, dim, 9200 + i) for i in range(c)]
+    ref, infos = bo.hmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=20, step_size=0.05)
+    st = bo.stack_tapes(tapes)
+    out, _, info = pkg.hmc_batched(xx, t, c, n_iter, burn, 20, 0.05, draws=st)
+    assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
+    assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
