@@ -51,6 +51,14 @@ void rmhmc_destroy(rmhmc_handle* h);
  * handle's stream.  This is what a caller that owns host buffers does before each batch of rounds. */
 int rmhmc_update_data(rmhmc_handle* h, const double* xx_dev, const double* t_dev);
 const char* rmhmc_last_error(const rmhmc_handle* h);
+/* Row-sharded data (very large N): every rank binds ITS rows with rmhmc_create and runs ALL chains;
+ * each metric / partials build then ends in one NCCL all-reduce (sum) of the partial
+ * G | X^T(t-p) | log-likelihood block resp. of T, after which the per-chain stages run replicated
+ * (bit-identical on every rank).  rank 0 creates the id, the caller distributes its 128 bytes
+ * (e.g. torch.distributed.broadcast), then every rank calls rmhmc_comm_init before chains_init.
+ * NCCL (libnccl.so.2) is loaded at run time; not needed otherwise. */
+int rmhmc_comm_unique_id(char* out128);
+int rmhmc_comm_init(rmhmc_handle* h, int world, int rank, const char* id128);
 /* cudaStream_t to enqueue on (0 = legacy default stream). */
 int rmhmc_set_stream(rmhmc_handle* h, void* cuda_stream);
 

@@ -9,13 +9,13 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "librmhmc_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["common.cuh", "metric_kernel.cuh", "tbuild_kernel.cuh", "chain_kernels.cuh", "hmc_kernels.cuh",
+HEADERS = ["common.cuh", "metric_kernel.cuh", "tbuild_kernel.cuh", "chain_kernels.cuh", "chain_big.cuh", "hmc_kernels.cuh",
            "ess_kernel.cuh", os.path.join("..", "..", "include", "rmhmc_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
-    "-Xptxas", "-v",
+    "-Xptxas", "-v", "-ldl",
 ]
 
 

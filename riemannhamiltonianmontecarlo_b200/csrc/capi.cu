@@ -2,6 +2,9 @@
 // Host side only orchestrates; all arithmetic is in the kernels of this directory.
 #include "../../include/rmhmc_b200.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -25,6 +28,33 @@ struct ProfSlot {
     double ms = 0.0;
     int64_t launches = 0;
 };
+}  // namespace
+
+// NCCL is resolved at run time (dlopen) so that the library loads on hosts without it; it is only
+// needed by the row-sharded mode (rmhmc_comm_init).
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    if (api.lib) return api;
+    api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.lib) return api;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+    return api;
+}
 }  // namespace
 
 struct rmhmc_handle {
@@ -52,6 +82,10 @@ struct rmhmc_handle {
     int64_t launches = 0;
     bool profiling = false;
     bool fuse_epilogues = false;
+    // row-sharded mode: this handle holds the rows of shard `shard_rank`; every build is all-reduced
+    ncclComm_t comm = nullptr;
+    int shard_world = 1, shard_rank = 0;
+    double* t_tmp = nullptr;        // [C][P3p] contiguous partials of the last build (sharded mode)
     ProfSlot prof[5];
     mutable std::string err;
 };
@@ -322,7 +356,8 @@ MetricArgs metric_args(rmhmc_handle* h, int64_t C, const double* theta, double* 
     a.g_out = g_out; a.grad_out = grad_out; a.loglik_out = loglik_out; a.cbuf = cbuf; a.extra_tile = h->extra_tile;
     a.tiles_per_cta = kMetricGWarps * h->nt; a.n_main_tiles = h->main_tiles;
     a.n_chains = (int)C; a.n_rows = (int)h->n_rows; a.n_rows_pad = h->n_rows_pad;
-    a.dim = h->dim; a.xs = h->xs; a.p2 = h->p2; a.p2p = h->p2p; a.alpha_inv = 1.0 / h->alpha;
+    a.dim = h->dim; a.xs = h->xs; a.p2 = h->p2; a.p2p = h->p2p;
+    a.alpha_inv = h->shard_rank == 0 ? 1.0 / h->alpha : 0.0;      // the prior term I/alpha is added once across shards
     return a;
 }
 
@@ -358,6 +393,7 @@ void free_chains(rmhmc_handle* h) {
     for (void* p : h->chain_allocs) cudaFree(p);
     h->chain_allocs.clear();
     h->S = ChainArrays{};
+    h->t_tmp = nullptr;
     h->n_chains = 0;
 }
 
@@ -390,14 +426,21 @@ int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
         rc |= dev_alloc(h, &S.tpack, 2 * c * h->p3p, tr);
         rc |= dev_alloc(h, &S.trace, 2 * c * D, tr);
         rc |= dev_alloc(h, &S.u0, c * D, tr);
-        rc |= dev_alloc(h, &S.g_tmp, c * h->p2p, tr);
         rc |= dev_alloc(h, &S.cbuf, (size_t)h->c_pad * h->n_rows_pad, tr);
+        if (h->comm) rc |= dev_alloc(h, &h->t_tmp, c * h->p3p, tr);
+    }
+    // build outputs are contiguous (g_tmp | grad_tmp | loglik_tmp) so that the row-sharded mode reduces them in one call
+    {
+        double* build = nullptr;
+        size_t g_len = hmc ? 0 : c * h->p2p;
+        rc |= dev_alloc(h, &build, g_len + c * D + c, tr);
+        S.g_tmp = hmc ? nullptr : build;
+        S.grad_tmp = build + g_len;
+        S.loglik_tmp = S.grad_tmp + c * D;
     }
     rc |= dev_alloc(h, &S.mom, c * D, tr);
     rc |= dev_alloc(h, &S.theta_w, c * D, tr);
     rc |= dev_alloc(h, &S.hcur, c, tr);
-    rc |= dev_alloc(h, &S.grad_tmp, c * D, tr);
-    rc |= dev_alloc(h, &S.loglik_tmp, c, tr);
     rc |= dev_alloc(h, &S.cur, c, tr);
     rc |= dev_alloc(h, &S.step, c, tr);
     rc |= dev_alloc(h, &S.nsteps, c, tr);
@@ -506,6 +549,46 @@ int launch_seam_factor(rmhmc_handle* h, const EngineParams& P, int64_t C, const 
     return RMHMC_OK;
 }
 
+int allreduce_sum(rmhmc_handle* h, double* buf, size_t count) {
+    if (!h->comm) return RMHMC_OK;
+    ncclResult_t r = nccl_api().AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->stream);
+    if (r != ncclSuccess) return fail(h, RMHMC_E_CUDA, std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r));
+    return RMHMC_OK;
+}
+// outputs of a metric build of the given mode, summed over the row shards
+template <int MODE>
+int reduce_build(rmhmc_handle* h) {
+    if (!h->comm) return RMHMC_OK;
+    const size_t c = (size_t)h->n_chains, D = (size_t)h->dim;
+    if (MODE == 0) return allreduce_sum(h, h->S.g_tmp, c * h->p2p);
+    if (MODE == 1) return allreduce_sum(h, h->S.g_tmp, c * h->p2p + c * D + c);
+    return allreduce_sum(h, h->S.grad_tmp, c * D + c);
+}
+__global__ void k_scatter_t(const double* __restrict__ src, double* __restrict__ tpack, const int* __restrict__ cur, int flip,
+                            size_t slot_stride, int64_t C, int p3p) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= C * (int64_t)(p3p / 2)) return;
+    int64_t c = i / (p3p / 2);
+    int k = (int)(i - c * (p3p / 2));
+    reinterpret_cast<double2*>(tpack + (size_t)(cur[c] ^ flip) * slot_stride + (size_t)c * p3p)[k] =
+        reinterpret_cast<const double2*>(src + (size_t)c * p3p)[k];
+}
+// partials build into the proposal (flip = 1) or current (flip = 0) slot; row-sharded: build into a
+// contiguous buffer, all-reduce, scatter into the slots
+int build_partials(rmhmc_handle* h, int flip) {
+    const int64_t C = h->n_chains;
+    ChainArrays& S = h->S;
+    if (!h->comm) return launch_tbuild(h, C, S.cbuf, S.tpack, S.cur, flip, h->P.slot_t);
+    int rc = launch_tbuild(h, C, S.cbuf, h->t_tmp, S.cur, 0, 0);       // slot stride 0: row c of t_tmp
+    if (rc) return rc;
+    rc = allreduce_sum(h, h->t_tmp, (size_t)C * h->p3p);
+    if (rc) return rc;
+    k_scatter_t<<<blocks_for(C * (h->p3p / 2), 256), 256, 0, h->stream>>>(h->t_tmp, S.tpack, S.cur, flip, h->P.slot_t, C, h->p3p);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
 // The builds of one RMHMC round (rmhmc.py:113-156 for every chain): F-1 position iterates, each a
 // metric build + per-chain solve, then the closing metric build, the partials build and the
 // per-chain factorisation of the new metric.  The
@@ -517,13 +600,15 @@ int rmhmc_round_builds(rmhmc_handle* h) {
     // SLOWER on B200 (metric 1.78 -> 2.95 ms per launch vs 0.62 ms for the stand-alone solve kernel at
     // 65536 chains: 12 warps per SM of straight-line code are instruction-fetch bound while the tensor
     // pipe idles), so it is off by default and kept for small chain counts / experiments.
-    const bool fuse = h->fuse_epilogues;
+    const bool fuse = h->fuse_epilogues && !h->comm && h->col_ctas == 1;
     for (int fi = 2; fi <= h->P.n_fixed; ++fi) {
         const int last = fi == h->P.n_fixed ? 1 : 0;
         MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, nullptr, nullptr, nullptr);
         int rc = fuse ? launch_metric<0>(h, a, fuse_args(h, kFuseSolve, last, 0)) : launch_metric<0>(h, a);
         if (rc) return rc;
         if (!fuse) {
+            rc = reduce_build<0>(h);            // row-sharded: one exchange per fixed-point iterate
+            if (rc) return rc;
             rc = launch_solve(h, last);
             if (rc) return rc;
         }
@@ -531,7 +616,9 @@ int rmhmc_round_builds(rmhmc_handle* h) {
     MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, S.grad_tmp, S.loglik_tmp, S.cbuf);
     int rc = fuse ? launch_metric<1>(h, a, fuse_args(h, kFuseFactor, 0, 0)) : launch_metric<1>(h, a);
     if (rc) return rc;
-    rc = launch_tbuild(h, C, S.cbuf, S.tpack, S.cur, 1, h->P.slot_t);
+    rc = reduce_build<1>(h);
+    if (rc) return rc;
+    rc = build_partials(h, 1);
     if (rc || fuse) return rc;
     return launch_factor(h, 0);
 }
@@ -556,6 +643,8 @@ int hmc_round(rmhmc_handle* h) {
     }
     MetricArgs a = metric_args(h, C, S.theta_w, nullptr, S.grad_tmp, S.loglik_tmp, nullptr);
     int rc = launch_metric<2>(h, a);
+    if (rc) return rc;
+    rc = reduce_build<2>(h);
     if (rc) return rc;
     {
         Bracket b(h, 3);
@@ -712,6 +801,7 @@ void rmhmc_destroy(rmhmc_handle* h) {
     cudaSetDevice(h->device);
     drain_profile(h);
     free_chains(h);
+    if (h->comm) nccl_api().CommDestroy(h->comm);
     cudaFree(h->x_pad); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
     cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
     delete h;
@@ -724,6 +814,31 @@ int rmhmc_update_data(rmhmc_handle* h, const double* xx_dev, const double* t_dev
     k_pad_design<<<blocks_for(total, 256), 256, 0, h->stream>>>(xx_dev, t_dev, h->x_pad, h->n_rows, h->dim, h->xs, h->n_rows_pad);
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+int rmhmc_comm_unique_id(char* out128) {
+    if (!out128) return RMHMC_E_INVALID;
+    NcclApi& api = nccl_api();
+    if (!api.ok) { g_create_error = "libnccl.so.2 not available"; return RMHMC_E_UNSUPPORTED; }
+    ncclUniqueId id;
+    if (api.GetUniqueId(&id) != ncclSuccess) return RMHMC_E_CUDA;
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, sizeof(id));
+    return RMHMC_OK;
+}
+
+int rmhmc_comm_init(rmhmc_handle* h, int world, int rank, const char* id128) {
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_comm_init: bad arguments") : RMHMC_E_INVALID;
+    if (h->n_chains > 0) return fail(h, RMHMC_E_STATE, "rmhmc_comm_init: call before chains_init");
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(h, RMHMC_E_UNSUPPORTED, "rmhmc_comm_init: libnccl.so.2 not available");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclResult_t r = api.CommInitRank(&h->comm, world, id, rank);
+    if (r != ncclSuccess) { h->comm = nullptr; return fail(h, RMHMC_E_CUDA, std::string("ncclCommInitRank: ") + api.GetErrorString(r)); }
+    h->shard_world = world; h->shard_rank = rank;
     return RMHMC_OK;
 }
 
@@ -831,6 +946,8 @@ static int chains_init_common(rmhmc_handle* h, int64_t C, const double* theta0, 
         MetricArgs a = metric_args(h, C, S.theta_w, nullptr, S.grad_tmp, S.loglik_tmp, nullptr);
         rc = launch_metric<2>(h, a);
         if (rc) return rc;
+        rc = reduce_build<2>(h);
+        if (rc) return rc;
         k_hmc_back<<<(unsigned)C, 32, 0, h->stream>>>(h->P, S, 1);
     } else {
         rc = set_chain_smem_attrs(h);
@@ -838,7 +955,9 @@ static int chains_init_common(rmhmc_handle* h, int64_t C, const double* theta0, 
         MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, S.grad_tmp, S.loglik_tmp, S.cbuf);
         rc = launch_metric<1>(h, a);
         if (rc) return rc;
-        rc = launch_tbuild(h, C, S.cbuf, S.tpack, S.cur, 0, h->P.slot_t);
+        rc = reduce_build<1>(h);
+        if (rc) return rc;
+        rc = build_partials(h, 0);
         if (rc) return rc;
         rc = launch_factor(h, 1);
         if (rc) return rc;

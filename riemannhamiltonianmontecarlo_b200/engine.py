@@ -24,10 +24,22 @@ def _ptr(t):
     return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
 
 
-class LogisticData:
-    """``(XX, t)`` of the Bayesian logistic regression, resident on one GPU."""
+def shard_rows(n_rows: int, rank: int, world: int):
+    """Contiguous row range [begin, end) of shard ``rank`` (row-sharded large-N mode)."""
+    base, rem = divmod(n_rows, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
 
-    def __init__(self, xx, t, alpha: float = 100.0, device: str | int = "cuda:0"):
+
+class LogisticData:
+    """``(XX, t)`` of the Bayesian logistic regression, resident on one GPU.
+
+    ``row_shard=(rank, world)``: ``xx`` / ``t`` hold only this rank's rows (see :func:`shard_rows`);
+    every metric / partials build is then summed over the ranks with NCCL inside the library
+    (``torch.distributed`` must be initialised: it carries the NCCL unique id to the other ranks).
+    """
+
+    def __init__(self, xx, t, alpha: float = 100.0, device: str | int = "cuda:0", row_shard=None):
         torch = _capi.require_cuda()
         self._lib = _capi.load()
         self.torch = torch
@@ -46,8 +58,23 @@ class LogisticData:
                                     self.alpha, _ptr(xx_d), _ptr(t_d))
         _capi.check(rc, None, "rmhmc_create")
         self.handle = handle
+        self.row_shard = row_shard
+        if row_shard is not None:
+            self._init_comm(*row_shard)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _capi.check(self._lib.rmhmc_set_stream(self.handle, c_void_p(stream)), self.handle, "rmhmc_set_stream")
+
+    def _init_comm(self, rank: int, world: int):
+        import torch.distributed as dist
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            rc = self._lib.rmhmc_comm_unique_id(buf)
+            if rc != 0:
+                raise _capi.RmhmcError(f"rmhmc_comm_unique_id failed (code {rc})")
+        box = [buf.raw]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        _capi.check(self._lib.rmhmc_comm_init(self.handle, int(world), int(rank), box[0]), self.handle, "rmhmc_comm_init")
 
     def update(self, xx_dev, t_dev):
         """Re-upload the design matrix / labels from device tensors of the bound shape."""

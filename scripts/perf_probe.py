@@ -5,8 +5,11 @@ import torch
 sys.path.insert(0, '.')
 import riemannhamiltonianmontecarlo_b200 as r
 
+import os
 shape = sys.argv[1] if len(sys.argv) > 1 else "german"
 chains = [int(a) for a in sys.argv[2:]] or [4096, 16384, 65536]
+R = int(os.environ.get("PROBE_ROUNDS", "20"))
+WARM = int(os.environ.get("PROBE_WARM", "10"))
 xx, t = r.datasets.shaped(shape)
 N, D = xx.shape
 P2, P3 = D * (D + 1) // 2, D * (D + 1) * (D + 2) // 6
@@ -15,9 +18,8 @@ for C in chains:
     data = r.LogisticData(xx, t)
     s = r.RMHMCSampler(data, C, 6, 0.5, F)
     s.set_philox(1234, 0)
-    s.advance(10); torch.cuda.synchronize()
+    s.advance(WARM); torch.cuda.synchronize()
     s.profile(True)
-    R = 20
     t0 = time.time(); s.advance(R); torch.cuda.synchronize(); dt = time.time() - t0
     prof = s.profile_read()
     s.profile(False)

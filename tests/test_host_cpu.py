@@ -103,11 +103,30 @@ def test_bench_reference_arm_prints_contract_json():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
 
 
+def test_row_shards_partition_the_rows():
+    from riemannhamiltonianmontecarlo_b200.engine import shard_rows
+    for n, world in [(1000, 1), (1003, 2), (690, 4), (10_000_000, 8), (5, 8)]:
+        spans = [shard_rows(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
 def _gloo_worker(rank, world, port, q):
+    import ctypes
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the row-sharded mode ships rank 0's NCCL unique id (128 bytes from the C ABI) to every rank
+    from riemannhamiltonianmontecarlo_b200 import _capi
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        assert _capi.load().rmhmc_comm_unique_id(buf) == 0
+    box = [buf.raw]
+    dist.broadcast_object_list(box, src=0)
+    assert len(box[0]) == 128 and any(box[0])
     # chain sharding: contiguous blocks, Philox streams keyed by the global chain id
     c_local = 6
     offset = rank * c_local

@@ -285,3 +285,21 @@ def test_large_dim_hmc_matches_oracle(pkg):
     out, _, info = pkg.hmc_batched(xx, t, c, n_iter, burn, 20, 0.05, draws=st)
     assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
     assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
+
+
+def test_row_sharded_matches_unsharded_on_two_gpus(pkg):
+    """BASELINE.json configs[4] mechanism: X row-sharded over ranks, NCCL all-reduce per build."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tests", "multi_gpu_row_shard.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert res["ok"], res
