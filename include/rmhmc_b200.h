@@ -83,6 +83,15 @@ int rmhmc_metric_partials(rmhmc_handle* h, int64_t n_chains, const double* theta
 int rmhmc_chol_logdet(rmhmc_handle* h, int64_t n_chains, const double* G, double* L, double* Ginv,
                       double* logdet);
 
+/* n generalized leapfrog steps (rmhmc.py:96-163) from caller-supplied states, no randomness: for each
+ * chain c, start at theta[c], momentum mom[c], integrate nsteps[c] steps in direction dir[c] (+1/-1)
+ * with StepSize = step_size and NumOfNewtonSteps = n_fixed.  Outputs (any may be NULL): final
+ * position / momentum (n_chains x dim) and the Hamiltonian (rmhmc.py:172,176) at the start and at
+ * the end.  Re-initialises the handle's chains; synchronises. */
+int rmhmc_leapfrog(rmhmc_handle* h, int64_t n_chains, const double* theta, const double* mom,
+                   const int32_t* dir, const int32_t* nsteps, double step_size, int n_fixed,
+                   double* out_theta, double* out_mom, double* out_h_start, double* out_h_end);
+
 /* ---- the sampler engine: rmhmc.py:37-191 batched over independent chains -------------------- */
 
 /* Allocate state for n_chains chains and evaluate it at theta0 (n_chains x dim; NULL = the
@@ -155,6 +164,11 @@ int hmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
 int blr_ess_batched(int device, void* cuda_stream, const double* samples, int64_t n_chains,
                     int64_t n_samples, int dim, int64_t chain_stride, int64_t row_stride,
                     int64_t max_lag, double* ess);
+
+/* tools.ac (tools.py:21-30) for n_series contiguous series of n_samples: normalised circular
+ * autocorrelation (period nextpow2(n)+1) at lags 0..n_lag; acf is (n_series x (n_lag+1)). */
+int blr_autocorr(int device, void* cuda_stream, const double* series, int64_t n_series,
+                 int64_t n_samples, int64_t n_lag, double* acf);
 
 /* Ragged variant for free-running chains: chain c uses rows [starts[c], starts[c] + counts[c]) of its
  * block (int64 device arrays) with max_lag = counts[c] - 1; max_samples bounds counts[c]. */

@@ -11,6 +11,7 @@ What it restates (reference = /root/reference/code, cited as file:line):
 * ``metric_partials``                    rmhmc.py:64-77 (= :142-156)
 * ``likelihood_gradient``                rmhmc.py:100 (= :140, hmc.py:53,61)
 * ``log_joint``                          rmhmc.py:31-34 (= :166-169, hmc.py:31-34,64-67)
+* ``leapfrog_step``                      rmhmc.py:96-163 (one generalized leapfrog step)
 * ``rmhmc_chain``                        rmhmc.py:37-191 (one chain, whole loop)
 * ``hmc_chain``                          hmc.py:38-89
 * ``rhat``                               not in the reference (classic Gelman-Rubin; own spec)
@@ -210,6 +211,72 @@ def _quadratic_terms(mom, inv_g_dg, u):
     return last
 
 
+def leapfrog_step(xx, t, w_new, mom, g, inv_g, inv_g_dg, tr, sgn, step_size, n_fixed, alpha=ALPHA):
+    """One generalized leapfrog step (rmhmc.py:96-163, R7-R14 in SURVEY.md 3.2).
+
+    ``g, inv_g, inv_g_dg, tr`` are the metric quantities at ``w_new`` on entry and at the new
+    position on exit.  Returns ``(w_new, mom, g, inv_g, inv_g_dg, tr, hacked)``; ``mom`` is a new
+    array, the inputs are not modified.
+    """
+    # R7/R8: implicit momentum half-step, exactly n_fixed fixed-point iterations
+    grad = likelihood_gradient(xx, t, w_new, alpha)
+    pm = mom.copy()
+    for _ in range(n_fixed):
+        u = inv_g.dot(pm)
+        last = _quadratic_terms(pm, inv_g_dg, u)
+        pm = mom + sgn * step_size / 2 * (grad - 0.5 * tr + last)
+    mom = pm
+
+    # R9/R10: implicit position step
+    u0 = np.linalg.solve(g, mom)
+    pw = w_new.copy()
+    for _ in range(n_fixed):
+        _, p, v, g = fisher_metric(xx, pw, alpha)
+        u = np.linalg.solve(g, mom)
+        pw = w_new + sgn * step_size / 2 * (u0 + u)
+    w_new = pw
+
+    # R11: position clamp hack
+    hacked = False
+    if np.linalg.norm(w_new) > 10:
+        w_new /= np.linalg.norm(w_new) * 3
+        hacked = True
+
+    # R12/R13: metric, gradient and partials at the new position
+    _, p, v, g = fisher_metric(xx, w_new, alpha)
+    inv_g = np.linalg.inv(g)
+    grad = likelihood_gradient(xx, t, w_new, alpha)
+    inv_g_dg, tr = metric_partials(xx, p, v, inv_g)
+
+    # R14: explicit closing momentum half-step
+    u = inv_g.dot(mom)
+    last = _quadratic_terms(mom, inv_g_dg, u)
+    mom += sgn * step_size / 2 * (grad - 0.5 * tr + last)
+    return w_new, mom, g, inv_g, inv_g_dg, tr, hacked
+
+
+def hamiltonian(xx, t, w, mom, alpha=ALPHA):
+    """H = -logjoint + sum log diag chol(G) + p^T G^-1 p / 2 (rmhmc.py:166-176)."""
+    _, _, _, g = fisher_metric(xx, w, alpha)
+    logdet = np.sum(np.log(np.diag(np.linalg.cholesky(g))))
+    return _scalar(-log_joint(xx, t, w, alpha) + logdet + mom.T.dot(np.linalg.inv(g)).dot(mom) / 2)
+
+
+def leapfrog(xx, t, w, mom, sgn, n_steps, step_size, n_fixed, alpha=ALPHA):
+    """``n_steps`` generalized leapfrog steps from (w, mom); returns (w, mom, H_start, H_end)."""
+    d = xx.shape[1]
+    w = np.array(w, dtype=float).reshape(d, 1)
+    mom = np.array(mom, dtype=float).reshape(d, 1)
+    h0 = hamiltonian(xx, t, w, mom, alpha)
+    _, p, v, g = fisher_metric(xx, w, alpha)
+    inv_g = np.linalg.inv(g)
+    inv_g_dg, tr = metric_partials(xx, p, v, inv_g)
+    for _ in range(n_steps):
+        w, mom, g, inv_g, inv_g_dg, tr, _ = leapfrog_step(xx, t, w, mom, g, inv_g, inv_g_dg, tr, sgn, step_size,
+                                                           n_fixed, alpha)
+    return w[:, 0], mom[:, 0], h0, hamiltonian(xx, t, w, mom, alpha)
+
+
 # --------------------------------------------------------------------------- RMHMC
 @dataclass
 class IterationRecord:
@@ -274,41 +341,12 @@ def rmhmc_chain(xx, t, tape: DrawTape, n_iter=6000, burn_in=1000, n_leapfrog=6,
             rec.n_steps, rec.direction, rec.momentum0 = n_steps, sgn, mom0.copy()
 
         for _step in range(n_steps):
-            # R7/R8: implicit momentum half-step, exactly n_fixed fixed-point iterations
-            grad = likelihood_gradient(xx, t, w_new, alpha)
-            pm = mom.copy()
-            for _ in range(n_fixed):
-                u = inv_g.dot(pm)
-                last = _quadratic_terms(pm, inv_g_dg, u)
-                pm = mom + sgn * step_size / 2 * (grad - 0.5 * tr + last)
-            mom = pm
-
-            # R9/R10: implicit position step
-            u0 = np.linalg.solve(g, mom)
-            pw = w_new.copy()
-            for _ in range(n_fixed):
-                _, p, v, g = fisher_metric(xx, pw, alpha)
-                u = np.linalg.solve(g, mom)
-                pw = w_new + sgn * step_size / 2 * (u0 + u)
-            w_new = pw
-
-            # R11: position clamp hack
-            if np.linalg.norm(w_new) > 10:
-                w_new /= np.linalg.norm(w_new) * 3
+            w_new, mom, g, inv_g, inv_g_dg, tr, hacked = leapfrog_step(
+                xx, t, w_new, mom, g, inv_g, inv_g_dg, tr, sgn, step_size, n_fixed, alpha)
+            if hacked:
                 n_renorm_w += 1
                 if rec:
                     rec.renorm_position += 1
-
-            # R12/R13: metric, gradient and partials at the new position
-            _, p, v, g = fisher_metric(xx, w_new, alpha)
-            inv_g = np.linalg.inv(g)
-            grad = likelihood_gradient(xx, t, w_new, alpha)
-            inv_g_dg, tr = metric_partials(xx, p, v, inv_g)
-
-            # R14: explicit closing momentum half-step
-            u = inv_g.dot(mom)
-            last = _quadratic_terms(mom, inv_g_dg, u)
-            mom += sgn * step_size / 2 * (grad - 0.5 * tr + last)
             if rec:
                 rec.theta_steps.append(w_new[:, 0].copy())
                 rec.mom_steps.append(mom[:, 0].copy())

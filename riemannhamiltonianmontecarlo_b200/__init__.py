@@ -6,7 +6,7 @@ Drop-in entry points with the reference's names (code/rmhmc.py, code/hmc.py, cod
 ``include/rmhmc_b200.h`` (``librmhmc_b200.so``, sm_100a only, no CPU fallback).
 """
 from . import datasets  # noqa: F401
-from .engine import HMCSampler, LogisticData, RMHMCSampler, ess_batched  # noqa: F401
+from .engine import HMCSampler, LogisticData, RMHMCSampler, autocorr_batched, ess_batched  # noqa: F401
 from .hmc import HMC, hmc_batched  # noqa: F401
 from .rmhmc import RMHMC, rmhmc_batched  # noqa: F401
 from .tools import CalculateESS, LogNormPDF, ac, nextpow2  # noqa: F401

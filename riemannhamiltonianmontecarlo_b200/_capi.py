@@ -27,6 +27,8 @@ SIGNATURES = {
     "rmhmc_metric": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rmhmc_metric_partials": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "rmhmc_chol_logdet": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rmhmc_leapfrog": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "rmhmc_chains_init": (c_int, [c_void_p, c_int64, c_void_p]),
     "rmhmc_configure": (c_int, [c_void_p, c_int, c_double, c_int]),
     "rmhmc_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -44,6 +46,7 @@ SIGNATURES = {
     "hmc_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "hmc_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     "blr_ess_batched": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p]),
+    "blr_autocorr": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "blr_ess_ragged": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -1048,6 +1048,50 @@ int hmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done) {
     return run_until(h, it_stop, rounds_done, true);
 }
 
+int rmhmc_leapfrog(rmhmc_handle* h, int64_t C, const double* theta, const double* mom, const int32_t* dir,
+                   const int32_t* nsteps, double step_size, int n_fixed, double* out_theta, double* out_mom,
+                   double* out_h_start, double* out_h_end) {
+    if (!h || C <= 0 || !theta || !mom || !dir || !nsteps || !(step_size > 0) || n_fixed < 0)
+        return h ? fail(h, RMHMC_E_INVALID, "rmhmc_leapfrog: bad arguments") : RMHMC_E_INVALID;
+    int rc = rmhmc_chains_init(h, C, theta);
+    if (rc) return rc;
+    std::vector<void*> tmp;
+    double *th_steps = nullptr, *m_end = nullptr, *t_end = nullptr, *m0 = nullptr, *hc = nullptr, *hp = nullptr;
+    int* fl = nullptr;
+    const size_t c = (size_t)C, D = (size_t)h->dim;
+    int max_steps = 1 << 12;            // bound of the per-step trace rows; steps themselves are unbounded
+    rc = dev_alloc(h, &th_steps, c * D, &tmp) | dev_alloc(h, &m_end, c * D, &tmp) | dev_alloc(h, &t_end, c * D, &tmp) |
+         dev_alloc(h, &m0, c * D, &tmp) | dev_alloc(h, &hc, c, &tmp) | dev_alloc(h, &hp, c, &tmp) | dev_alloc(h, &fl, c, &tmp);
+    (void)max_steps;
+    if (!rc) {
+        EngineParams saved = h->P;
+        h->P.n_leapfrog = 1;            // trace row stride; theta_steps is not reported by this seam
+        h->P.step_size = step_size; h->P.n_fixed = n_fixed;
+        h->P.rng_mode = 1; h->P.seed = 0; h->P.chain_offset = 0;          // only the (irrelevant) accept draw uses it
+        h->P.ext_mom = mom; h->P.ext_nsteps = nsteps; h->P.ext_dir = dir;
+        h->P.samples = nullptr;
+        h->P.tr_iters = 1; h->P.tr_theta_steps = nullptr; h->P.tr_mom_end = m_end; h->P.tr_theta_end = t_end;
+        h->P.tr_mom0 = m0; h->P.tr_hcur = hc; h->P.tr_hprop = hp; h->P.tr_flags = fl;
+        h->configured = true; h->rng_set = true;
+        rc = run_until(h, 1, nullptr, false);
+        h->P.ext_mom = nullptr; h->P.ext_nsteps = nullptr; h->P.ext_dir = nullptr;
+        h->P.n_leapfrog = saved.n_leapfrog; h->P.step_size = saved.step_size; h->P.n_fixed = saved.n_fixed;
+        h->P.tr_iters = 0; h->P.tr_mom_end = nullptr; h->P.tr_theta_end = nullptr; h->P.tr_mom0 = nullptr;
+        h->P.tr_hcur = nullptr; h->P.tr_hprop = nullptr; h->P.tr_flags = nullptr;
+        h->rng_set = false;
+        if (!rc) {
+            if (out_theta) cudaMemcpyAsync(out_theta, t_end, c * D * 8, cudaMemcpyDeviceToDevice, h->stream);
+            if (out_mom) cudaMemcpyAsync(out_mom, m_end, c * D * 8, cudaMemcpyDeviceToDevice, h->stream);
+            if (out_h_start) cudaMemcpyAsync(out_h_start, hc, c * 8, cudaMemcpyDeviceToDevice, h->stream);
+            if (out_h_end) cudaMemcpyAsync(out_h_end, hp, c * 8, cudaMemcpyDeviceToDevice, h->stream);
+            cudaError_t e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) { h->err = std::string("rmhmc_leapfrog: ") + cudaGetErrorString(e); rc = RMHMC_E_CUDA; }
+        }
+    }
+    for (void* p : tmp) cudaFree(p);
+    return rc;
+}
+
 int rmhmc_read_state(rmhmc_handle* h, double* theta, int64_t* iters, int64_t* accepted, int64_t* leapfrogs,
                      int32_t* renorm_mom, int32_t* renorm_pos) {
     if (!h) return RMHMC_E_INVALID;
@@ -1099,6 +1143,22 @@ int blr_ess_batched(int device, void* cuda_stream, const double* samples, int64_
     dim3 grid((unsigned)n_chains, (unsigned)dim);
     k_ess<<<grid, kEssThreads, smem, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
         samples, (size_t)chain_stride, (size_t)row_stride, (int)n_samples, (int)max_lag, n_fft, ess, dim, nullptr, nullptr);
+    return cudaGetLastError() == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
+}
+
+int blr_autocorr(int device, void* cuda_stream, const double* series, int64_t n_series, int64_t n_samples,
+                 int64_t n_lag, double* acf) {
+    if (!series || !acf || n_series <= 0 || n_samples < 2 || n_lag < 0) return RMHMC_E_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return RMHMC_E_CUDA;
+    int n_fft = 1;
+    while (n_fft < n_samples) n_fft *= 2;           // tools.py:16-19
+    n_fft += 1;                                     // tools.py:23
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    dim3 grid((unsigned)(n_lag + 1), (unsigned)n_series);
+    k_acf_raw<<<grid, kEssThreads, 0, st>>>(series, (int)n_samples, n_fft, (int)n_lag, acf);
+    int64_t total = n_series * (n_lag + 1);
+    k_acf_normalise<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(acf, (int)n_lag, (int)n_series);
+    k_acf_lag0<<<(unsigned)((n_series + 255) / 256), 256, 0, st>>>(acf, (int)n_lag, (int)n_series);
     return cudaGetLastError() == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
 }
 

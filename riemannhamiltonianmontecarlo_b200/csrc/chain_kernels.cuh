@@ -32,6 +32,10 @@ struct EngineParams {
     long long tape_base;               // iteration index of tape row 0
     unsigned long long seed;
     long long chain_offset;            // global id of local chain 0 (multi-GPU sharding)
+    // leapfrog seam (rmhmc_leapfrog): momentum, trajectory length and direction supplied by the caller
+    const double* ext_mom;             // [C][D] or null
+    const int* ext_nsteps;             // [C]
+    const int* ext_dir;                // [C]
     double* samples;                   // [C][cap][D] or null
     // optional per-step trace for the parity tests (null in production)
     double* tr_theta_steps;            // [C][TI][L][D]
@@ -606,35 +610,43 @@ k_chain_turn(EngineParams P, ChainArrays S, int do_back, int do_front, int init)
     int sgn, nsteps;
     if (step == 0) {
         // ---- R4-R6: p = L^T z with the current position's Cholesky factor, H_current
-        double z = 0.0, u_step, z_dir;
-        if (P.rng_mode == 0) {
-            size_t row = (size_t)(it - P.tape_base) * P.n_chains + c;
-            if (live) z = P.tape_z[row * D + tid];
-            u_step = P.tape_u_step[row];
-            z_dir = P.tape_z_dir[row];
+        if (P.ext_mom) {
+            // leapfrog seam: the caller supplies p, RandomStep and TimeStep
+            if (live) v_p[tid] = P.ext_mom[(size_t)c * D + tid];
+            nsteps = P.ext_nsteps[c];
+            sgn = P.ext_dir[c];
+            __syncthreads();
         } else {
-            if (live) z = philox_normal(P, c, it, (uint32_t)tid);
-            u_step = philox_pair(P, c, it, 0x100u).u0;
-            z_dir = philox_normal(P, c, it, 0x101u);
-        }
-        if (live) v_x[tid] = z;
-        __syncthreads();
-        if (live) {
-            const double* lf = S.lfac + in_slot * P.slot_invg + (size_t)c * D * D;
-            double p = 0.0;
-            for (int i = tid; i < D; ++i) p = fma(lf[i * D + tid], v_x[i], p);     // (z L)^T = L^T z, rmhmc.py:80
-            v_p[tid] = p;
-        }
-        __syncthreads();
-        double nrm = sqrt(dot(v_p, v_p));
-        if (nrm > 100.0) {                                                          // rmhmc.py:81-85
+            double z = 0.0, u_step, z_dir;
+            if (P.rng_mode == 0) {
+                size_t row = (size_t)(it - P.tape_base) * P.n_chains + c;
+                if (live) z = P.tape_z[row * D + tid];
+                u_step = P.tape_u_step[row];
+                z_dir = P.tape_z_dir[row];
+            } else {
+                if (live) z = philox_normal(P, c, it, (uint32_t)tid);
+                u_step = philox_pair(P, c, it, 0x100u).u0;
+                z_dir = philox_normal(P, c, it, 0x101u);
+            }
+            if (live) v_x[tid] = z;
             __syncthreads();
-            if (live) v_p[tid] /= nrm * 25.0;
-            if (tid == 0) ++S.renorm_mom[c];
+            if (live) {
+                const double* lf = S.lfac + in_slot * P.slot_invg + (size_t)c * D * D;
+                double p = 0.0;
+                for (int i = tid; i < D; ++i) p = fma(lf[i * D + tid], v_x[i], p);     // (z L)^T = L^T z, rmhmc.py:80
+                v_p[tid] = p;
+            }
             __syncthreads();
+            double nrm = sqrt(dot(v_p, v_p));
+            if (nrm > 100.0) {                                                          // rmhmc.py:81-85
+                __syncthreads();
+                if (live) v_p[tid] /= nrm * 25.0;
+                if (tid == 0) ++S.renorm_mom[c];
+                __syncthreads();
+            }
+            nsteps = (int)ceil(u_step * (double)P.n_leapfrog);                          // rmhmc.py:89
+            sgn = z_dir > 0.5 ? 1 : -1;                                                 // rmhmc.py:90-93
         }
-        nsteps = (int)ceil(u_step * (double)P.n_leapfrog);                          // rmhmc.py:89
-        sgn = z_dir > 0.5 ? 1 : -1;                                                 // rmhmc.py:90-93
         matvec(v_p, v_u);
         double hcur = -S.logjoint[in_slot * P.slot_scalar + c] + S.logdet[in_slot * P.slot_scalar + c] +
                       0.5 * dot(v_p, v_u);                                          // rmhmc.py:175-176

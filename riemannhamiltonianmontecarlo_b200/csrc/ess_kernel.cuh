@@ -87,6 +87,37 @@ __global__ void __launch_bounds__(kEssThreads) k_ess(const double* __restrict__ 
         ess_out[(size_t)c * D + d] = (a0 > 0.0) ? (double)S / mono : __longlong_as_double(0x7ff8000000000000LL);
     }
 }
+// ---- tools.ac (tools.py:21-30): normalised circular autocorrelation, lags 0..n_lag, one series per
+// blockIdx.y, one lag per blockIdx.x.  acf[series][lag] is written UN-normalised; k_acf_normalise
+// divides by lag 0 afterwards.
+__global__ void __launch_bounds__(kEssThreads) k_acf_raw(const double* __restrict__ series, int S, int n_fft,
+                                                         int n_lag, double* __restrict__ acf) {
+    __shared__ double scratch[4];
+    const int k = blockIdx.x;
+    const double* x = series + (size_t)blockIdx.y * S;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < S; t += kEssThreads) s += x[t];
+    const double mean = block_sum_128(s, scratch) / S;
+    double a = 0.0;
+    if (k < S)
+        for (int t = threadIdx.x; t + k < S; t += kEssThreads) a += (x[t] - mean) * (x[t + k] - mean);
+    const int k2 = n_fft - k;                            // circular alias (nFFT = nextpow2(S) + 1)
+    if (k > 0 && k2 < S)
+        for (int t = threadIdx.x; t + k2 < S; t += kEssThreads) a += (x[t] - mean) * (x[t + k2] - mean);
+    a = block_sum_128(a, scratch);
+    if (threadIdx.x == 0) acf[(size_t)blockIdx.y * (n_lag + 1) + k] = a;
+}
+__global__ void k_acf_normalise(double* acf, int n_lag, int n_series) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_series * (n_lag + 1)) return;
+    int sidx = i / (n_lag + 1), k = i - sidx * (n_lag + 1);
+    double a0 = acf[(size_t)sidx * (n_lag + 1)];
+    if (k > 0) acf[i] /= a0;
+}
+__global__ void k_acf_lag0(double* acf, int n_lag, int n_series) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_series) acf[(size_t)s * (n_lag + 1)] = acf[(size_t)s * (n_lag + 1)] / acf[(size_t)s * (n_lag + 1)];
+}
 #endif
 
 }  // namespace rmhmc

@@ -127,6 +127,21 @@ class LogisticData:
         return l.cpu().numpy(), gi.cpu().numpy(), ld.cpu().numpy()
 
 
+    def leapfrog(self, theta, mom, direction, n_steps, step_size: float, n_fixed: int):
+        """Deterministic generalized leapfrog seam (rmhmc.py:96-163): ``n_steps[c]`` steps from
+        ``(theta[c], mom[c])`` in direction ``direction[c]``; returns (theta, mom, H_start, H_end)."""
+        t = self.torch
+        th, mo = self._dev(np.atleast_2d(theta)), self._dev(np.atleast_2d(mom))
+        c = th.shape[0]
+        di = self._dev(np.asarray(direction).reshape(c), dtype=np.int32)
+        ns = self._dev(np.asarray(n_steps).reshape(c), dtype=np.int32)
+        o_th, o_mo, h0, h1 = self._empty(c, self.dim), self._empty(c, self.dim), self._empty(c), self._empty(c)
+        _capi.check(self._lib.rmhmc_leapfrog(self.handle, c, _ptr(th), _ptr(mo), _ptr(di), _ptr(ns), float(step_size),
+                                             int(n_fixed), _ptr(o_th), _ptr(o_mo), _ptr(h0), _ptr(h1)),
+                    self.handle, "rmhmc_leapfrog")
+        return o_th.cpu().numpy(), o_mo.cpu().numpy(), h0.cpu().numpy(), h1.cpu().numpy()
+
+
 class _SamplerBase:
     _is_hmc = False
 
@@ -317,4 +332,20 @@ def ess_ragged(samples, starts, counts):
                             samples.stride(0), samples.stride(1), _ptr(starts), _ptr(counts), _ptr(out))
     if rc != 0:
         raise _capi.RmhmcError(f"blr_ess_ragged failed (code {rc})")
+    return out
+
+
+def autocorr_batched(series, n_lag: int):
+    """tools.ac for every row of ``series`` (n_series, S) -> device tensor (n_series, n_lag+1)."""
+    torch = _capi.require_cuda()
+    lib = _capi.load()
+    if isinstance(series, np.ndarray):
+        series = torch.from_numpy(np.ascontiguousarray(series, dtype=np.float64)).cuda()
+    series = series.contiguous()
+    n, s = series.shape
+    out = torch.empty(n, int(n_lag) + 1, dtype=torch.float64, device=series.device)
+    stream = torch.cuda.current_stream(series.device).cuda_stream
+    rc = lib.blr_autocorr(series.device.index or 0, c_void_p(stream), _ptr(series), n, s, int(n_lag), _ptr(out))
+    if rc != 0:
+        raise _capi.RmhmcError(f"blr_autocorr failed (code {rc})")
     return out

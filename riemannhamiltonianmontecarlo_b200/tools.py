@@ -1,16 +1,15 @@
 """Drop-in for the reference's ``code/tools.py``: LogNormPDF, nextpow2, ac, CalculateESS.
 
-``CalculateESS`` (the benchmark's metric, tools.py:32-74) runs on the GPU through
-``blr_ess_batched``; it raises without a CUDA device -- no CPU fallback.  ``LogNormPDF`` and
-``nextpow2`` are scalar host helpers (the samplers evaluate the Gaussian log-prior inside their
-kernels; this function exists for callers of the reference API) and ``ac`` returns the
-reference's circular autocorrelation for one series.
+``CalculateESS`` (the benchmark's metric, tools.py:32-74) and ``ac`` run on the GPU through
+``blr_ess_batched`` / ``blr_autocorr``; they raise without a CUDA device -- no CPU fallback.
+``LogNormPDF`` and ``nextpow2`` are scalar host helpers (the samplers evaluate the Gaussian
+log-prior inside their kernels; these exist for callers of the reference API).
 """
 from __future__ import annotations
 
 import numpy as np
 
-from .engine import ess_batched
+from .engine import autocorr_batched, ess_batched
 
 
 def LogNormPDF(Values, Means, Variance):
@@ -30,19 +29,9 @@ def nextpow2(i):
 
 
 def ac(Series, nLag):
-    """Normalised circular autocorrelation, lags 0..nLag, period nextpow2(len)+1 (tools.py:21-30)."""
+    """Normalised circular autocorrelation, lags 0..nLag, period nextpow2(len)+1 (tools.py:21-30), on the GPU."""
     x = np.asarray(Series, dtype=np.float64).flatten()
-    n = len(x)
-    n_fft = nextpow2(n) + 1
-    y = x - x.mean()
-    lin = np.correlate(y, y, mode="full")[n - 1:]          # lin[j] = sum_t y_t y_{t+j}
-    out = np.empty(nLag + 1)
-    for k in range(nLag + 1):
-        v = lin[k] if k < n else 0.0
-        if k > 0 and n_fft - k < n:
-            v += lin[n_fft - k]
-        out[k] = v
-    return out / out[0]
+    return autocorr_batched(x[None, :], int(nLag)).cpu().numpy()[0]
 
 
 def CalculateESS(Samples, MaxLag):

@@ -179,6 +179,10 @@ def test_ess_matches_reference(pkg, golden):
     assert rel_err(got, fx["ess_full"]) < 1e-9
     assert rel_err(pkg.CalculateESS(x[:599], 598), fx["ess_599"]) < 1e-9
     assert rel_err(pkg.CalculateESS(x, 50), fx["ess_lag50"]) < 1e-9
+    # tools.ac on the GPU, including lags beyond nFFT - n where the port's circular aliasing kicks in
+    for j in (0, 2, 3):
+        assert np.abs(pkg.ac(x[:, j], 200) - fx["ac_200"][:, j]).max() < 1e-12
+    assert np.abs(pkg.ac(x[:700, 3], 699) - bo.autocorr(x[:700, 3], 699)).max() < 1e-12
     # batched = column by column
     many = np.stack([x[:2000], x[1000:3000], x[3000:5000]])
     got = pkg.ess_batched(many).cpu().numpy()
@@ -303,3 +307,23 @@ def test_row_sharded_matches_unsharded_on_two_gpus(pkg):
     assert out.returncode == 0, out.stderr[-3000:]
     res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
     assert res["ok"], res
+
+
+@pytest.mark.parametrize("shape", ["australian", "german"])
+def test_leapfrog_seam_matches_oracle(pkg, shape):
+    """rmhmc_leapfrog: deterministic generalized leapfrog from given (theta, p), both directions."""
+    xx, t = pkg.datasets.shaped(shape)
+    d = xx.shape[1]
+    rng = np.random.default_rng(77)
+    c = 6
+    theta = rng.normal(0, 0.3, (c, d))
+    mom = rng.normal(0, 4.0, (c, d))
+    direction = np.array([1, -1, 1, -1, 1, -1])
+    n_steps = np.array([1, 2, 3, 4, 5, 6])
+    data = pkg.LogisticData(xx, t)
+    th, mo, h0, h1 = data.leapfrog(theta, mom, direction, n_steps, 0.5, 6)
+    data.close()
+    for i in range(c):
+        w_ref, p_ref, h0_ref, h1_ref = bo.leapfrog(xx, t, theta[i], mom[i], int(direction[i]), int(n_steps[i]), 0.5, 6)
+        assert rel_err(th[i], w_ref) < RTOL and rel_err(mo[i], p_ref) < RTOL
+        assert abs(h0[i] - h0_ref) < RTOL * abs(h0_ref) and abs(h1[i] - h1_ref) < RTOL * abs(h1_ref)
