@@ -372,7 +372,7 @@ int launch_tbuild(rmhmc_handle* h, int64_t C, const double* cbuf, double* tpack,
     dim3 grid((unsigned)((h->p3p + kTbCols - 1) / kTbCols), blocks_for(C, kTbChains));
     {
         Bracket b(h, 2);
-        k_tbuild<<<grid, 256, smem, h->stream>>>(a);
+        k_tbuild<<<grid, kTbThreads, smem, h->stream>>>(a);
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -410,7 +410,7 @@ void fill_engine_params(rmhmc_handle* h) {
 int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
     free_chains(h);
     h->n_chains = C;
-    h->c_pad = pad_up((int)C, 64);
+    h->c_pad = pad_up((int)C, kTbChains);
     h->is_hmc = hmc;
     auto* tr = &h->chain_allocs;
     size_t c = (size_t)C, D = (size_t)h->dim;
@@ -879,7 +879,7 @@ int rmhmc_metric_partials(rmhmc_handle* h, int64_t C, const double* theta, doubl
     std::vector<void*> tmp;
     double *gp = nullptr, *graw = nullptr, *ll = nullptr, *cbuf = nullptr, *tp = nullptr;
     int* cur = nullptr;
-    int64_t cpad = pad_up((int)C, 64);
+    int64_t cpad = pad_up((int)C, kTbChains);
     int rc = dev_alloc(h, &gp, (size_t)C * h->p2p, &tmp) | dev_alloc(h, &graw, (size_t)C * h->dim, &tmp) |
              dev_alloc(h, &ll, (size_t)C, &tmp) | dev_alloc(h, &cbuf, (size_t)cpad * h->n_rows_pad, &tmp) |
              dev_alloc(h, &tp, (size_t)C * h->p3p, &tmp) | dev_alloc(h, &cur, (size_t)C, &tmp);

@@ -141,9 +141,6 @@ __device__ __forceinline__ double fast_log1p_01(double e, const double* __restri
     return fma(p, r, tab[2 * j + 1]);
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
 
 // MODE 0: G only (position fixed-point iterates); 1: closing build (G, gradient, log-likelihood,
 // cbuf); 2: gradient and log-likelihood only (Euclidean HMC, hmc.py:52-53,60-61,65-66).

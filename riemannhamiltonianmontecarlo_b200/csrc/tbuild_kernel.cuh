@@ -6,14 +6,15 @@
 // tensor cores (DMMA.8x8x4):
 //     T[chains x P3] = Cw[chains x rows] . KR3(X)[rows x P3],  KR3(X)[n,(i,j,k)] = x_ni x_nj x_nk
 // KR3 is never materialised: each lane forms its B-fragment element from three staged X values.
-// Cw tiles (written by the closing metric build) stream through cp.async, X row blocks through
-// 1-D bulk TMA, in a 3-stage ring.  This kernel carries ~60% of the algorithmic flops.
+// Cw tiles (written by the closing metric build) and X row blocks both stream through 1-D bulk TMA
+// into a 3-stage mbarrier ring filled by a dedicated producer warp.  This kernel carries ~60% of the
+// algorithmic flops.
 #pragma once
 #include "common.cuh"
 
 namespace rmhmc {
 
-constexpr int kTbChains = 64;     // chains per CTA
+constexpr int kTbChains = 128;    // chains per CTA
 constexpr int kTbCols = 128;      // packed-triple columns per CTA
 constexpr int kTbRows = 32;       // rows per staged block (K tile)
 constexpr int kTbStages = 3;
@@ -31,53 +32,58 @@ struct TBuildArgs {
 };
 
 __host__ inline size_t tbuild_smem_bytes(int xs) {
-    return (size_t)kTbStages * ((size_t)kTbChains * kTbAS + (size_t)kTbRows * xs) * 8 + 64;
+    return (size_t)kTbStages * ((size_t)kTbChains * kTbAS + (size_t)kTbRows * xs) * 8 + 2 * kTbStages * 8;
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(256, 2) k_tbuild(TBuildArgs a) {
+// 16 warps, 4 x 4 over the 128 x 128 tile (32 chains x 32 columns each).  The 3-stage ring is filled
+// with bulk TMA only -- 128 row segments of Cw (256 B each, landing in the padded smem rows; every warp
+// issues 8 of them) and one contiguous X row block per stage -- all completing on the stage's `full`
+// mbarrier; a stage is refilled once all 16 warps have released it through its `empty` mbarrier.  There
+// is no CTA-wide barrier in the main loop, so warps drift apart and their fragment loads overlap the
+// other warps' DMMAs.
+constexpr int kTbWarps = 16;
+constexpr int kTbThreads = kTbWarps * 32;
+
+__global__ void __launch_bounds__(kTbThreads, 1) k_tbuild(TBuildArgs a) {
     constexpr int MC = kTbChains, KB = kTbRows, AS = kTbAS, ST = kTbStages;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int xs = a.xs;
     double* a_ring = reinterpret_cast<double*>(smem_raw);                 // [ST][MC][AS]
     double* x_ring = a_ring + (size_t)ST * MC * AS;                       // [ST][KB][xs]
     uint64_t* full = reinterpret_cast<uint64_t*>(x_ring + (size_t)ST * KB * xs);
+    uint64_t* empty = full + ST;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-    const int wm = warp & 1, wn = warp >> 1;
     const int chain0 = blockIdx.y * MC;
-    const int col0 = blockIdx.x * kTbCols + wn * 32;
     if (chain0 >= a.n_chains) return;
     const int n_blocks = a.n_rows_pad / KB;
     const uint32_t x_bytes = (uint32_t)(KB * xs * 8);
+    const uint32_t stage_bytes = x_bytes + (uint32_t)(MC * KB * 8);
 
     if (tid == 0) {
-        for (int s = 0; s < ST; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTbWarps); }
         mbar_fence_init();
     }
     __syncthreads();
 
-    auto issue = [&](int rb, int stage) {
-        // Cw tile: 64 chains x 32 rows, 16-byte chunks
-        double* as = a_ring + (size_t)stage * MC * AS;
-#pragma unroll
-        for (int i = 0; i < (MC * KB / 2) / 256; ++i) {
-            int chunk = tid + i * 256;           // 0..1023
-            int m = chunk >> 4, part = chunk & 15;
-            cp_async16(as + (size_t)m * AS + part * 2,
-                       a.cbuf + (size_t)(chain0 + m) * a.n_rows_pad + (size_t)rb * KB + part * 2);
-        }
+    // every warp loads 8 chain rows of the Cw tile; warp 0 also arms the barrier and loads the X block
+    auto issue = [&](int rb) {
+        const int stage = rb % ST;
         if (tid == 0) {
-            mbar_expect_tx(&full[stage], x_bytes);
+            mbar_expect_tx(&full[stage], stage_bytes);
             tma_bulk_g2s(x_ring + (size_t)stage * KB * xs, a.x + (size_t)rb * KB * xs, x_bytes, &full[stage]);
         }
+        if (lane < MC / kTbWarps) {
+            const int m = warp * (MC / kTbWarps) + lane;
+            tma_bulk_g2s(a_ring + ((size_t)stage * MC + m) * AS,
+                         a.cbuf + (size_t)(chain0 + m) * a.n_rows_pad + (size_t)rb * KB, (uint32_t)(KB * 8), &full[stage]);
+        }
     };
+    for (int s = 0; s < ST - 1 && s < n_blocks; ++s) issue(s);
 
-    for (int s = 0; s < ST - 1; ++s) {
-        if (s < n_blocks) issue(s, s);
-        cp_async_commit();
-    }
-
+    const int wm = warp & 3, wn = warp >> 2;
+    const int col0 = blockIdx.x * kTbCols + wn * 32;
     int ti[4], tj[4], tk[4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
@@ -93,13 +99,7 @@ __global__ void __launch_bounds__(256, 2) k_tbuild(TBuildArgs a) {
 
     for (int rb = 0; rb < n_blocks; ++rb) {
         const int stage = rb % ST;
-        // prefetch block rb+ST-1 into the stage freed at the end of iteration rb-1
-        if (rb + ST - 1 < n_blocks) issue(rb + ST - 1, (rb + ST - 1) % ST);
-        cp_async_commit();
-        cp_async_wait<ST - 1>();
         mbar_wait(&full[stage], (uint32_t)((rb / ST) & 1));
-        __syncthreads();
-
         const double* as = a_ring + (size_t)stage * MC * AS + (size_t)(wm * 32 + g) * AS + q;
         const double* xb = x_ring + (size_t)stage * KB * xs;
 #pragma unroll 2
@@ -115,7 +115,14 @@ __global__ void __launch_bounds__(256, 2) k_tbuild(TBuildArgs a) {
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) dmma884(acc[m][nt][0], acc[m][nt][1], af[m], bf[nt]);
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        // refill the stage of block rb-1 (released by everybody by now, or very soon) with block rb+ST-1
+        const int nb = rb + ST - 1;
+        if (nb < n_blocks) {
+            if (rb >= 1) mbar_wait(&empty[nb % ST], (uint32_t)(((rb - 1) / ST) & 1));
+            issue(nb);
+        }
     }
 
 #pragma unroll

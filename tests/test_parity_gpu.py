@@ -327,3 +327,24 @@ def test_leapfrog_seam_matches_oracle(pkg, shape):
         w_ref, p_ref, h0_ref, h1_ref = bo.leapfrog(xx, t, theta[i], mom[i], int(direction[i]), int(n_steps[i]), 0.5, 6)
         assert rel_err(th[i], w_ref) < RTOL and rel_err(mo[i], p_ref) < RTOL
         assert abs(h0[i] - h0_ref) < RTOL * abs(h0_ref) and abs(h1[i] - h1_ref) < RTOL * abs(h1_ref)
+
+
+def test_main_py_harness_runs_headless(pkg, tmp_path):
+    """main.py:20-79 workflow: CSV -> preprocessing -> repeated chains -> averaged-chain ESS summary."""
+    from riemannhamiltonianmontecarlo_b200 import harness
+    rng = np.random.default_rng(5)
+    x = rng.normal(2.0, 3.0, (300, 5))
+    beta = rng.normal(0, 1, 5)
+    lab = (rng.random(300) < 1 / (1 + np.exp(-((x - 2.0) / 3.0) @ beta))).astype(float) + 1.0      # labels {1, 2}
+    path = tmp_path / "toy.csv"
+    np.savetxt(path, np.hstack([x, lab[:, None]]), delimiter=",")
+    XX, t = pkg.datasets.load_csv(str(path), relabel_12=True)
+    out = harness.run_experiments(XX, t, "rmhmc", n_experiments=4, NumOfIterations=300, BurnIn=60, seed=3, verbose=False,
+                                  NumOfNewtonSteps=5)
+    assert out["results_beta"].shape == (4, 240, 6) and out["ESS"].shape == (6, 1)
+    assert out["Min"] > 20 and 0.6 < out["accept_rate"] <= 1.0 and out["TimePerMinESS"] > 0
+    ref = bo.ess(out["avg_beta_posterior"], 239)
+    assert rel_err(out["ESS"], ref) < 1e-9
+    out_h = harness.run_experiments(XX, t, "hmc", n_experiments=3, NumOfIterations=200, BurnIn=50, verbose=False,
+                                    StepSize=0.1, NumOfLeapFrogSteps=30)
+    assert out_h["results_beta"].shape == (3, 150, 6) and out_h["accept_rate"] > 0.3
