@@ -66,6 +66,7 @@ struct rmhmc_handle {
     double alpha = 100.0;
     // data set
     double* x_pad = nullptr;
+    double* kr3 = nullptr;          // [Np][P3p] KR3(X), only when it fits kKr3Budget (else formed on the fly)
     uchar2* pair_tab = nullptr;
     uchar4* tri_tab = nullptr;
     unsigned short* tidx = nullptr;
@@ -367,12 +368,20 @@ int launch_tbuild(rmhmc_handle* h, int64_t C, const double* cbuf, double* tpack,
     a.x = h->x_pad; a.tri_tab = h->tri_tab; a.cbuf = cbuf; a.tpack = tpack; a.cur = cur; a.flip = flip;
     a.slot_stride = slot_stride; a.n_chains = (int)C; a.n_rows_pad = h->n_rows_pad; a.xs = h->xs;
     a.p3 = h->p3; a.p3p = h->p3p;
-    size_t smem = tbuild_smem_bytes(h->xs);
-    CUDA_TRY(h, cudaFuncSetAttribute(k_tbuild, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a.kr3 = h->kr3;
     dim3 grid((unsigned)((h->p3p + kTbCols - 1) / kTbCols), blocks_for(C, kTbChains));
-    {
+    if (h->kr3) {
+        size_t smem = tbuild_pre_smem_bytes();
+        CUDA_TRY(h, cudaFuncSetAttribute(k_tbuild_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Bracket b(h, 2);
-        k_tbuild<<<grid, kTbThreads, smem, h->stream>>>(a);
+        k_tbuild_pre<<<grid, kTbThreads, smem, h->stream>>>(a);
+    } else {
+        const int stages = tbuild_stages(h->xs);
+        size_t smem = tbuild_smem_bytes(h->xs, stages);
+        auto kern = stages == 3 ? k_tbuild<3> : k_tbuild<2>;
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        Bracket b(h, 2);
+        kern<<<grid, kTbThreads, smem, h->stream>>>(a);
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -788,6 +797,16 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
     int64_t total = (int64_t)h->n_rows_pad * h->xs;
     k_pad_design<<<blocks_for(total, 256), 256>>>(xx_dev, t_dev, h->x_pad, n_rows, dim, h->xs, h->n_rows_pad);
     CREATE_TRY(cudaGetLastError());
+    {
+        const size_t kKr3Budget = (size_t)1 << 30;      // 1 GiB: German-shaped needs 23 MB, Australian-shaped 4 MB
+        size_t bytes = (size_t)h->n_rows_pad * h->p3p * 8;
+        if (bytes <= kKr3Budget) {
+            CREATE_TRY(cudaMalloc((void**)&h->kr3, bytes));
+            long long n = (long long)h->n_rows_pad * h->p3p;
+            k_form_kr3<<<blocks_for(n, 256), 256>>>(h->x_pad, h->tri_tab, h->kr3, h->n_rows_pad, h->xs, h->p3p);
+            CREATE_TRY(cudaGetLastError());
+        }
+    }
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
     h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
@@ -802,7 +821,7 @@ void rmhmc_destroy(rmhmc_handle* h) {
     drain_profile(h);
     free_chains(h);
     if (h->comm) nccl_api().CommDestroy(h->comm);
-    cudaFree(h->x_pad); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
+    cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
     cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
     delete h;
 }
@@ -813,6 +832,11 @@ int rmhmc_update_data(rmhmc_handle* h, const double* xx_dev, const double* t_dev
     int64_t total = (int64_t)h->n_rows_pad * h->xs;
     k_pad_design<<<blocks_for(total, 256), 256, 0, h->stream>>>(xx_dev, t_dev, h->x_pad, h->n_rows, h->dim, h->xs, h->n_rows_pad);
     h->launches += 1;
+    if (h->kr3) {
+        long long n = (long long)h->n_rows_pad * h->p3p;
+        k_form_kr3<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->x_pad, h->tri_tab, h->kr3, h->n_rows_pad, h->xs, h->p3p);
+        h->launches += 1;
+    }
     CUDA_TRY(h, cudaGetLastError());
     return RMHMC_OK;
 }
