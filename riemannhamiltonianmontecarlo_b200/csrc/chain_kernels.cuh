@@ -102,16 +102,27 @@ __device__ __forceinline__ void load_packed_rows(const double* __restrict__ gp, 
 // sum_k log L_kk = 0.5 log|G| (rmhmc.py:171,175); dinv = 1 / L[lane][lane].  A non-PD matrix yields
 // NaNs, which the accept test then rejects (the reference would raise LinAlgError; it cannot happen
 // since G >= I/alpha).
+// 1/sqrt(a): rsqrt.approx.ftz.f64 (20-bit seed) + two Newton steps (~1 ulp); NaN for a < 0 like sqrt
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double h = 0.5 * a;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+}
+
 template <int DMAX>
 __device__ __forceinline__ double chol_regs(double (&row)[DMAX], int D, int lane, double& dinv) {
-    double diag = 1.0;
+    double diag = 1.0, dinv_acc = 0.0;
 #pragma unroll
     for (int k = 0; k < DMAX; ++k) {
         if (k < D) {
-            double lkk = sqrt(__shfl_sync(kFull, row[k], k));
-            double inv = 1.0 / lkk;
+            double akk = __shfl_sync(kFull, row[k], k);
+            double inv = fast_rsqrt(akk);
+            double lkk = akk * inv;
             double lik = (lane == k) ? lkk : row[k] * inv;
-            if (lane == k) diag = lkk;
+            if (lane == k) { diag = lkk; dinv_acc = inv; }
             row[k] = lik;
 #pragma unroll
             for (int j = k + 1; j < DMAX; ++j) {
@@ -122,7 +133,37 @@ __device__ __forceinline__ double chol_regs(double (&row)[DMAX], int D, int lane
             }
         }
     }
-    dinv = 1.0 / diag;
+    dinv = dinv_acc;
+    return warp_sum(lane < D ? log(diag) : 0.0);
+}
+
+// Same factorisation, but column k is broadcast through a 32-double shared buffer (one LDS per
+// trailing element instead of two SHFL): fewer instructions in the instruction-bound per-chain kernels.
+template <int DMAX>
+__device__ __forceinline__ double chol_regs_sm(double (&row)[DMAX], double* colbuf, int D, int lane, double& dinv) {
+    double diag = 1.0, dinv_acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) {
+        if (k < D) {
+            double akk = __shfl_sync(kFull, row[k], k);
+            double inv = fast_rsqrt(akk);
+            double lkk = akk * inv;
+            double lik = (lane == k) ? lkk : row[k] * inv;
+            if (lane == k) { diag = lkk; dinv_acc = inv; }
+            row[k] = lik;
+            __syncwarp();
+            colbuf[lane] = lik;
+            __syncwarp();
+#pragma unroll
+            for (int j = k + 1; j < DMAX; ++j) {
+                if (j < D) {
+                    double ljk = colbuf[j];
+                    if (lane >= j) row[j] = fma(-lik, ljk, row[j]);
+                }
+            }
+        }
+    }
+    dinv = dinv_acc;
     return warp_sum(lane < D ? log(diag) : 0.0);
 }
 
@@ -381,7 +422,7 @@ __global__ void __launch_bounds__(32) k_chain_factor(EngineParams P, ChainArrays
     {
         double lrow[DMAX];
         load_packed_rows<DMAX>(S.g_tmp + (size_t)c * P.p2p, lrow, D, lane);
-        double logdet = chol_regs<DMAX>(lrow, D, lane, dinv);
+        double logdet = chol_regs_sm<DMAX>(lrow, Msm, D, lane, dinv);      // Msm doubles as the column buffer
         store_rows<DMAX>(Lsm, lrow, D, DS, lane);
         if (lane == 0) S.logdet[out * P.slot_scalar + c] = logdet;
     }
@@ -717,7 +758,7 @@ __global__ void __launch_bounds__(32) k_chain_solve(EngineParams P, ChainArrays 
     double p = live ? S.mom[(size_t)c * D + lane] : 0.0;
     double w = live ? S.theta[in_slot * P.slot_theta + (size_t)c * D + lane] : 0.0;
     double u0 = live ? S.u0[(size_t)c * D + lane] : 0.0;
-    chol_regs<DMAX>(lrow, D, lane, dinv);
+    chol_regs_sm<DMAX>(lrow, Lsm, D, lane, dinv);                                  // Lsm doubles as the column buffer
     store_rows<DMAX>(Lsm, lrow, D, DS, lane);
     double u = chol_solve_regs<DMAX>(lrow, Lsm, dinv, D, DS, lane, p);             // rmhmc.py:121
     double pw = w + (S.dir[c] * P.step_size / 2) * (u0 + u);                        // rmhmc.py:122
