@@ -379,9 +379,12 @@ __device__ __forceinline__ void tensor_contract(const double* Tsm, const double 
 template <int NCH>
 __device__ __forceinline__ void quad_terms(const EngineParams& P, const PairRegs<NCH>& pr, const double* Tsm,
                                            const double* u, double* out, int warp, int n_warps, int lane) {
+    // every warp holds u in its lanes and picks u_a, u_b by shuffle (no shared-memory gathers)
+    const double ul = lane < P.dim ? u[lane] : 0.0;
     double q[NCH];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) q[ch] = pr.w[ch] * u[pr.pa[ch]] * u[pr.pb[ch]];
+    for (int ch = 0; ch < NCH; ++ch)
+        q[ch] = pr.w[ch] * __shfl_sync(kFull, ul, pr.pa[ch]) * __shfl_sync(kFull, ul, pr.pb[ch]);
     tensor_contract<NCH>(Tsm, q, P.tidx, out, P.dim, P.p2, warp, n_warps, lane);
 }
 
@@ -534,9 +537,12 @@ k_chain_turn(EngineParams P, ChainArrays S, int do_back, int do_front, int init)
         __syncthreads();
     };
     auto dot = [&](const double* x, const double* y) {     // every thread gets the same value
-        double s = 0.0;
-        for (int b = 0; b < D; ++b) s = fma(x[b], y[b], s);
-        return s;
+        if (BIG) {
+            double s = 0.0;
+            for (int b = 0; b < D; ++b) s = fma(x[b], y[b], s);
+            return s;
+        }
+        return warp_sum(lane < D ? x[lane] * y[lane] : 0.0);    // D <= 32: one lane per term, fixed butterfly
     };
 
     if (do_back) {
