@@ -562,9 +562,9 @@ k_chain_turn(EngineParams P, ChainArrays S, int do_back, int do_front, int init)
             }
             __syncthreads();
             trace(v_tr);
+            const double half_log = 0.5 * log(2.0 * 3.14159265358979323846 * P.alpha);
             double lp = 0.0;
-            for (int b = 0; b < D; ++b)
-                lp += -0.5 * log(2.0 * 3.14159265358979323846 * P.alpha) - v_th[b] * v_th[b] / (2.0 * P.alpha);
+            for (int b = 0; b < D; ++b) lp += -half_log - v_th[b] * v_th[b] / (2.0 * P.alpha);
             const double ljl = S.loglik_tmp[c] + lp;                        // rmhmc.py:166-169, tools.py:10-14
             const double logdet = S.logdet[out * P.slot_scalar + c];
             if (live) {
