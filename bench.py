@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--workload", default="german", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: per workload)")
     ap.add_argument("--rounds-per-step", type=int, default=0)
+    ap.add_argument("--partials", default="matrix_free", choices=["matrix_free", "tensor"],
+                    help="how the engine evaluates the metric partials (include/rmhmc_b200.h)")
     ap.add_argument("--ref-iters-per-step", type=int, default=30)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,7 +241,7 @@ def gpu_main(args):
     xx_dev = torch.empty_like(xx_host, device=device)
     t_dev = torch.empty_like(t_host, device=device)
 
-    data = r.LogisticData(xx, t, device=device)
+    data = r.LogisticData(xx, t, device=device, partials=args.partials)
     sampler = r.RMHMCSampler(data, C, N_LEAPFROG, STEP_SIZE, N_FIXED)
     sampler.set_philox(20261018, chain_offset=rank * C)
     total_rounds = (W + K * (1 if args.no_e2e else 2)) * R
@@ -364,34 +366,50 @@ def gpu_main(args):
             dist.destroy_process_group()
         return 0
 
-    # ---------------------------------------------------------------- roofline (dominant kernel: partials build)
-    part_ms, part_n = prof["partials"]
-    flops_per_launch = 2.0 * C * N * P3                       # algorithmic: packed symmetric contraction
-    achieved = flops_per_launch / (part_ms / max(part_n, 1) * 1e-3) / 1e12 if part_n else None
+    # ---------------------------------------------------------------- roofline (dominant kernel of the mode)
+    # algorithmic flops per launch (packed symmetric contractions)
+    alg_flops = {"metric_fp": 2.0 * C * N * (P2 + D), "metric_closing": 2.0 * C * N * (P2 + 2 * D),
+                 "partials": 2.0 * C * N * P3, "quad_pass": 4.0 * C * N * D, "leverage_gemm": 2.0 * C * N * P2,
+                 "trace_pass": 2.0 * C * N * D}
+    if args.partials == "tensor":
+        top, top_name = "partials", "k_tbuild_pre (partials build T = Cw . KR3(X), FP64 DMMA.8x8x4)"
+        w_alg = 2.0 * N * P3 + 2.0 * N_FIXED * N * P2         # SURVEY.md 8d, per chain-leapfrog-step
+    else:
+        top, top_name = "metric_fp", "k_metric<MODE 0> (f = X theta, G = V . KR2(X), FP64 DMMA.8x8x4)"
+        # F metric builds + leverage GEMM + (F + 1) quadratic-form passes + trace pass
+        w_alg = 2.0 * N_FIXED * N * (P2 + D) + 2.0 * N * P2 + (N_FIXED + 1) * 4.0 * N * D + 2.0 * N * D
+    top_ms, top_n = prof[top]
+    flops_per_launch = alg_flops[top]
+    achieved = flops_per_launch / (top_ms / max(top_n, 1) * 1e-3) / 1e12 if top_n else None
     microbench_peak = 37.1                                     # profiles/microbench/r01_fp64_peak_b200.txt
     peak = max(fp64_peak, microbench_peak)
     kernels = {}
-    alg_flops = {"metric_fp": 2.0 * C * N * P2, "metric_closing": 2.0 * C * N * P2, "partials": flops_per_launch}
     wall_ms = seconds * 1e3
     for name, (ms, n) in prof.items():
+        if not n:
+            continue
         kernels[name] = {"launches": n, "ms_total": ms, "ms_avg": ms / max(n, 1), "share_of_step": ms / wall_ms}
         if name in alg_flops and n:
             kernels[name]["tflops_alg"] = alg_flops[name] / (ms / n * 1e-3) / 1e12
-    w_alg = 2.0 * N * P3 + 2.0 * N_FIXED * N * P2             # SURVEY.md 8d, per chain-leapfrog-step
+    if args.partials == "tensor":
+        ws_note = "per-round working set (T slots + cbuf, %.1f GB) exceeds the 126 MB L2" % (
+            (2 * C * (P3 + 8) * 8 + C * 1024 * 8) / 1e9)
+    else:
+        ws_note = "per-round working set (c_n slots + leverages + G^-1/L per chain, %.1f GB) exceeds the 126 MB L2" % (
+            (3 * C * 1024 * 8 + 4 * C * D * D * 8) / 1e9)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": seconds / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": descr, "chains_per_gpu": C, "chains_total": C * world, "rounds_per_step": R,
-                   "rng": "philox4x32-10 on device",
-                   "l2": "per-round working set (T slots + cbuf, %.1f GB) exceeds the 126 MB L2" %
-                         ((2 * C * (P3 + 8) * 8 + C * 1024 * 8) / 1e9)},
+                   "rng": "philox4x32-10 on device", "partials": args.partials, "l2": ws_note},
         "leapfrog_steps_per_sec": leapfrogs / seconds,
         "iterations_per_sec": iters_done / seconds,
         "samples_in_timed_region": n_samples, "accept_rate": accept, "renorm_events": renorm,
         "rhat_max": rhat_max,
         "alg_tflops_overall": w_alg * leapfrogs / seconds / 1e12 / world,
-        "roofline": {"bound": "tensor", "kernel": "k_tbuild (partials build, FP64 DMMA.8x8x4)",
+        "alg_flops_per_chain_leapfrog": w_alg,
+        "roofline": {"bound": "tensor", "kernel": top_name,
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None,
                      "peak_source": "max(cuBLAS DGEMM 4096^3 measured live = %.1f, DMMA issue microbenchmark = %.1f); "

@@ -51,6 +51,16 @@ void rmhmc_destroy(rmhmc_handle* h);
  * handle's stream.  This is what a caller that owns host buffers does before each batch of rounds. */
 int rmhmc_update_data(rmhmc_handle* h, const double* xx_dev, const double* t_dev);
 const char* rmhmc_last_error(const rmhmc_handle* h);
+/* How the engine evaluates the metric partials dG/dw_d = X^T diag(v (1-2p) x_d) X (rmhmc.py:64-77,142-161):
+ *   TENSOR       build the packed symmetric tensor T (all D partials) per chain and contract it per chain --
+ *                what the reference does, with the symmetry exploited (O(N D^3) per chain and leapfrog step);
+ *   MATRIX_FREE  never form them: tr(G^-1 dG_d) = sum_n c_n x_nd (x_n^T G^-1 x_n) and
+ *                p^T G^-1 dG_d G^-1 p = sum_n c_n x_nd (x_n . G^-1 p)^2 as passes over the data (O(N D^2));
+ *                same numbers up to summation order.  Default when KR2(X)^T fits in device memory.
+ * Frees the handle's chains (call before *_chains_init).  rmhmc_metric_partials always builds the tensor. */
+enum { RMHMC_PARTIALS_TENSOR = 0, RMHMC_PARTIALS_MATRIX_FREE = 1 };
+int rmhmc_set_partials_mode(rmhmc_handle* h, int mode);
+int rmhmc_get_partials_mode(const rmhmc_handle* h);
 /* Row-sharded data (very large N): every rank binds ITS rows with rmhmc_create and runs ALL chains;
  * each metric / partials build then ends in one NCCL all-reduce (sum) of the partial
  * G | X^T(t-p) | log-likelihood block resp. of T, after which the per-chain stages run replicated
@@ -143,8 +153,9 @@ int64_t rmhmc_launch_count(const rmhmc_handle* h);
 
 /* CUDA-event timing of the engine's kernels: when enabled, every launch of a given kernel class is
  * bracketed by events on the handle's stream.  kind: 0 metric build (position iterates),
- * 1 metric build (closing), 2 partials build, 3 per-chain turn (end of one leapfrog step + start of
- * the next), 4 per-chain position solve.  Returns accumulated
+ * 1 metric build (closing), 2 partials build (tensor mode), 3 per-chain turn (end of one leapfrog step +
+ * start of the next; matrix-free: also the momentum iterates), 4 per-chain position solve / factorisation,
+ * 5 quadratic-form pass, 6 leverage GEMM, 7 trace pass (matrix-free mode).  Returns accumulated
  * milliseconds and launch count since the last reset; synchronises. */
 int rmhmc_profile_enable(rmhmc_handle* h, int enable);
 int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches);

@@ -21,6 +21,8 @@ SIGNATURES = {
     "rmhmc_destroy": (None, [c_void_p]),
     "rmhmc_last_error": (c_char_p, [c_void_p]),
     "rmhmc_update_data": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "rmhmc_set_partials_mode": (c_int, [c_void_p, c_int]),
+    "rmhmc_get_partials_mode": (c_int, [c_void_p]),
     "rmhmc_comm_unique_id": (c_int, [c_char_p]),
     "rmhmc_comm_init": (c_int, [c_void_p, c_int, c_int, c_char_p]),
     "rmhmc_set_stream": (c_int, [c_void_p, c_void_p]),

@@ -9,13 +9,14 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "librmhmc_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["common.cuh", "metric_kernel.cuh", "tbuild_kernel.cuh", "chain_kernels.cuh", "chain_big.cuh", "hmc_kernels.cuh",
+HEADERS = ["common.cuh", "metric_kernel.cuh", "tbuild_kernel.cuh", "chain_kernels.cuh", "chain_big.cuh", "mf_kernels.cuh", "hmc_kernels.cuh",
            "ess_kernel.cuh", os.path.join("..", "..", "include", "rmhmc_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
     "-Xptxas", "-v", "-ldl",
+    "-split-compile", "0",          # optimise the ~130 kernel instantiations of the single TU on all host cores
 ]
 
 

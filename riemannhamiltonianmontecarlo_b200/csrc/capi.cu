@@ -16,6 +16,7 @@
 #include "ess_kernel.cuh"
 #include "hmc_kernels.cuh"
 #include "metric_kernel.cuh"
+#include "mf_kernels.cuh"
 #include "tbuild_kernel.cuh"
 
 using namespace rmhmc;
@@ -67,6 +68,9 @@ struct rmhmc_handle {
     // data set
     double* x_pad = nullptr;
     double* kr3 = nullptr;          // [Np][P3p] KR3(X), only when it fits kKr3Budget (else formed on the fly)
+    double* kr2t = nullptr;         // [P2k][Np] KR2(X)^T: B operand of the leverage GEMM (matrix-free partials)
+    int p2k = 0;                    // P2 padded to the GEMM's K tile
+    bool matrix_free = false;       // partials mode of the engine (rmhmc_set_partials_mode)
     uchar2* pair_tab = nullptr;
     uchar4* tri_tab = nullptr;
     unsigned short* tidx = nullptr;
@@ -87,7 +91,7 @@ struct rmhmc_handle {
     ncclComm_t comm = nullptr;
     int shard_world = 1, shard_rank = 0;
     double* t_tmp = nullptr;        // [C][P3p] contiguous partials of the last build (sharded mode)
-    ProfSlot prof[5];
+    ProfSlot prof[8];
     mutable std::string err;
 };
 
@@ -120,6 +124,21 @@ __global__ void k_pad_design(const double* __restrict__ xx, const double* __rest
         else if (col == xs - 1) v = t[r];
     }
     xp[i] = v;
+}
+
+// KR2(X)^T: row k = packed pair (a, b), column n = design-matrix row: x_na x_nb (zero rows for k >= P2)
+__global__ void k_form_kr2t(const double* __restrict__ x, const uchar2* __restrict__ pair_tab, double* __restrict__ kr2t,
+                            long long n_rows_pad, int xs, int p2, int p2k) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_rows_pad * p2k) return;
+    int k = (int)(i / n_rows_pad);
+    long long n = i - (long long)k * n_rows_pad;
+    double v = 0.0;
+    if (k < p2) {
+        uchar2 ab = pair_tab[k];
+        v = x[n * xs + ab.x] * x[n * xs + ab.y];
+    }
+    kr2t[i] = v;
 }
 
 __global__ void k_fill(double* p, int64_t n, double v) {
@@ -324,10 +343,10 @@ FuseArgs fuse_args(rmhmc_handle* h, int mode, int is_last, int init) {
 template <int MODE>
 int launch_metric(rmhmc_handle* h, const MetricArgs& a, const FuseArgs& fz = FuseArgs{}) {
     size_t smem = metric_smem_bytes(h->xs, h->p2p, fz.mode != kFuseNone);
-    dim3 grid(blocks_for(a.n_chains, kMetricChains), MODE == 2 ? (unsigned)((h->dim + 31) / 32) : (unsigned)h->col_ctas);
+    dim3 grid(blocks_for(a.n_chains, kMetricChains), MODE >= 2 ? (unsigned)((h->dim + 31) / 32) : (unsigned)h->col_ctas);
     if (fz.mode != kFuseNone && grid.y != 1) return fail(h, RMHMC_E_UNSUPPORTED, "fused epilogues need a single column CTA");
     void (*kern)(MetricArgs, FuseArgs) = nullptr;
-    int nt = MODE == 2 ? 1 : h->nt;
+    int nt = MODE >= 2 ? 1 : h->nt;
     switch (nt) {
         case 1: kern = k_metric<1, MODE>; break;
         case 2: kern = k_metric<2, MODE>; break;
@@ -342,7 +361,7 @@ int launch_metric(rmhmc_handle* h, const MetricArgs& a, const FuseArgs& fz = Fus
     }
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
-        Bracket b(h, MODE == 0 ? 0 : 1);
+        Bracket b(h, MODE == 0 ? 0 : (MODE == 3 ? 5 : (MODE == 4 ? 7 : 1)));
         kern<<<grid, kMetricThreads, smem, h->stream>>>(a, fz);
     }
     h->launches += 1;
@@ -359,6 +378,21 @@ MetricArgs metric_args(rmhmc_handle* h, int64_t C, const double* theta, double* 
     a.n_chains = (int)C; a.n_rows = (int)h->n_rows; a.n_rows_pad = h->n_rows_pad;
     a.dim = h->dim; a.xs = h->xs; a.p2 = h->p2; a.p2p = h->p2p;
     a.alpha_inv = h->shard_rank == 0 ? 1.0 / h->alpha : 0.0;      // the prior term I/alpha is added once across shards
+    return a;
+}
+
+// closing build of the engine: in matrix-free mode c_n goes to the proposal (flip = 1) / current (flip = 0) slot
+MetricArgs closing_args(rmhmc_handle* h, int flip) {
+    ChainArrays& S = h->S;
+    MetricArgs a = metric_args(h, h->n_chains, S.theta_w, S.g_tmp, S.grad_tmp, S.loglik_tmp, h->matrix_free ? S.cw : S.cbuf);
+    if (h->matrix_free) { a.cw_cur = S.cur; a.cw_flip = flip; a.cw_slot = h->P.slot_cw; }
+    return a;
+}
+// passes over the data of the matrix-free mode: MODE 3 quadratic forms (u = uvec), MODE 4 traces (h = hbuf)
+MetricArgs pass_args(rmhmc_handle* h, double* out) {
+    ChainArrays& S = h->S;
+    MetricArgs a = metric_args(h, h->n_chains, S.uvec, nullptr, out, nullptr, S.cw);
+    a.aslot = S.aslot; a.cw_slot = h->P.slot_cw; a.hbuf = S.hbuf;
     return a;
 }
 
@@ -382,6 +416,24 @@ int launch_tbuild(rmhmc_handle* h, int64_t C, const double* cbuf, double* tpack,
         CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Bracket b(h, 2);
         kern<<<grid, kTbThreads, smem, h->stream>>>(a);
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+// leverages of the newest metric, hbuf[c][n] = x_n^T G_c^-1 x_n = sum_pairs q_c[pair] KR2(X)[n][pair]: the same
+// TMA-fed DMMA GEMM as the partials build with (A, B, K, columns) = (qpack, KR2(X)^T, P2k, Np)
+int launch_leverage(rmhmc_handle* h) {
+    TBuildArgs a{};
+    a.kr3 = h->kr2t; a.cbuf = h->S.qpack; a.tpack = h->S.hbuf; a.cur = h->S.cur; a.flip = 0; a.slot_stride = 0;
+    a.n_chains = (int)h->n_chains; a.n_rows_pad = h->p2k; a.p3 = h->n_rows_pad; a.p3p = h->n_rows_pad;
+    dim3 grid((unsigned)((h->n_rows_pad + kTbCols - 1) / kTbCols), blocks_for(h->n_chains, kTbChains));
+    size_t smem = tbuild_pre_smem_bytes();
+    CUDA_TRY(h, cudaFuncSetAttribute(k_tbuild_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        Bracket b(h, 6);
+        k_tbuild_pre<<<grid, kTbThreads, smem, h->stream>>>(a);
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -414,6 +466,7 @@ void fill_engine_params(rmhmc_handle* h) {
     size_t C = (size_t)h->n_chains;
     P.slot_theta = C * h->dim; P.slot_scalar = C;
     P.slot_invg = C * h->dim * h->dim; P.slot_t = C * h->p3p;
+    P.matrix_free = h->matrix_free ? 1 : 0; P.p2k = h->p2k; P.slot_cw = (size_t)h->c_pad * h->n_rows_pad;
 }
 
 int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
@@ -432,11 +485,21 @@ int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
         rc |= dev_alloc(h, &S.lfac, 2 * c * D * D, tr);
         rc |= dev_alloc(h, &S.invg, 2 * c * D * D, tr);
         rc |= dev_alloc(h, &S.logdet, 2 * c, tr);
-        rc |= dev_alloc(h, &S.tpack, 2 * c * h->p3p, tr);
         rc |= dev_alloc(h, &S.trace, 2 * c * D, tr);
         rc |= dev_alloc(h, &S.u0, c * D, tr);
-        rc |= dev_alloc(h, &S.cbuf, (size_t)h->c_pad * h->n_rows_pad, tr);
-        if (h->comm) rc |= dev_alloc(h, &h->t_tmp, c * h->p3p, tr);
+        if (h->matrix_free) {
+            rc |= dev_alloc(h, &S.cw, 2 * (size_t)h->c_pad * h->n_rows_pad, tr);
+            rc |= dev_alloc(h, &S.hbuf, (size_t)h->c_pad * h->n_rows_pad, tr);
+            rc |= dev_alloc(h, &S.qpack, (size_t)h->c_pad * h->p2k, tr);
+            rc |= dev_alloc(h, &S.uvec, c * D, tr);
+            rc |= dev_alloc(h, &S.quad_tmp, 2 * c * D, tr);          // quad_tmp | trace_tmp: one exchange when row-sharded
+            S.trace_tmp = S.quad_tmp ? S.quad_tmp + c * D : nullptr;
+            rc |= dev_alloc(h, &S.aslot, c, tr);
+        } else {
+            rc |= dev_alloc(h, &S.tpack, 2 * c * h->p3p, tr);
+            rc |= dev_alloc(h, &S.cbuf, (size_t)h->c_pad * h->n_rows_pad, tr);
+            if (h->comm) rc |= dev_alloc(h, &h->t_tmp, c * h->p3p, tr);
+        }
     }
     // build outputs are contiguous (g_tmp | grad_tmp | loglik_tmp) so that the row-sharded mode reduces them in one call
     {
@@ -506,6 +569,30 @@ int launch_turn(rmhmc_handle* h, int do_back, int do_front, int init) {
             case 1: k_chain_turn<11, false><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init); break;
             default: k_chain_turn<17, false><<<C, kTurnThreads, smem, h->stream>>>(h->P, h->S, do_back, do_front, init);
         }
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
+// matrix-free mode: per-chain halves of a round and one iterate of the implicit momentum half-step
+int launch_mf_turn(rmhmc_handle* h, int do_back, int do_front, int init) {
+    const unsigned C = (unsigned)h->n_chains;
+    {
+        Bracket b(h, 3);
+        if (is_big(h)) k_mf_turn<128><<<C, 128, 0, h->stream>>>(h->P, h->S, do_back, do_front, init);
+        else k_mf_turn<32><<<C, 32, 0, h->stream>>>(h->P, h->S, do_back, do_front, init);
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+int launch_mf_mom_iter(rmhmc_handle* h, int is_last) {
+    const unsigned C = (unsigned)h->n_chains;
+    {
+        Bracket b(h, 3);
+        if (is_big(h)) k_mf_mom_iter<128><<<C, 128, 0, h->stream>>>(h->P, h->S, is_last);
+        else k_mf_mom_iter<32><<<C, 32, 0, h->stream>>>(h->P, h->S, is_last);
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -598,6 +685,32 @@ int build_partials(rmhmc_handle* h, int flip) {
     return RMHMC_OK;
 }
 
+// ---- matrix-free partials (mf_kernels.cuh)
+// F iterates of the implicit momentum half-step (rmhmc.py:102-110): quadratic forms by a pass over the data,
+// then the per-chain update and u = G^-1 PM for the next pass
+int mf_momentum_fixed_point(rmhmc_handle* h) {
+    ChainArrays& S = h->S;
+    const size_t cd = (size_t)h->n_chains * h->dim;
+    for (int fi = 0; fi < h->P.n_fixed; ++fi) {
+        int rc = launch_metric<3>(h, pass_args(h, S.quad_tmp));
+        if (!rc) rc = allreduce_sum(h, S.quad_tmp, cd);
+        if (!rc) rc = launch_mf_mom_iter(h, fi + 1 == h->P.n_fixed ? 1 : 0);
+        if (rc) return rc;
+    }
+    return RMHMC_OK;
+}
+// after the factorisation of the new metric: leverages, tr(G^-1 dG_d) and -- unless init -- the quadratic forms of
+// the explicit momentum half-step (rmhmc.py:142-161)
+int mf_closing_passes(rmhmc_handle* h, int init) {
+    ChainArrays& S = h->S;
+    const size_t cd = (size_t)h->n_chains * h->dim;
+    int rc = launch_leverage(h);
+    if (!rc) rc = launch_metric<4>(h, pass_args(h, S.trace_tmp));
+    if (!rc && !init) rc = launch_metric<3>(h, pass_args(h, S.quad_tmp));
+    if (!rc) rc = init ? allreduce_sum(h, S.trace_tmp, cd) : allreduce_sum(h, S.quad_tmp, 2 * cd);
+    return rc;
+}
+
 // The builds of one RMHMC round (rmhmc.py:113-156 for every chain): F-1 position iterates, each a
 // metric build + per-chain solve, then the closing metric build, the partials build and the
 // per-chain factorisation of the new metric.  The
@@ -609,7 +722,7 @@ int rmhmc_round_builds(rmhmc_handle* h) {
     // SLOWER on B200 (metric 1.78 -> 2.95 ms per launch vs 0.62 ms for the stand-alone solve kernel at
     // 65536 chains: 12 warps per SM of straight-line code are instruction-fetch bound while the tensor
     // pipe idles), so it is off by default and kept for small chain counts / experiments.
-    const bool fuse = h->fuse_epilogues && !h->comm && h->col_ctas == 1;
+    const bool fuse = h->fuse_epilogues && !h->comm && h->col_ctas == 1 && !h->matrix_free;
     for (int fi = 2; fi <= h->P.n_fixed; ++fi) {
         const int last = fi == h->P.n_fixed ? 1 : 0;
         MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, nullptr, nullptr, nullptr);
@@ -622,11 +735,16 @@ int rmhmc_round_builds(rmhmc_handle* h) {
             if (rc) return rc;
         }
     }
-    MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, S.grad_tmp, S.loglik_tmp, S.cbuf);
+    MetricArgs a = closing_args(h, 1);
     int rc = fuse ? launch_metric<1>(h, a, fuse_args(h, kFuseFactor, 0, 0)) : launch_metric<1>(h, a);
     if (rc) return rc;
     rc = reduce_build<1>(h);
     if (rc) return rc;
+    if (h->matrix_free) {
+        rc = launch_factor(h, 0);
+        if (!rc) rc = mf_closing_passes(h, 0);
+        return rc;
+    }
     rc = build_partials(h, 1);
     if (rc || fuse) return rc;
     return launch_factor(h, 0);
@@ -635,10 +753,12 @@ int rmhmc_round_builds(rmhmc_handle* h) {
 // n_rounds rounds: front | builds | back+front | builds | ... | back
 int rmhmc_rounds(rmhmc_handle* h, int64_t n_rounds) {
     if (n_rounds <= 0) return RMHMC_OK;
-    int rc = launch_turn(h, 0, 1, 0);
+    const bool mf = h->matrix_free;
+    int rc = mf ? launch_mf_turn(h, 0, 1, 0) : launch_turn(h, 0, 1, 0);
     for (int64_t r = 0; r < n_rounds && !rc; ++r) {
-        rc = rmhmc_round_builds(h);
-        if (!rc) rc = launch_turn(h, 1, r + 1 < n_rounds ? 1 : 0, 0);
+        if (mf) rc = mf_momentum_fixed_point(h);
+        if (!rc) rc = rmhmc_round_builds(h);
+        if (!rc) rc = mf ? launch_mf_turn(h, 1, r + 1 < n_rounds ? 1 : 0, 0) : launch_turn(h, 1, r + 1 < n_rounds ? 1 : 0, 0);
     }
     return rc;
 }
@@ -698,7 +818,7 @@ int run_until(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done, bool hmc) 
 // ====================================================================== extern "C"
 extern "C" {
 
-const char* rmhmc_version(void) { return "rmhmc_b200 0.1 (sm_100a, fp64 dmma)"; }
+const char* rmhmc_version(void) { return "rmhmc_b200 0.2 (sm_100a, fp64 dmma)"; }
 
 const char* rmhmc_last_error(const rmhmc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -736,6 +856,7 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
     h->n_rows_pad = pad_up((int)n_rows, 32);
     h->p2 = num_pairs(dim); h->p2p = pad_up(h->p2, 8);
     h->p3 = num_triples(dim); h->p3p = pad_up(h->p3, 8);
+    h->p2k = pad_up(h->p2, kTbRows);
     {
         // packed-column tiles per G-warp; a single left-over tile is split over chain tiles instead
         int tiles = h->p2p / 8;
@@ -807,6 +928,21 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
             CREATE_TRY(cudaGetLastError());
         }
     }
+    {
+        // matrix-free partials need KR2(X)^T resident (2.7 MB German-shaped, 4 GB for N = 1e5, D = 100); without it
+        // the engine falls back to the materialised tensor build
+        const size_t kKr2Budget = (size_t)48 << 30;
+        size_t bytes = (size_t)h->p2k * h->n_rows_pad * 8;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes <= kKr2Budget && bytes < free_b / 2) {
+            CREATE_TRY(cudaMalloc((void**)&h->kr2t, bytes));
+            long long n = (long long)h->n_rows_pad * h->p2k;
+            k_form_kr2t<<<blocks_for(n, 256), 256>>>(h->x_pad, h->pair_tab, h->kr2t, h->n_rows_pad, h->xs, h->p2, h->p2k);
+            CREATE_TRY(cudaGetLastError());
+            h->matrix_free = true;
+        }
+    }
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
     h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
@@ -821,7 +957,7 @@ void rmhmc_destroy(rmhmc_handle* h) {
     drain_profile(h);
     free_chains(h);
     if (h->comm) nccl_api().CommDestroy(h->comm);
-    cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
+    cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->kr2t); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
     cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
     delete h;
 }
@@ -837,8 +973,26 @@ int rmhmc_update_data(rmhmc_handle* h, const double* xx_dev, const double* t_dev
         k_form_kr3<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->x_pad, h->tri_tab, h->kr3, h->n_rows_pad, h->xs, h->p3p);
         h->launches += 1;
     }
+    if (h->kr2t) {
+        long long n = (long long)h->n_rows_pad * h->p2k;
+        k_form_kr2t<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->x_pad, h->pair_tab, h->kr2t, h->n_rows_pad, h->xs, h->p2, h->p2k);
+        h->launches += 1;
+    }
     CUDA_TRY(h, cudaGetLastError());
     return RMHMC_OK;
+}
+
+int rmhmc_set_partials_mode(rmhmc_handle* h, int mode) {
+    if (!h || (mode != RMHMC_PARTIALS_TENSOR && mode != RMHMC_PARTIALS_MATRIX_FREE))
+        return h ? fail(h, RMHMC_E_INVALID, "rmhmc_set_partials_mode: bad arguments") : RMHMC_E_INVALID;
+    if (mode == RMHMC_PARTIALS_MATRIX_FREE && !h->kr2t)
+        return fail(h, RMHMC_E_UNSUPPORTED, "rmhmc_set_partials_mode: KR2(X)^T does not fit on this device");
+    if (h->n_chains > 0) free_chains(h);
+    h->matrix_free = mode == RMHMC_PARTIALS_MATRIX_FREE;
+    return RMHMC_OK;
+}
+int rmhmc_get_partials_mode(const rmhmc_handle* h) {
+    return h ? (h->matrix_free ? RMHMC_PARTIALS_MATRIX_FREE : RMHMC_PARTIALS_TENSOR) : RMHMC_E_INVALID;
 }
 
 int rmhmc_comm_unique_id(char* out128) {
@@ -976,16 +1130,19 @@ static int chains_init_common(rmhmc_handle* h, int64_t C, const double* theta0, 
     } else {
         rc = set_chain_smem_attrs(h);
         if (rc) return rc;
-        MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, S.grad_tmp, S.loglik_tmp, S.cbuf);
-        rc = launch_metric<1>(h, a);
+        rc = launch_metric<1>(h, closing_args(h, 0));
         if (rc) return rc;
         rc = reduce_build<1>(h);
         if (rc) return rc;
-        rc = build_partials(h, 0);
-        if (rc) return rc;
-        rc = launch_factor(h, 1);
-        if (rc) return rc;
-        rc = launch_turn(h, 1, 0, 1);
+        if (h->matrix_free) {
+            rc = launch_factor(h, 1);
+            if (!rc) rc = mf_closing_passes(h, 1);
+            if (!rc) rc = launch_mf_turn(h, 1, 0, 1);
+        } else {
+            rc = build_partials(h, 0);
+            if (!rc) rc = launch_factor(h, 1);
+            if (!rc) rc = launch_turn(h, 1, 0, 1);
+        }
         if (rc) return rc;
     }
     h->launches += 1;
@@ -1145,7 +1302,7 @@ int rmhmc_profile_enable(rmhmc_handle* h, int enable) {
     return RMHMC_OK;
 }
 int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches) {
-    if (!h || kind < 0 || kind > 4) return RMHMC_E_INVALID;
+    if (!h || kind < 0 || kind > 7) return RMHMC_E_INVALID;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     drain_profile(h);
     if (ms) *ms = h->prof[kind].ms;

@@ -51,6 +51,10 @@ struct EngineParams {
     const unsigned char* pair_a;       // [P2]
     const unsigned char* pair_b;       // [P2]
     size_t slot_theta, slot_scalar, slot_invg, slot_t;   // doubles between slot 0 and slot 1
+    // matrix-free partials
+    int matrix_free;                   // 1: no packed T; traces / quadratic forms by passes over the data
+    int p2k;                           // P2 padded to the K tile of the leverage GEMM (32)
+    size_t slot_cw;                    // doubles between the two c_n slots
 };
 
 __host__ inline size_t factor_smem_bytes(int dim) { return (size_t)2 * dim * (dim | 1) * 8; }
@@ -436,6 +440,21 @@ __global__ void __launch_bounds__(32) k_chain_factor(EngineParams P, ChainArrays
 #pragma unroll
     for (int b = 0; b < DMAX; ++b)
         if (b < D && lane < D) igd[lane * D + b] = ig[b];
+    if (P.matrix_free) {
+        // q = packed G^-1 with doubled off-diagonals (A operand of the leverage GEMM h = KR2(X) q); lane = column b
+        // of the symmetric inverse, so that for a fixed row a consecutive lanes write consecutive packed entries
+        double* qp = S.qpack + (size_t)c * P.p2k;
+#pragma unroll
+        for (int a = 0; a < DMAX; ++a)
+            if (a < D && lane >= a && lane < D) qp[a * D - a * (a - 1) / 2 + (lane - a)] = lane == a ? ig[a] : 2.0 * ig[a];
+        if (lane == 0) S.aslot[c] = out;
+        if (!init) {
+            // u = G_new^-1 p for the quadratic form of the explicit momentum half-step (rmhmc.py:158-161)
+            const double pm = lane < D ? S.mom[(size_t)c * D + lane] : 0.0;
+            const double u = matvec_regs<DMAX>(ig, D, pm);
+            if (lane < D) S.uvec[(size_t)c * D + lane] = u;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- the per-round chain kernel
@@ -791,6 +810,22 @@ __global__ void __launch_bounds__(kBigThreads) k_chain_factor_big(EngineParams P
     chol_inverse_cta(A, B, D, DS);
     double* igd = S.invg + out * P.slot_invg + (size_t)c * D * D;
     for (int idx = tid; idx < D * D; idx += kBigThreads) igd[idx] = B[(idx / D) * DS + (idx % D)];
+    if (P.matrix_free) {
+        double* qp = S.qpack + (size_t)c * P.p2k;
+        for (int p = tid; p < P.p2; p += kBigThreads) {
+            int pa = P.pair_a[p], pb = P.pair_b[p];
+            qp[p] = (pa == pb ? 1.0 : 2.0) * B[pa * DS + pb];
+        }
+        if (tid == 0) S.aslot[c] = out;
+        if (!init && tid < D) {
+            const double* mom = S.mom + (size_t)c * D;
+            double y0 = 0.0, y1 = 0.0;
+            int b = 0;
+            for (; b + 1 < D; b += 2) { y0 = fma(B[b * DS + tid], mom[b], y0); y1 = fma(B[(b + 1) * DS + tid], mom[b + 1], y1); }
+            if (b < D) y0 = fma(B[b * DS + tid], mom[b], y0);
+            S.uvec[(size_t)c * D + tid] = y0 + y1;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kBigThreads) k_chain_solve_big(EngineParams P, ChainArrays S, int is_last) {

@@ -130,7 +130,15 @@ struct ChainArrays {
     double* g_tmp;     // [C][P2p] metric at theta_w (output of a metric build)
     double* grad_tmp;  // [C][D]   X^T (t - p) at theta_w (closing build only)
     double* loglik_tmp;// [C]      log-likelihood at theta_w (closing build only)
-    double* cbuf;      // [C][Np]  c_n = v_n (1 - 2 p_n) at theta_w (closing build only)
+    double* cbuf;      // [C][Np]  c_n = v_n (1 - 2 p_n) at theta_w (closing build only; materialised-partials mode)
+    // matrix-free partials (mf_kernels.cuh): tr(G^-1 dG_d) and u^T dG_d u straight from the data
+    double* cw;        // [2][Cpad][Np]  c_n of each slot's position (replaces the packed tensor T)
+    double* hbuf;      // [Cpad][Np]     leverages h_n = x_n^T G^-1 x_n of the newest metric
+    double* qpack;     // [Cpad][P2k]    packed G^-1, off-diagonal pairs doubled (A operand of the leverage GEMM)
+    double* uvec;      // [C][D]         G^-1 PM: input of the next quadratic-form pass
+    double* quad_tmp;  // [C][D]         sum_n c_n (x_n.u)^2 x_nd = u^T dG_d u
+    double* trace_tmp; // [C][D]         sum_n c_n h_n x_nd = tr(G^-1 dG_d)   (directly after quad_tmp)
+    int* aslot;        // [C]  slot whose c_n the next pass over the data reads
     int* cur;          // [C]  which slot holds the current state
     int* step;         // [C]  leapfrog steps done in the running trajectory
     int* nsteps;       // [C]  RandomStep of the running trajectory

@@ -33,7 +33,13 @@ struct MetricArgs {
     double* g_out;            // [C][P2p]  packed metric
     double* grad_out;         // [C][D]    (closing) X^T (t - p)
     double* loglik_out;       // [C]       (closing)
-    double* cbuf;             // [C][Np]   (closing)
+    double* cbuf;             // [C][Np]   (closing: written; MODE 3/4: read) c_n = v_n (1 - 2 p_n)
+    // c_n slot selection: closing writes slot cw_cur[c] ^ cw_flip, the data passes read slot aslot[c]
+    const int* cw_cur;        // [C] or null (single buffer)
+    int cw_flip;
+    size_t cw_slot;           // doubles between the two c_n slots
+    const int* aslot;         // [C] or null
+    const double* hbuf;       // [Cpad][Np] leverages (MODE 4)
     int n_chains, n_rows, n_rows_pad, dim, xs, p2, p2p;
     int extra_tile;           // n-tile split over the chain tiles of G-warps 0..3, or -1
     int tiles_per_cta;        // packed-column tiles owned by one CTA (blockIdx.y selects the range)
@@ -144,6 +150,11 @@ __device__ __forceinline__ double fast_log1p_01(double e, const double* __restri
 
 // MODE 0: G only (position fixed-point iterates); 1: closing build (G, gradient, log-likelihood,
 // cbuf); 2: gradient and log-likelihood only (Euclidean HMC, hmc.py:52-53,60-61,65-66).
+// Matrix-free partials (the D matrices dG/dw_d = X^T diag(c x_d) X are never formed):
+// MODE 3: quadratic forms  out[c][d] = sum_n c_n (x_n . u_c)^2 x_nd = u^T dG_d u with u = a.theta
+//         (LastTerm of rmhmc.py:105-107 / :159-161 without the 0.5)
+// MODE 4: traces           out[c][d] = sum_n c_n h_n x_nd = tr(G^-1 dG_d), h = a.hbuf  (rmhmc.py:76-77,155-156)
+// Both reuse the gradient contraction R . X of the closing build with a different R.
 //
 // Warp-specialised: 4 F-warps (one 8-row tile each, all 32 chains) compute f^T = Theta X^T on the
 // tensor cores, the logistic terms, and publish V (and R) for row block rb+1 while the 8 G-warps
@@ -154,7 +165,8 @@ __device__ __forceinline__ double fast_log1p_01(double e, const double* __restri
 // so that all four SM sub-partitions issue the same number of DMMAs.
 template <int NT, int MODE>
 __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, FuseArgs fz) {
-    constexpr bool CLOSING = MODE >= 1, WITH_G = MODE <= 1, WITH_C = MODE == 1;
+    constexpr bool CLOSING = MODE == 1 || MODE == 2, WITH_G = MODE <= 1, WITH_C = MODE == 1;
+    constexpr bool APPLY = MODE >= 3, WITH_R = MODE >= 1, WITH_F = MODE != 4;
     constexpr int MC = kMetricChains, NB = kMetricRows, VS = kMetricVS, ST = kMetricStages;
     constexpr int GW = kMetricGWarps, FW = kMetricFWarps;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -202,11 +214,31 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
                 tma_bulk_g2s(xs_ring + (size_t)s * NB * xs, a.x + (size_t)s * NB * xs, stage_bytes, &x_full[s]);
             }
         }
-        const int k_steps_f = (a.dim + 3) / 4;
+        const int k_steps_f = WITH_F ? (a.dim + 3) / 4 : 0;
         double ll_acc[4] = {0.0, 0.0, 0.0, 0.0};
         const int tcol = xs - 1;
+        // MODE 3/4: this lane's c_n (and h_n) rows: chain m*8+g, columns rb*NB + fw*8 + 2q, +1
+        const double* cw_row[4];
+        const double* h_row[4];
+        if (APPLY) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int c = chain0 + m * 8 + g;
+                const size_t slot = (a.aslot && c < a.n_chains) ? (size_t)a.aslot[c] * a.cw_slot : 0;
+                cw_row[m] = a.cbuf + slot + (size_t)c * a.n_rows_pad + fw * 8 + 2 * q;
+                h_row[m] = MODE == 4 ? a.hbuf + (size_t)c * a.n_rows_pad + fw * 8 + 2 * q : nullptr;
+            }
+        }
         for (int rb = 0; rb < n_blocks; ++rb) {
             const int stage = rb % ST, buf = rb & 1;
+            double2 cwv[4], hv[4];
+            if (APPLY) {              // issued before the barrier waits: independent of the staged X block
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    cwv[m] = *reinterpret_cast<const double2*>(cw_row[m] + rb * NB);
+                    if (MODE == 4) hv[m] = *reinterpret_cast<const double2*>(h_row[m] + rb * NB);
+                }
+            }
             // refill the stage freed two blocks ago (the G-warps have released it: see v_empty below)
             if (rb >= 2) mbar_wait(&v_empty[buf], (uint32_t)(((rb - 2) >> 1) & 1));
             if (fw == 0 && lane == 0 && rb >= 2 && rb + ST - 2 < n_blocks) {
@@ -235,6 +267,15 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
             }
             double* vdst = v_buf + (size_t)buf * MC * VS;
             double* rdst = r_buf + (size_t)buf * MC * VS;
+            if (APPLY) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    double2 rr;
+                    if (MODE == 3) rr = make_double2(cwv[m].x * f[m][0] * f[m][0], cwv[m].y * f[m][1] * f[m][1]);
+                    else rr = make_double2(cwv[m].x * hv[m].x, cwv[m].y * hv[m].y);
+                    *reinterpret_cast<double2*>(rdst + (size_t)(m * 8 + g) * VS + r_local) = rr;
+                }
+            } else {
             // the 8 (chain, row) pairs of this lane, evaluated in lock-step for instruction-level parallelism
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -271,13 +312,16 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
                 }
                 const int m_local = m * 8 + g;
                 if (WITH_G) *reinterpret_cast<double2*>(vdst + (size_t)m_local * VS + r_local) = make_double2(vv[0], vv[1]);
-                if (CLOSING) *reinterpret_cast<double2*>(rdst + (size_t)m_local * VS + r_local) = make_double2(rr[0], rr[1]);
+                if (WITH_R) *reinterpret_cast<double2*>(rdst + (size_t)m_local * VS + r_local) = make_double2(rr[0], rr[1]);
                 if (WITH_C && blockIdx.y == 0) {
                     int c = chain0 + m_local;
-                    if (c < a.n_chains)
-                        *reinterpret_cast<double2*>(a.cbuf + (size_t)c * a.n_rows_pad + rb * NB + r_local) =
+                    if (c < a.n_chains) {
+                        const size_t slot = a.cw_cur ? (size_t)(a.cw_cur[c] ^ a.cw_flip) * a.cw_slot : 0;
+                        *reinterpret_cast<double2*>(a.cbuf + slot + (size_t)c * a.n_rows_pad + rb * NB + r_local) =
                             make_double2(cc[0], cc[1]);
+                    }
                 }
+            }
             }
             }
             __syncwarp();
@@ -352,7 +396,7 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
                         dmma884(eacc[0], eacc[1], asel, b);
                     }
                 }
-                if (CLOSING) {
+                if (WITH_R) {
 #pragma unroll
                     for (int h = 0; h < GT; ++h) {
                         int tix = gw + h * GW;
@@ -396,7 +440,7 @@ __global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, Fuse
             }
             if (has_extra) store_tile(a.extra_tile, gw, eacc[0], eacc[1]);
         }
-        if (CLOSING) {
+        if (WITH_R) {
 #pragma unroll
             for (int h = 0; h < GT; ++h) {
                 int tix = gw + h * GW;

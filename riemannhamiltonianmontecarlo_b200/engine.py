@@ -39,7 +39,9 @@ class LogisticData:
     (``torch.distributed`` must be initialised: it carries the NCCL unique id to the other ranks).
     """
 
-    def __init__(self, xx, t, alpha: float = 100.0, device: str | int = "cuda:0", row_shard=None):
+    PARTIALS = {"tensor": 0, "matrix_free": 1}
+
+    def __init__(self, xx, t, alpha: float = 100.0, device: str | int = "cuda:0", row_shard=None, partials=None):
         torch = _capi.require_cuda()
         self._lib = _capi.load()
         self.torch = torch
@@ -63,6 +65,19 @@ class LogisticData:
             self._init_comm(*row_shard)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _capi.check(self._lib.rmhmc_set_stream(self.handle, c_void_p(stream)), self.handle, "rmhmc_set_stream")
+        if partials is not None:
+            self.set_partials_mode(partials)
+
+    def set_partials_mode(self, mode: str):
+        """``"tensor"``: build the packed partials tensor per chain (the reference's formulation);
+        ``"matrix_free"`` (default when it fits): traces and quadratic forms as passes over the data.
+        Drops the handle's chains: call before creating a sampler."""
+        _capi.check(self._lib.rmhmc_set_partials_mode(self.handle, self.PARTIALS[mode]), self.handle,
+                    "rmhmc_set_partials_mode")
+
+    @property
+    def partials_mode(self) -> str:
+        return "matrix_free" if self._lib.rmhmc_get_partials_mode(self.handle) == 1 else "tensor"
 
     def _init_comm(self, rank: int, world: int):
         import torch.distributed as dist
@@ -254,7 +269,8 @@ class RMHMCSampler(_SamplerBase):
 
     def profile_read(self):
         """{kind: (milliseconds, launches)} per kernel class."""
-        names = ["metric_fp", "metric_closing", "partials", "chain_turn", "chain_solve"]
+        names = ["metric_fp", "metric_closing", "partials", "chain_turn", "chain_solve", "quad_pass", "leverage_gemm",
+                 "trace_pass"]
         out = {}
         for k, nm in enumerate(names):
             ms, n = ctypes.c_double(0), c_int64(0)

@@ -78,11 +78,16 @@ def test_chol_seam_matches_numpy(pkg):
     data.close()
 
 
-def _run_tape_fixture(pkg, fx, n_chains=None):
+PARTIALS = ["matrix_free", "tensor"]      # both evaluations of the metric partials (include/rmhmc_b200.h)
+
+
+def _run_tape_fixture(pkg, fx, n_chains=None, partials=None):
     xx, t = fx["xx"], fx["t"]
     n_iter, burn_in = int(fx["n_iter"]), int(fx["burn_in"])
     c = fx["z"].shape[1] if n_chains is None else n_chains
-    data = pkg.LogisticData(xx, t)
+    data = pkg.LogisticData(xx, t, partials=partials)
+    if partials is not None:
+        assert data.partials_mode == partials
     s = pkg.RMHMCSampler(data, c, int(fx["n_leapfrog"]), float(fx["step_size"]), int(fx["n_fixed"]))
     s.set_tape(fx["z"][:, :c], fx["u_step"][:, :c], fx["z_dir"][:, :c], fx["u_acc"][:, :c])
     s.set_samples(n_iter - burn_in, burn_in)
@@ -95,12 +100,13 @@ def _run_tape_fixture(pkg, fx, n_chains=None):
     return tr, samples, st
 
 
+@pytest.mark.parametrize("partials", PARTIALS)
 @pytest.mark.parametrize("name", ["rmhmc_australian_shaped", "rmhmc_german_shaped", "rmhmc_german_real",
                                   "rmhmc_pima_real"])
-def test_rmhmc_trajectories_match_reference(pkg, golden, name):
+def test_rmhmc_trajectories_match_reference(pkg, golden, name, partials):
     """Same data, same host draws: per-step theta, end momentum, H and the accept decisions."""
     fx = golden(name)
-    tr, samples, st = _run_tape_fixture(pkg, fx)
+    tr, samples, st = _run_tape_fixture(pkg, fx, partials=partials)
     c, n_iter = fx["n_steps"].shape
     # decisions and integer draws: bit-exact
     assert np.array_equal(tr["n_steps"], fx["n_steps"])
@@ -139,11 +145,12 @@ def test_rmhmc_matches_live_oracle_on_fresh_tape(pkg):
     assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
 
 
-def test_chains_are_independent_of_batch_composition(pkg, golden):
+@pytest.mark.parametrize("partials", PARTIALS)
+def test_chains_are_independent_of_batch_composition(pkg, golden, partials):
     """A chain's result does not depend on which other chains share its tile (bit-exact)."""
     fx = golden("rmhmc_australian_shaped")
-    tr_all, s_all, _ = _run_tape_fixture(pkg, fx)
-    tr_two, s_two, _ = _run_tape_fixture(pkg, fx, n_chains=2)
+    tr_all, s_all, _ = _run_tape_fixture(pkg, fx, partials=partials)
+    tr_two, s_two, _ = _run_tape_fixture(pkg, fx, n_chains=2, partials=partials)
     assert np.array_equal(s_all[:2], s_two)
     assert np.array_equal(tr_all["h_proposed"][:2], tr_two["h_proposed"])
 
@@ -268,13 +275,14 @@ def test_large_dim_seams_match_oracle(pkg, dim, n_rows):
     data.close()
 
 
+@pytest.mark.parametrize("partials", PARTIALS)
 @pytest.mark.parametrize("dim,n_rows", [(40, 500), (64, 700)])
-def test_large_dim_rmhmc_matches_oracle(pkg, dim, n_rows):
+def test_large_dim_rmhmc_matches_oracle(pkg, dim, n_rows, partials):
     xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 4100 + dim)
     n_iter, burn, c = 5, 1, 3
     tapes = [bo.make_tape(n_iter, dim, 9100 + i) for i in range(c)]
     ref, infos = bo.rmhmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=4, step_size=0.3, n_fixed=4)
-    out, _, info = pkg.rmhmc_batched(xx, t, c, n_iter, burn, 4, 0.3, 4, draws=bo.stack_tapes(tapes))
+    out, _, info = pkg.rmhmc_batched(xx, t, c, n_iter, burn, 4, 0.3, 4, draws=bo.stack_tapes(tapes), partials=partials)
     assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
     assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
 
