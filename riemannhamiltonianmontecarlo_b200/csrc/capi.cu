@@ -545,15 +545,12 @@ int set_chain_smem_attrs(rmhmc_handle* h) {
         return RMHMC_OK;
     }
     int turn = (int)turn_smem_bytes(h->dim, h->p2, h->p3p, false), seam = (int)seam_smem_bytes(h->dim, h->p3p, true);
-    int fac = (int)factor_smem_bytes(h->dim);
     CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
     CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
     CUDA_TRY(h, cudaFuncSetAttribute(k_chain_turn<17, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, turn));
     CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
     CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<32, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
     CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<32, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_factor<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fac));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_factor<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, fac));
     return RMHMC_OK;
 }
 
@@ -604,8 +601,12 @@ int launch_factor(rmhmc_handle* h, int init) {
     {
         Bracket b(h, 4);
         if (is_big(h)) k_chain_factor_big<<<C, kBigThreads, big_mat_smem_bytes(h->dim, 2), h->stream>>>(h->P, h->S, init);
-        else if (dmax_variant(h) == 0) k_chain_factor<16><<<C, 32, factor_smem_bytes(h->dim), h->stream>>>(h->P, h->S, init);
-        else k_chain_factor<32><<<C, 32, factor_smem_bytes(h->dim), h->stream>>>(h->P, h->S, init);
+        else switch (chain_order(h->dim)) {
+            case 8: k_chain_factor<8><<<C, 32, factor_smem_bytes(8), h->stream>>>(h->P, h->S, init); break;
+            case 16: k_chain_factor<16><<<C, 32, factor_smem_bytes(16), h->stream>>>(h->P, h->S, init); break;
+            case 25: k_chain_factor<25><<<C, 32, factor_smem_bytes(25), h->stream>>>(h->P, h->S, init); break;
+            default: k_chain_factor<32><<<C, 32, factor_smem_bytes(32), h->stream>>>(h->P, h->S, init);
+        }
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -614,12 +615,15 @@ int launch_factor(rmhmc_handle* h, int init) {
 
 int launch_solve(rmhmc_handle* h, int is_last) {
     const unsigned C = (unsigned)h->n_chains;
-    size_t smem = (size_t)h->dim * (h->dim | 1) * 8;
     {
         Bracket b(h, 4);
         if (is_big(h)) k_chain_solve_big<<<C, kBigThreads, big_mat_smem_bytes(h->dim, 1), h->stream>>>(h->P, h->S, is_last);
-        else if (dmax_variant(h) == 0) k_chain_solve<16><<<C, 32, smem, h->stream>>>(h->P, h->S, is_last);
-        else k_chain_solve<32><<<C, 32, smem, h->stream>>>(h->P, h->S, is_last);
+        else switch (chain_order(h->dim)) {
+            case 8: k_chain_solve<8><<<C, 32, solve_smem_bytes(8), h->stream>>>(h->P, h->S, is_last); break;
+            case 16: k_chain_solve<16><<<C, 32, solve_smem_bytes(16), h->stream>>>(h->P, h->S, is_last); break;
+            case 25: k_chain_solve<25><<<C, 32, solve_smem_bytes(25), h->stream>>>(h->P, h->S, is_last); break;
+            default: k_chain_solve<32><<<C, 32, solve_smem_bytes(32), h->stream>>>(h->P, h->S, is_last);
+        }
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -992,7 +996,8 @@ int rmhmc_set_partials_mode(rmhmc_handle* h, int mode) {
     return RMHMC_OK;
 }
 int rmhmc_get_partials_mode(const rmhmc_handle* h) {
-    return h ? (h->matrix_free ? RMHMC_PARTIALS_MATRIX_FREE : RMHMC_PARTIALS_TENSOR) : RMHMC_E_INVALID;
+    if (!h) return RMHMC_E_INVALID;
+    return h->matrix_free ? (int)RMHMC_PARTIALS_MATRIX_FREE : (int)RMHMC_PARTIALS_TENSOR;
 }
 
 int rmhmc_comm_unique_id(char* out128) {

@@ -57,7 +57,8 @@ struct EngineParams {
     size_t slot_cw;                    // doubles between the two c_n slots
 };
 
-__host__ inline size_t factor_smem_bytes(int dim) { return (size_t)2 * dim * (dim | 1) * 8; }
+__host__ inline size_t factor_smem_bytes(int order) { return ((size_t)2 * order * (order | 1) + 64) * 8; }
+__host__ inline size_t solve_smem_bytes(int order) { return ((size_t)order * (order | 1) + 64) * 8; }
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- Philox4x32-10
@@ -322,6 +323,106 @@ __device__ __forceinline__ void chol_inverse_packed(const double* Lp, double* Mp
     __syncwarp();
 }
 
+
+// ---------------------------------------------------------------- fixed-order variants (engine kernels)
+// The per-chain kernels are instruction-issue bound (ncu: 5.4 k warp instructions per 25 x 25 solve, more than
+// half of them loop guards and lane predicates).  These variants take the order N at compile time
+// (N >= D; lanes / columns >= D carry the identity, i.e. the matrix factored is blockdiag(G, I), whose
+// factor, inverse and log-det restricted to the leading D x D block are those of G) and update the unused
+// strict upper triangle along with the rest instead of predicating it away -- it never feeds a used entry.
+template <int N>
+__device__ __forceinline__ void load_packed_rows_pad(const double* __restrict__ gp, double (&row)[N], int D, int lane) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+        row[j] = (j < D && lane >= j && lane < D) ? gp[j * D - j * (j - 1) / 2 + (lane - j)] : (j == lane ? 1.0 : 0.0);
+}
+
+// colbuf: 2 x 32 doubles of shared memory (column k is broadcast through buffer k & 1: one __syncwarp per column)
+template <int N>
+__device__ __forceinline__ double chol_fixed(double (&row)[N], double* colbuf, int lane, double& dinv) {
+    double diag = 1.0, dinv_acc = 1.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double akk = __shfl_sync(kFull, row[k], k);
+        const double inv = fast_rsqrt(akk);
+        const double lkk = akk * inv;
+        const double lik = (lane == k) ? lkk : row[k] * inv;
+        if (lane == k) { diag = lkk; dinv_acc = inv; }
+        row[k] = lik;
+        double* cb = colbuf + (k & 1) * 32;
+        cb[lane] = lik;
+        __syncwarp();
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) row[j] = fma(-lik, cb[j], row[j]);
+    }
+    dinv = dinv_acc;
+    return warp_sum(lane < N ? log(diag) : 0.0);
+}
+
+template <int N>
+__device__ __forceinline__ void store_rows_fixed(double* Lsm, const double (&row)[N], int lane) {
+    constexpr int NS = N | 1;
+    if (lane < N) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) Lsm[lane * NS + j] = (j <= lane) ? row[j] : 0.0;
+    }
+    __syncwarp();
+}
+
+// Solve L L^T x = b; lane i holds b_i on entry and x_i on exit (rmhmc.py:113,121)
+template <int N>
+__device__ __forceinline__ double chol_solve_fixed(const double (&row)[N], const double* Lsm, double dinv, int lane, double b) {
+    constexpr int NS = N | 1;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {                       // forward: L y = b
+        const double yk = __shfl_sync(kFull, b * dinv, k);
+        b = lane == k ? yk : (lane > k ? fma(-row[k], yk, b) : b);
+    }
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {                  // backward: L^T x = y
+        const double xk = __shfl_sync(kFull, b * dinv, k);
+        const double lkj = Lsm[k * NS + (lane < N ? lane : 0)];
+        b = lane == k ? xk : (lane < k ? fma(-lkj, xk, b) : b);
+    }
+    return b;
+}
+
+// ig[b] = (L L^T)^-1 [lane][b]: lane j builds column j of M = L^-1 (mirrored in Msm), then G^-1 = M^T M
+template <int N>
+__device__ __forceinline__ void chol_inverse_fixed(const double* Lsm, double* Msm, double dinv, double (&ig)[N], int lane) {
+    constexpr int NS = N | 1;
+    double m[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            if (k & 1) s1 = fma(Lsm[i * NS + k], m[k], s1);
+            else s0 = fma(Lsm[i * NS + k], m[k], s0);
+        }
+        const double di = __shfl_sync(kFull, dinv, i);
+        m[i] = (i == lane) ? di : (i > lane ? -(s0 + s1) * di : 0.0);
+    }
+    if (lane < N) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) Msm[i * NS + lane] = m[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < N; ++b) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = b; k < N; ++k) {
+            if (k & 1) s1 = fma(m[k], Msm[k * NS + b], s1);
+            else s0 = fma(m[k], Msm[k * NS + b], s0);
+        }
+        ig[b] = s0 + s1;
+    }
+    __syncwarp();
+}
+
+__host__ __device__ inline int chain_order(int dim) { return dim <= 8 ? 8 : (dim <= 16 ? 16 : (dim <= 25 ? 25 : 32)); }
+
 template <int DMAX>
 __device__ __forceinline__ double matvec_regs(const double (&ig)[DMAX], int D, double x) {
     double y0 = 0.0, y1 = 0.0;
@@ -416,42 +517,44 @@ __device__ __forceinline__ double clamp_position(double w, int lane, int dim, in
 // ---------------------------------------------------------------- factor kernel (one warp per chain)
 // Cholesky factor, inverse and log-det of the metric built at theta_w (rmhmc.py:138,171 / :58-60).
 // Writes L, G^-1 and 0.5 log|G| of the proposal slot (of slot `cur` when init != 0).
-template <int DMAX>
+template <int N>
 __global__ void __launch_bounds__(32) k_chain_factor(EngineParams P, ChainArrays S, int init) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int c = blockIdx.x, lane = threadIdx.x, D = P.dim, DS = P.ds;
+    constexpr int NS = N | 1;
+    const int c = blockIdx.x, lane = threadIdx.x, D = P.dim;
     if (c >= P.n_chains) return;
     if (!init && (S.iter[c] >= P.it_stop || S.nsteps[c] <= 0)) return;
-    double* Lsm = reinterpret_cast<double*>(smem_raw);
-    double* Msm = Lsm + D * DS;
+    double* colbuf = reinterpret_cast<double*>(smem_raw);
+    double* Lsm = colbuf + 64;
+    double* Msm = Lsm + N * NS;
     const int out = init ? S.cur[c] : 1 - S.cur[c];
-    double dinv, ig[DMAX];
+    double dinv, ig[N];
     {
-        double lrow[DMAX];
-        load_packed_rows<DMAX>(S.g_tmp + (size_t)c * P.p2p, lrow, D, lane);
-        double logdet = chol_regs_sm<DMAX>(lrow, Msm, D, lane, dinv);      // Msm doubles as the column buffer
-        store_rows<DMAX>(Lsm, lrow, D, DS, lane);
+        double lrow[N];
+        load_packed_rows_pad<N>(S.g_tmp + (size_t)c * P.p2p, lrow, D, lane);
+        double logdet = chol_fixed<N>(lrow, colbuf, lane, dinv);
+        store_rows_fixed<N>(Lsm, lrow, lane);
         if (lane == 0) S.logdet[out * P.slot_scalar + c] = logdet;
     }
     double* ld = S.lfac + out * P.slot_invg + (size_t)c * D * D;
-    for (int idx = lane; idx < D * D; idx += 32) ld[idx] = Lsm[(idx / D) * DS + (idx % D)];
-    chol_inverse_regs<DMAX>(Lsm, Msm, dinv, ig, D, DS, lane);
+    for (int idx = lane; idx < D * D; idx += 32) ld[idx] = Lsm[(idx / D) * NS + (idx % D)];
+    chol_inverse_fixed<N>(Lsm, Msm, dinv, ig, lane);
     double* igd = S.invg + out * P.slot_invg + (size_t)c * D * D;
 #pragma unroll
-    for (int b = 0; b < DMAX; ++b)
+    for (int b = 0; b < N; ++b)
         if (b < D && lane < D) igd[lane * D + b] = ig[b];
     if (P.matrix_free) {
         // q = packed G^-1 with doubled off-diagonals (A operand of the leverage GEMM h = KR2(X) q); lane = column b
         // of the symmetric inverse, so that for a fixed row a consecutive lanes write consecutive packed entries
         double* qp = S.qpack + (size_t)c * P.p2k;
 #pragma unroll
-        for (int a = 0; a < DMAX; ++a)
+        for (int a = 0; a < N; ++a)
             if (a < D && lane >= a && lane < D) qp[a * D - a * (a - 1) / 2 + (lane - a)] = lane == a ? ig[a] : 2.0 * ig[a];
         if (lane == 0) S.aslot[c] = out;
         if (!init) {
             // u = G_new^-1 p for the quadratic form of the explicit momentum half-step (rmhmc.py:158-161)
             const double pm = lane < D ? S.mom[(size_t)c * D + lane] : 0.0;
-            const double u = matvec_regs<DMAX>(ig, D, pm);
+            const double u = matvec_regs<N>(ig, N, pm);
             if (lane < D) S.uvec[(size_t)c * D + lane] = u;
         }
     }
@@ -768,24 +871,25 @@ k_chain_turn(EngineParams P, ChainArrays S, int do_back, int do_front, int init)
 
 // ---------------------------------------------------------------- position fixed-point iterate (x (F-1))
 // solve G(theta_w) u = p, theta_w <- theta + s eps/2 (u0 + u)   (rmhmc.py:116-122)
-template <int DMAX>
+template <int N>
 __global__ void __launch_bounds__(32) k_chain_solve(EngineParams P, ChainArrays S, int is_last) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int c = blockIdx.x, lane = threadIdx.x, D = P.dim, DS = P.ds;
+    const int c = blockIdx.x, lane = threadIdx.x, D = P.dim;
     if (c >= P.n_chains) return;
     if (S.iter[c] >= P.it_stop || S.nsteps[c] <= 0) return;
-    double* Lsm = reinterpret_cast<double*>(smem_raw);
+    double* colbuf = reinterpret_cast<double*>(smem_raw);
+    double* Lsm = colbuf + 64;
     const bool live = lane < D;
     const int cur = S.cur[c];
     const int in_slot = S.step[c] == 0 ? cur : 1 - cur;
-    double lrow[DMAX], dinv;
-    load_packed_rows<DMAX>(S.g_tmp + (size_t)c * P.p2p, lrow, D, lane);
+    double lrow[N], dinv;
+    load_packed_rows_pad<N>(S.g_tmp + (size_t)c * P.p2p, lrow, D, lane);
     double p = live ? S.mom[(size_t)c * D + lane] : 0.0;
     double w = live ? S.theta[in_slot * P.slot_theta + (size_t)c * D + lane] : 0.0;
     double u0 = live ? S.u0[(size_t)c * D + lane] : 0.0;
-    chol_regs_sm<DMAX>(lrow, Lsm, D, lane, dinv);                                  // Lsm doubles as the column buffer
-    store_rows<DMAX>(Lsm, lrow, D, DS, lane);
-    double u = chol_solve_regs<DMAX>(lrow, Lsm, dinv, D, DS, lane, p);             // rmhmc.py:121
+    chol_fixed<N>(lrow, colbuf, lane, dinv);
+    store_rows_fixed<N>(Lsm, lrow, lane);
+    double u = chol_solve_fixed<N>(lrow, Lsm, dinv, lane, p);                        // rmhmc.py:121
     double pw = w + (S.dir[c] * P.step_size / 2) * (u0 + u);                        // rmhmc.py:122
     if (is_last) pw = clamp_position(pw, lane, D, &S.renorm_pos[c]);
     if (live) S.theta_w[(size_t)c * D + lane] = pw;

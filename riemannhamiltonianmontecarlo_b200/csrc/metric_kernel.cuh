@@ -160,11 +160,12 @@ __device__ __forceinline__ double fast_log1p_01(double e, const double* __restri
 // tensor cores, the logistic terms, and publish V (and R) for row block rb+1 while the 8 G-warps
 // accumulate G += V . KR2(X) for row block rb.  Everything is handed over through mbarriers
 // (X ring full/empty, V double buffer full/empty); there is no CTA-wide barrier in the main loop.
+// MODE >= 2 has no G accumulators and little work per row block: two CTAs per SM hide each other's latencies.
 // NT = packed-column tiles (8 columns) per G-warp (tile t belongs to warp t mod GW); when the tile
 // count is 1 mod 4 the last tile is split over the four chain tiles of G-warps 0..3 (a.extra_tile)
 // so that all four SM sub-partitions issue the same number of DMMAs.
 template <int NT, int MODE>
-__global__ void __launch_bounds__(kMetricThreads, 1) k_metric(MetricArgs a, FuseArgs fz) {
+__global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(MetricArgs a, FuseArgs fz) {
     constexpr bool CLOSING = MODE == 1 || MODE == 2, WITH_G = MODE <= 1, WITH_C = MODE == 1;
     constexpr bool APPLY = MODE >= 3, WITH_R = MODE >= 1, WITH_F = MODE != 4;
     constexpr int MC = kMetricChains, NB = kMetricRows, VS = kMetricVS, ST = kMetricStages;
