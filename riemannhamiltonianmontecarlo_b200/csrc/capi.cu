@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,6 +18,7 @@
 #include "hmc_kernels.cuh"
 #include "metric_kernel.cuh"
 #include "mf_kernels.cuh"
+#include "momfp_kernel.cuh"
 #include "tbuild_kernel.cuh"
 
 using namespace rmhmc;
@@ -87,6 +89,7 @@ struct rmhmc_handle {
     int64_t launches = 0;
     bool profiling = false;
     bool fuse_epilogues = false;
+    bool fuse_momentum = true;      // implicit momentum half-step: all fixed-point iterates in one launch
     // row-sharded mode: this handle holds the rows of shard `shard_rank`; every build is all-reduced
     ncclComm_t comm = nullptr;
     int shard_world = 1, shard_rank = 0;
@@ -695,6 +698,18 @@ int build_partials(rmhmc_handle* h, int flip) {
 int mf_momentum_fixed_point(rmhmc_handle* h) {
     ChainArrays& S = h->S;
     const size_t cd = (size_t)h->n_chains * h->dim;
+    if (h->fuse_momentum && !is_big(h) && !h->comm && h->P.n_fixed >= 2) {
+        // all F iterates in one launch (momfp_kernel.cuh); needs no exchange between iterates
+        const size_t smem = momfp_smem_bytes(h->xs);
+        CUDA_TRY(h, cudaFuncSetAttribute(k_mom_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            Bracket b(h, 5);
+            k_mom_fp<<<blocks_for(h->n_chains, kMetricChains), kMomThreads, smem, h->stream>>>(h->P, S, h->x_pad, h->xs);
+        }
+        h->launches += 1;
+        CUDA_TRY(h, cudaGetLastError());
+        return RMHMC_OK;
+    }
     for (int fi = 0; fi < h->P.n_fixed; ++fi) {
         int rc = launch_metric<3>(h, pass_args(h, S.quad_tmp));
         if (!rc) rc = allreduce_sum(h, S.quad_tmp, cd);
@@ -950,6 +965,7 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
     h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
+    if (const char* e = std::getenv("RMHMC_FUSE_MOMENTUM")) h->fuse_momentum = std::atoi(e) != 0;      // A/B switch for profiling
     h->P.it_stop = 0; h->P.burn_in = 0; h->P.sample_cap = 0;
     *out = h;
     return RMHMC_OK;
