@@ -19,6 +19,7 @@
 #include "metric_kernel.cuh"
 #include "mf_kernels.cuh"
 #include "momfp_kernel.cuh"
+#include "pass_kernel.cuh"
 #include "tbuild_kernel.cuh"
 
 using namespace rmhmc;
@@ -89,7 +90,7 @@ struct rmhmc_handle {
     int64_t launches = 0;
     bool profiling = false;
     bool fuse_epilogues = false;
-    bool fuse_momentum = true;      // implicit momentum half-step: all fixed-point iterates in one launch
+    int fuse_momentum = 1;          // implicit momentum half-step: 1 all iterates in one k_pass launch, 2 k_mom_fp, 0 unfused
     // row-sharded mode: this handle holds the rows of shard `shard_rank`; every build is all-reduced
     ncclComm_t comm = nullptr;
     int shard_world = 1, shard_rank = 0;
@@ -357,9 +358,6 @@ int launch_metric(rmhmc_handle* h, const MetricArgs& a, const FuseArgs& fz = Fus
         case 4: kern = k_metric<4, MODE>; break;
         case 5: kern = k_metric<5, MODE>; break;
         case 6: kern = k_metric<6, MODE>; break;
-        case 7: kern = k_metric<7, MODE>; break;
-        case 8: kern = k_metric<8, MODE>; break;
-        case 9: kern = k_metric<9, MODE>; break;
         default: return fail(h, RMHMC_E_UNSUPPORTED, "metric kernel: dim too large");
     }
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -695,11 +693,33 @@ int build_partials(rmhmc_handle* h, int flip) {
 // ---- matrix-free partials (mf_kernels.cuh)
 // F iterates of the implicit momentum half-step (rmhmc.py:102-110): quadratic forms by a pass over the data,
 // then the per-chain update and u = G^-1 PM for the next pass
+template <int KIND>
+int launch_pass(rmhmc_handle* h) {
+    // 64 chains per CTA; 16 when that grid would leave SMs idle (BASELINE.json configs[1]: 4096 chains)
+    const bool small = h->n_chains < (int64_t)148 * 2 * kPassWarps * 8;
+    const int warps = small ? kPassWarpsSmall : kPassWarps;
+    const size_t smem = pass_smem_bytes(h->xs, warps);
+    auto kern = small ? k_pass<KIND, kPassWarpsSmall> : k_pass<KIND, kPassWarps>;
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        Bracket b(h, KIND == kPassTrace || KIND == kPassPair ? 7 : 5);
+        kern<<<blocks_for(h->n_chains, warps * 8), warps * 32, smem, h->stream>>>(h->P, h->S, h->x_pad, h->xs);
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
 int mf_momentum_fixed_point(rmhmc_handle* h) {
     ChainArrays& S = h->S;
     const size_t cd = (size_t)h->n_chains * h->dim;
-    if (h->fuse_momentum && !is_big(h) && !h->comm && h->P.n_fixed >= 2) {
-        // all F iterates in one launch (momfp_kernel.cuh); needs no exchange between iterates
+    // all F iterates in one launch (needs no exchange between iterates).  Two formulations: one warp per 8 chains
+    // (pass_kernel.cuh; 2.58 vs 3.02 ms at 65 536 German-shaped chains) or 12 cooperating warps per 32 chains
+    // (momfp_kernel.cuh; shorter dependent chains, 0.08 vs 0.23 ms when 4096 chains leave most of the GPU idle)
+    const bool fusable = !is_big(h) && !h->comm && h->P.n_fixed >= 2;
+    const bool few_chains = h->n_chains < (int64_t)148 * 2 * kPassWarps * 8;
+    if (fusable && (h->fuse_momentum == 1 && !few_chains)) return launch_pass<kPassMomFp>(h);
+    if (fusable && (h->fuse_momentum == 2 || (h->fuse_momentum == 1 && few_chains))) {
         const size_t smem = momfp_smem_bytes(h->xs);
         CUDA_TRY(h, cudaFuncSetAttribute(k_mom_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
@@ -711,7 +731,7 @@ int mf_momentum_fixed_point(rmhmc_handle* h) {
         return RMHMC_OK;
     }
     for (int fi = 0; fi < h->P.n_fixed; ++fi) {
-        int rc = launch_metric<3>(h, pass_args(h, S.quad_tmp));
+        int rc = is_big(h) ? launch_metric<3>(h, pass_args(h, S.quad_tmp)) : launch_pass<kPassQuad>(h);
         if (!rc) rc = allreduce_sum(h, S.quad_tmp, cd);
         if (!rc) rc = launch_mf_mom_iter(h, fi + 1 == h->P.n_fixed ? 1 : 0);
         if (rc) return rc;
@@ -724,8 +744,9 @@ int mf_closing_passes(rmhmc_handle* h, int init) {
     ChainArrays& S = h->S;
     const size_t cd = (size_t)h->n_chains * h->dim;
     int rc = launch_leverage(h);
-    if (!rc) rc = launch_metric<4>(h, pass_args(h, S.trace_tmp));
-    if (!rc && !init) rc = launch_metric<3>(h, pass_args(h, S.quad_tmp));
+    if (!rc && !is_big(h)) rc = init ? launch_pass<kPassTrace>(h) : launch_pass<kPassPair>(h);
+    if (!rc && is_big(h)) rc = launch_metric<4>(h, pass_args(h, S.trace_tmp));
+    if (!rc && is_big(h) && !init) rc = launch_metric<3>(h, pass_args(h, S.quad_tmp));
     if (!rc) rc = init ? allreduce_sum(h, S.trace_tmp, cd) : allreduce_sum(h, S.quad_tmp, 2 * cd);
     return rc;
 }
@@ -965,7 +986,7 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
     h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
-    if (const char* e = std::getenv("RMHMC_FUSE_MOMENTUM")) h->fuse_momentum = std::atoi(e) != 0;      // A/B switch for profiling
+    if (const char* e = std::getenv("RMHMC_FUSE_MOMENTUM")) h->fuse_momentum = std::atoi(e);      // A/B switch for profiling
     h->P.it_stop = 0; h->P.burn_in = 0; h->P.sample_cap = 0;
     *out = h;
     return RMHMC_OK;

@@ -1,0 +1,251 @@
+// Passes over the design matrix of the matrix-free partials (mf_kernels.cuh), D <= 32:
+//   QUAD    quad[c][d]  = sum_n c_n (x_n . u_c)^2 x_nd  = u^T dG_d u         (rmhmc.py:105-107, :159-161)
+//   TRACE   trace[c][d] = sum_n c_n h_n x_nd            = tr(G^-1 dG_d)      (rmhmc.py:76-77, :155-156)
+//   PAIR    both in one pass (the closing half of a leapfrog step)
+//   MOMFP   the whole implicit momentum half-step (rmhmc.py:102-110): F fixed-point iterates, each a QUAD pass
+//           followed by PM <- p + s eps/2 (grad - tr/2 + quad/2), u <- G^-1 PM; the last iterate also does
+//           rmhmc.py:110,113 and the first position iterate (whose metric is the one already held)
+// on the FP64 tensor cores (DMMA.8x8x4).  One WARP owns 8 chains (one DMMA m-tile) for the whole kernel and does
+// both contractions of a pass itself:
+//   S[8 chains x 8 rows] = U . X^T (K = D; U fragments live in registers), R = c .* S .* S (or c .* h),
+//   R's C-fragment -> A-fragment by four warp shuffles,  Q[8 chains x D] += R . X (K = 8 rows)
+// so there is no hand-off between warps: the only shared object is the X row-block ring (bulk TMA + full/empty
+// mbarriers, one wait and one arrive per warp per 32 rows).  The warp-specialised formulation these replace
+// (k_metric MODE 3/4, k_mom_fp: F-warps -> shared R tile -> G-warps) was issue-bound on its barrier traffic
+// (ncu: 2.06 G instructions, 3.0 ms for the six passes of one momentum half-step at 65 536 chains).
+#pragma once
+#include "chain_kernels.cuh"
+#include "common.cuh"
+
+namespace rmhmc {
+
+constexpr int kPassWarps = 8;          // m-tiles (8 chains each) per CTA; kPassWarpsSmall when the grid would not fill the GPU
+constexpr int kPassWarpsSmall = 2;
+constexpr int kPassRows = 32;          // rows per staged X block
+constexpr int kPassStages = 4;
+enum { kPassQuad = 0, kPassTrace = 1, kPassPair = 2, kPassMomFp = 3 };
+
+__host__ inline size_t pass_smem_bytes(int xs, int warps) {
+    return (size_t)kPassStages * kPassRows * xs * 8 + (size_t)warps * 2 * 8 * 32 * 8 + 2 * kPassStages * 8;
+}
+
+#ifdef __CUDACC__
+template <int KIND, int W>
+__global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P, ChainArrays S, const double* __restrict__ x, int xs) {
+    constexpr int NB = kPassRows, ST = kPassStages;
+    constexpr bool WITH_U = KIND != kPassTrace, WITH_H = KIND == kPassTrace || KIND == kPassPair;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* xs_ring = reinterpret_cast<double*>(smem_raw);                    // [ST][NB][xs]
+    double* scratch = xs_ring + (size_t)ST * NB * xs;                         // [W][2][8][32]  PM and u of the warp's chains
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(scratch + (size_t)W * 2 * 8 * 32);
+    uint64_t* x_empty = x_full + ST;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int D = P.dim;
+    const int chain0 = (blockIdx.x * W + warp) * 8;          // first chain of this warp
+    const int n_blocks = P.n_rows_pad / NB;
+    const int n_iter = KIND == kPassMomFp ? P.n_fixed : 1;
+    const int n_total = n_blocks * n_iter;
+    const uint32_t stage_bytes = (uint32_t)(NB * xs * 8);
+
+    if (tid == 0) {
+        for (int s = 0; s < ST; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], W); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < ST && s < n_total; ++s) {
+            mbar_expect_tx(&x_full[s], stage_bytes);
+            tma_bulk_g2s(xs_ring + (size_t)s * NB * xs, x + (size_t)(s % n_blocks) * NB * xs, stage_bytes, &x_full[s]);
+        }
+    }
+
+    // ---- this lane's chain (m-tile row g): slot, step direction, operand pointers
+    const int c = chain0 + g;
+    int slot = -1;                 // slot whose c_n this pass reads; -1: idle chain (contributes zeros, stores nothing)
+    double hstep = 0.0;
+    if (c < P.n_chains) {
+        if (KIND == kPassMomFp) {
+            if (S.iter[c] < P.it_stop && S.nsteps[c] > 0) {
+                const int cur = S.cur[c];
+                slot = S.step[c] == 0 ? cur : 1 - cur;
+                hstep = S.dir[c] * P.step_size / 2;
+            }
+        } else {
+            slot = S.aslot[c];
+        }
+    }
+    const bool active = slot >= 0;
+    // rows beyond n_chains exist in the c_n / leverage buffers (chain padding), so the loads below stay in bounds
+    const double* cw_row = S.cw + (slot > 0 ? P.slot_cw : 0) + (size_t)c * P.n_rows_pad + 2 * q;
+    const double* h_row = WITH_H ? S.hbuf + (size_t)c * P.n_rows_pad + 2 * q : nullptr;
+    double ua[8];                  // U A-fragments: u[c][4 ks + q], zero beyond D (the staged label column meets a zero)
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        const int d = ks * 4 + q;
+        ua[ks] = (WITH_U && active && d < D) ? S.uvec[(size_t)c * D + d] : 0.0;
+    }
+    // momentum fixed point: p and grad - tr/2 of this lane's (chain, parameter) pairs, in accumulator layout
+    double pl[4][2], bl[4][2];
+    if (KIND == kPassMomFp) {
+#pragma unroll
+        for (int dt = 0; dt < 4; ++dt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int d = dt * 8 + 2 * q + j;
+                pl[dt][j] = bl[dt][j] = 0.0;
+                if (active && d < D) {
+                    const size_t so = slot * P.slot_theta + (size_t)c * D + d;
+                    pl[dt][j] = S.mom[(size_t)c * D + d];
+                    bl[dt][j] = S.grad[so] - 0.5 * S.trace[so];
+                }
+            }
+    }
+    const int k_steps = (D + 3) / 4;
+    const int d_tiles = (D + 7) / 8;
+    const int src0 = g * 4 + (q >> 1), src1 = src0 + 2;      // shuffle sources of the C -> A fragment conversion
+    const bool odd = q & 1;
+    double* pm_s = scratch + (size_t)warp * 2 * 8 * 32;      // [8][32]
+    double* u_s = pm_s + 8 * 32;                             // [8][32]
+
+    int gb = 0;
+    for (int fi = 0; fi < n_iter; ++fi) {
+        double acc[4][2], acc2[4][2];                        // acc: QUAD / TRACE; acc2: QUAD of PAIR
+#pragma unroll
+        for (int dt = 0; dt < 4; ++dt) acc[dt][0] = acc[dt][1] = acc2[dt][0] = acc2[dt][1] = 0.0;
+        for (int rb = 0; rb < n_blocks; ++rb, ++gb) {
+            const int stage = gb % ST;
+            // c_n (and h_n) of the block's four row groups: issued before the barrier wait
+            double2 cwv[4], hv[4];
+#pragma unroll
+            for (int r8 = 0; r8 < 4; ++r8) {
+                cwv[r8] = *reinterpret_cast<const double2*>(cw_row + rb * NB + r8 * 8);
+                if (WITH_H) hv[r8] = *reinterpret_cast<const double2*>(h_row + rb * NB + r8 * 8);
+            }
+            if (warp == 0 && lane == 0 && gb >= 1 && gb - 1 + ST < n_total) {
+                // refill the stage of block gb-1 once every warp has released it
+                const int nb = gb - 1 + ST, ns = nb % ST;
+                mbar_wait(&x_empty[ns], (uint32_t)(((gb - 1) / ST) & 1));
+                mbar_expect_tx(&x_full[ns], stage_bytes);
+                tma_bulk_g2s(xs_ring + (size_t)ns * NB * xs, x + (size_t)(nb % n_blocks) * NB * xs, stage_bytes, &x_full[ns]);
+            }
+            __syncwarp();
+            mbar_wait(&x_full[stage], (uint32_t)((gb / ST) & 1));
+            const double* xb = xs_ring + (size_t)stage * NB * xs;
+            // stage 1 for the block's four 8-row groups at once: four independent DMMA chains (the FP64 DMMA has a
+            // long dependent-issue latency; a single chain per warp left the pipe idle)
+            double sv[4][2];
+#pragma unroll
+            for (int r8 = 0; r8 < 4; ++r8) sv[r8][0] = sv[r8][1] = 0.0;
+            if (WITH_U) {
+                const double* xrow = xb + (size_t)g * xs + q;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    if (ks < k_steps) {
+#pragma unroll
+                        for (int r8 = 0; r8 < 4; ++r8) dmma884(sv[r8][0], sv[r8][1], ua[ks], xrow[(size_t)(r8 * 8) * xs + ks * 4]);
+                    }
+                }
+            }
+            // R = c .* S .* S (and / or c .* h); C fragment (chain g; rows 2q, 2q+1) -> A fragments (chain g; row q) of
+            // the two 4-row k-steps of every group
+            double aq[4][2], at[4][2];
+#pragma unroll
+            for (int r8 = 0; r8 < 4; ++r8) {
+                if (KIND != kPassTrace) {
+                    const double r0 = cwv[r8].x * sv[r8][0] * sv[r8][0], r1 = cwv[r8].y * sv[r8][1] * sv[r8][1];
+                    const double e0 = __shfl_sync(kFull, r0, src0), o0 = __shfl_sync(kFull, r1, src0);
+                    const double e1 = __shfl_sync(kFull, r0, src1), o1 = __shfl_sync(kFull, r1, src1);
+                    aq[r8][0] = odd ? o0 : e0;
+                    aq[r8][1] = odd ? o1 : e1;
+                }
+                if (WITH_H) {
+                    const double t0 = cwv[r8].x * hv[r8].x, t1 = cwv[r8].y * hv[r8].y;
+                    const double e0 = __shfl_sync(kFull, t0, src0), o0 = __shfl_sync(kFull, t1, src0);
+                    const double e1 = __shfl_sync(kFull, t0, src1), o1 = __shfl_sync(kFull, t1, src1);
+                    at[r8][0] = odd ? o0 : e0;
+                    at[r8][1] = odd ? o1 : e1;
+                }
+            }
+            // stage 2: Q += R . X over the block's eight 4-row k-steps; d-tiles are the independent chains
+#pragma unroll
+            for (int r8 = 0; r8 < 4; ++r8) {
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const double* xr = xb + (size_t)(r8 * 8 + kk * 4 + q) * xs;
+#pragma unroll
+                    for (int dt = 0; dt < 4; ++dt) {
+                        if (dt < d_tiles) {
+                            const int dcol = dt * 8 + g;
+                            const double b = dcol < D ? xr[dcol] : 0.0;
+                            if (KIND == kPassTrace) dmma884(acc[dt][0], acc[dt][1], at[r8][kk], b);
+                            else dmma884(acc[dt][0], acc[dt][1], aq[r8][kk], b);
+                            if (KIND == kPassPair) dmma884(acc2[dt][0], acc2[dt][1], at[r8][kk], b);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x_empty[stage]);
+        }
+
+        if (KIND != kPassMomFp) {
+            if (active) {
+#pragma unroll
+                for (int dt = 0; dt < 4; ++dt)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int d = dt * 8 + 2 * q + j;
+                        if (d < D) {
+                            if (KIND == kPassTrace) S.trace_tmp[(size_t)c * D + d] = acc[dt][j];
+                            else S.quad_tmp[(size_t)c * D + d] = acc[dt][j];
+                            if (KIND == kPassPair) S.trace_tmp[(size_t)c * D + d] = acc2[dt][j];
+                        }
+                    }
+            }
+        } else {
+            // ---- PM = p + s eps/2 (grad - tr/2 + quad/2) for this lane's pairs                      rmhmc.py:108
+#pragma unroll
+            for (int dt = 0; dt < 4; ++dt)
+                *reinterpret_cast<double2*>(pm_s + g * 32 + dt * 8 + 2 * q) =
+                    make_double2(pl[dt][0] + hstep * (bl[dt][0] + 0.5 * acc[dt][0]),
+                                 pl[dt][1] + hstep * (bl[dt][1] + 0.5 * acc[dt][1]));
+            __syncwarp();
+            // ---- u = G^-1 PM, one chain at a time: lane i owns u_i, G^-1 read by columns (coalesced)   rmhmc.py:103
+            const bool last = fi + 1 == n_iter;
+            for (int j = 0; j < 8; ++j) {
+                const int cj = chain0 + j;
+                const int slot_j = __shfl_sync(kFull, slot, j * 4);
+                const double h_j = __shfl_sync(kFull, hstep, j * 4);
+                if (slot_j < 0) continue;
+                double y0 = 0.0, y1 = 0.0;
+                const double* xv = pm_s + j * 32;
+                if (lane < D) {
+                    const double* col = S.invg + slot_j * P.slot_invg + (size_t)cj * D * D + lane;
+                    int b = 0;
+#pragma unroll 4
+                    for (; b + 1 < D; b += 2) {
+                        y0 = fma(col[(size_t)b * D], xv[b], y0);
+                        y1 = fma(col[(size_t)(b + 1) * D], xv[b + 1], y1);
+                    }
+                    if (b < D) y0 = fma(col[(size_t)b * D], xv[b], y0);
+                }
+                const double u = y0 + y1;
+                u_s[j * 32 + lane] = lane < D ? u : 0.0;
+                if (last && lane < D) {
+                    const size_t cd = (size_t)cj * D + lane;
+                    S.mom[cd] = xv[lane];                                                    // rmhmc.py:110
+                    S.u0[cd] = u;                                                            // rmhmc.py:113
+                    S.theta_w[cd] = S.theta[slot_j * P.slot_theta + cd] + h_j * (u + u);     // rmhmc.py:116-122, first iterate
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) ua[ks] = active ? u_s[g * 32 + ks * 4 + q] : 0.0;
+            __syncwarp();
+        }
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace rmhmc
