@@ -10,7 +10,11 @@ shape = sys.argv[1] if len(sys.argv) > 1 else "german"
 chains = [int(a) for a in sys.argv[2:]] or [4096, 16384, 65536]
 R = int(os.environ.get("PROBE_ROUNDS", "20"))
 WARM = int(os.environ.get("PROBE_WARM", "10"))
-xx, t = r.datasets.shaped(shape)
+if shape.startswith("synthetic:"):          # synthetic:N:D:seed  (BASELINE.json configs[2]: synthetic:100000:100:1236)
+    _, n_, d_, seed_ = shape.split(":")
+    xx, t = r.datasets.synthetic_logistic(int(n_), int(d_), int(seed_))
+else:
+    xx, t = r.datasets.shaped(shape)
 N, D = xx.shape
 P2, P3 = D * (D + 1) // 2, D * (D + 1) * (D + 2) // 6
 F = 6
