@@ -112,3 +112,27 @@ def test_oracle_matches_live_reference_on_a_fresh_tape():
     tools = ref_live.load_reference()["tools"]
     x = np.random.default_rng(5).standard_normal((700, 2)).cumsum(axis=0) * 0.05 + np.random.default_rng(6).standard_normal((700, 2))
     assert np.array_equal(tools.CalculateESS(x, 699), bo.ess(x, 699))
+
+
+def test_matrix_free_identities_equal_the_reference_partials():
+    """The two contractions the reference forms InvGdG for (rmhmc.py:77, :105-107), evaluated without it.
+
+    tr(G^-1 dG_d) = sum_n c_n x_nd (x_n^T G^-1 x_n) and p^T G^-1 dG_d G^-1 p = sum_n c_n x_nd (x_n . G^-1 p)^2 with
+    c_n = v_n (1 - 2 p_n): what the CUDA engine's MATRIX_FREE partials mode computes (include/rmhmc_b200.h).
+    """
+    from riemannhamiltonianmontecarlo_b200 import datasets
+    xx, t = datasets.shaped("australian")
+    rng = np.random.default_rng(5)
+    w = rng.normal(0, 0.4, (xx.shape[1], 1))
+    mom = rng.normal(0, 3.0, (xx.shape[1], 1))
+    _, p, v, g = bo.fisher_metric(xx, w)
+    inv_g = np.linalg.inv(g)
+    inv_g_dg, tr_ref = bo.metric_partials(xx, p, v, inv_g)                     # the reference's formulation
+    u = inv_g.dot(mom)
+    last_ref = np.array([bo._scalar(mom.T.dot(inv_g_dg[d]).dot(u)) for d in range(xx.shape[1])])
+    c = v * (1 - 2 * p[:, 0])
+    lev = np.einsum("na,ab,nb->n", xx, inv_g, xx)
+    tr_mf = xx.T.dot(c * lev)
+    quad_mf = xx.T.dot(c * xx.dot(u)[:, 0] ** 2)
+    assert np.abs(tr_mf - tr_ref[:, 0]).max() < 1e-12 * np.abs(tr_ref).max()
+    assert np.abs(quad_mf - last_ref).max() < 1e-12 * np.abs(last_ref).max()
