@@ -17,7 +17,6 @@
 #include "ess_kernel.cuh"
 #include "hmc_kernels.cuh"
 #include "metric_kernel.cuh"
-#include "metric2_kernel.cuh"
 #include "mf_kernels.cuh"
 #include "momfp_kernel.cuh"
 #include "pass_kernel.cuh"
@@ -91,7 +90,6 @@ struct rmhmc_handle {
     int64_t launches = 0;
     bool profiling = false;
     bool fuse_epilogues = false;
-    bool metric2 = true;            // metric builds by k_metric2 where it applies (RMHMC_METRIC2=0: always k_metric)
     int fuse_momentum = 1;          // implicit momentum half-step: 1 all iterates in one k_pass launch, 2 k_mom_fp, 0 unfused
     // row-sharded mode: this handle holds the rows of shard `shard_rank`; every build is all-reduced
     ncclComm_t comm = nullptr;
@@ -346,37 +344,8 @@ FuseArgs fuse_args(rmhmc_handle* h, int mode, int is_last, int init) {
     return f;
 }
 
-// second formulation of the metric build (metric2_kernel.cuh): D <= 25 and enough chains to fill the GPU with
-// 64-chain CTAs
-template <int TILES, int MODE>
-int launch_metric2_t(rmhmc_handle* h, const MetricArgs& a) {
-    const size_t smem = metric2_smem_bytes(h->xs, TILES);
-    CUDA_TRY(h, cudaFuncSetAttribute(k_metric2<TILES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        Bracket b(h, MODE == 0 ? 0 : 1);
-        k_metric2<TILES, MODE><<<blocks_for(a.n_chains, kM2Warps * 8), kM2Threads, smem, h->stream>>>(a);
-    }
-    h->launches += 1;
-    CUDA_TRY(h, cudaGetLastError());
-    return RMHMC_OK;
-}
-bool use_metric2(const rmhmc_handle* h, int64_t n_chains) {
-    return h->metric2 && h->p2p / 8 <= 41 && n_chains >= (int64_t)148 * kM2Warps * 8;
-}
-template <int MODE>
-int launch_metric2(rmhmc_handle* h, const MetricArgs& a) {
-    const int tiles = h->p2p / 8;
-    if (tiles <= 6) return launch_metric2_t<6, MODE>(h, a);
-    if (tiles <= 17) return launch_metric2_t<17, MODE>(h, a);
-    if (tiles <= 29) return launch_metric2_t<29, MODE>(h, a);
-    return launch_metric2_t<41, MODE>(h, a);
-}
-
 template <int MODE>
 int launch_metric(rmhmc_handle* h, const MetricArgs& a, const FuseArgs& fz = FuseArgs{}) {
-    if constexpr (MODE <= 1) {
-        if (fz.mode == kFuseNone && use_metric2(h, a.n_chains)) return launch_metric2<MODE>(h, a);
-    }
     size_t smem = metric_smem_bytes(h->xs, h->p2p, fz.mode != kFuseNone);
     dim3 grid(blocks_for(a.n_chains, kMetricChains), MODE >= 2 ? (unsigned)((h->dim + 31) / 32) : (unsigned)h->col_ctas);
     if (fz.mode != kFuseNone && grid.y != 1) return fail(h, RMHMC_E_UNSUPPORTED, "fused epilogues need a single column CTA");
@@ -1017,7 +986,6 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
     h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
-    if (const char* e = std::getenv("RMHMC_METRIC2")) h->metric2 = std::atoi(e) != 0;
     if (const char* e = std::getenv("RMHMC_FUSE_MOMENTUM")) h->fuse_momentum = std::atoi(e);      // A/B switch for profiling
     h->P.it_stop = 0; h->P.burn_in = 0; h->P.sample_cap = 0;
     *out = h;
