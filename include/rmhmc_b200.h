@@ -168,6 +168,21 @@ int hmc_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const doubl
                  const double* u_step, const double* u_acc);
 int hmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
 
+/* ---- manifold MALA / simplified manifold MALA -------------------------------------------------
+ * MATLAB-only in the reference: code/authors_code/Bayes_Log_Reg/MCMC/BLR_mMALA.m:159-330 and
+ * BLR_mMALA_Simp.m:170-290.  One iteration = one metric evaluation at the proposal
+ *   w' = Mean + (z chol(eps G^-1))',  Mean = w + eps/2 G^-1 grad - eps sum_d G^-1 dG_d G^-1 e_d + eps/2 G^-1 tr
+ * (simplified != 0: Mean = w + eps/2 G^-1 grad), accepted with the Metropolis-Hastings ratio of BLR_mMALA.m:282.
+ * theta0 NULL = zeros (BLR_mMALA.m:165).  step_size is the reference's StepSize (= eps, default 1); it is fixed at
+ * chains_init because the cached drift and proposal factor of the current state depend on it.  The tape holds
+ * z (n_window x n_chains x dim) and u_acc (n_window x n_chains; consumed only if Ratio <= 0); rmhmc_set_philox,
+ * rmhmc_set_samples (row it - burn_in for it >= burn_in, as in the MATLAB loop), rmhmc_set_trace (theta_end = the
+ * proposal, h_current = log q(new|old), h_proposed = Ratio, flags bit0 accepted / bit1 uniform consumed) and
+ * rmhmc_read_state apply.  dim <= 32.  The full drift runs on the MATRIX_FREE partials (the handle is switched). */
+int mmala_chains_init(rmhmc_handle* h, int64_t n_chains, const double* theta0, int simplified, double step_size);
+int mmala_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const double* z, const double* u_acc);
+int mmala_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
+
 /* ---- tools.py:32-74 batched ------------------------------------------------------------------ */
 /* ESS of every (chain, parameter) series: samples (n_chains x n_samples x dim) with the given
  * strides in doubles; ess (n_chains x dim).  Exactly tools.CalculateESS(series, max_lag) incl. the

@@ -445,6 +445,87 @@ def hmc_chain(xx, t, tape: DrawTape, n_iter=6000, burn_in=1000, n_leapfrog=100,
     return samples, info
 
 
+# --------------------------------------------------------------------------- mMALA (MATLAB original only)
+def _mmala_terms(xx, t, w, alpha, simplified):
+    """G, G^-1 and the drift pieces of BLR_mMALA.m:187-213 / :246-271 (BLR_mMALA_Simp.m:176-180,:214-224) at w."""
+    d = xx.shape[1]
+    f, p, v, g = fisher_metric(xx, w, alpha)
+    inv_g = np.linalg.inv(g)
+    first = inv_g.dot(xx.T.dot(t - np.exp(f) / (1 + np.exp(f))) - np.eye(d) * (1 / alpha) @ w)
+    if simplified:
+        return g, inv_g, first, None, None
+    inv_g_dg, tr = metric_partials(xx, p, v, inv_g)
+    second = np.empty((d, d))
+    for k in range(d):
+        second[:, k] = inv_g_dg[k].dot(inv_g[:, k])                    # InvGdG{d} * InvG(:, d)
+    third = inv_g.dot(tr)
+    return g, inv_g, first, second, third
+
+
+def mmala_chain(xx, t, tape: DrawTape, n_iter=10000, burn_in=5000, step_size=1.0, alpha=ALPHA, simplified=False,
+                record=False):
+    """One (simplified) manifold-MALA chain under a draw tape; restates the MATLAB original
+    ``code/authors_code/Bayes_Log_Reg/MCMC/BLR_mMALA.m:159-330`` (``BLR_mMALA_Simp.m:170-290``).
+
+    PARITY UNPINNED: the reference has no Python mMALA and MATLAB/Octave is not available, so this port cannot be
+    run against the original.  Conventions: iterations are 0-based here (MATLAB IterationNum = it + 1); the sample
+    after iteration ``it`` goes to row ``it - burn_in`` for ``it >= burn_in`` (MATLAB: IterationNum > BurnIn);
+    per iteration the tape supplies ``z[it]`` (``randn(1,D)``, :233) and ``u_acc[it]`` (``rand``, :289, consumed only
+    if Ratio <= 0 -- MATLAB ``||`` short-circuits); ``chol`` is MATLAB's upper factor R (R'R = A), so the proposal
+    ``(randn(1,D) * chol(S))'`` is ``L z`` with the lower factor ``L = R'``.
+    """
+    n, d = xx.shape
+    w = np.zeros((d, 1))                                                   # :165
+    samples = np.zeros((n_iter - burn_in, d))
+    cur_ljl = log_joint(xx, t, w, alpha)                                   # :169-172
+    cur_g, cur_inv_g, cur_first, cur_second, cur_third = _mmala_terms(xx, t, w, alpha, simplified)
+    accepted = np.zeros(n_iter, dtype=bool)
+    records = []
+
+    def drift(wv, first, second, third):
+        mean = wv + (step_size / 2) * first                                # :227-229 / Simp :207
+        if not simplified:
+            mean = mean - step_size * np.sum(second, axis=1, keepdims=True) + (step_size / 2) * third
+        return mean
+
+    for it in range(n_iter):
+        mean = drift(w, cur_first, cur_second, cur_third)
+        l_prop = np.linalg.cholesky(step_size * cur_inv_g)
+        w_new = mean + l_prop.dot(tape.z[it].reshape(d, 1))                # :233
+        prop_ljl = log_joint(xx, t, w_new, alpha)                          # :236-239
+        diff = mean - w_new
+        p_new_old = -np.sum(np.log(np.diag(l_prop))) - 0.5 * _scalar(diff.T.dot(cur_g / step_size).dot(diff))   # :241
+        g, inv_g, first, second, third = _mmala_terms(xx, t, w_new, alpha, simplified)
+        mean_back = drift(w_new, first, second, third)                     # :275-277
+        diff = mean_back - w
+        p_old_new = -np.sum(np.log(np.diag(np.linalg.cholesky(step_size * inv_g)))) \
+            - 0.5 * _scalar(diff.T.dot(g / step_size).dot(diff))           # :279
+        ratio = _scalar(prop_ljl) + p_old_new - _scalar(cur_ljl) - p_new_old   # :282
+        take = bool(ratio > 0)
+        used_u = False
+        if not take:
+            used_u = True
+            take = bool(ratio > np.log(tape.u_acc[it]))                    # :285
+        if record:
+            records.append({"theta": w_new[:, 0].copy(), "ratio": ratio, "accepted": take, "used_uniform": used_u,
+                            "prop_ljl": _scalar(prop_ljl)})
+        if take:
+            cur_ljl = prop_ljl
+            cur_g, cur_inv_g, cur_first, cur_second, cur_third = g, inv_g, first, second, third
+            w = w_new
+            accepted[it] = True
+        if it >= burn_in:
+            samples[it - burn_in, :] = w.T                                 # :313-315
+
+    info = {"w": w[:, 0].copy(), "log_joint": _scalar(cur_ljl), "accepted": accepted, "records": records}
+    return samples, info
+
+
+def mmala_chains(xx, t, tapes: list[DrawTape], **kw):
+    out = [mmala_chain(xx, t, tp, **kw) for tp in tapes]
+    return np.stack([o[0] for o in out]), [o[1] for o in out]
+
+
 # --------------------------------------------------------------------------- batched helpers
 def rmhmc_chains(xx, t, tapes: list[DrawTape], **kw):
     """Run independent chains one after another; returns samples (C, S, D) and the infos."""

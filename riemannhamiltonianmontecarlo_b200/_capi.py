@@ -47,6 +47,9 @@ SIGNATURES = {
     "hmc_configure": (c_int, [c_void_p, c_int, c_double]),
     "hmc_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "hmc_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
+    "mmala_chains_init": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_double]),
+    "mmala_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "mmala_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     "blr_ess_batched": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p]),
     "blr_autocorr": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "blr_ess_ragged": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),

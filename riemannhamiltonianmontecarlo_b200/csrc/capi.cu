@@ -20,6 +20,7 @@
 #include "mf_kernels.cuh"
 #include "momfp_kernel.cuh"
 #include "pass_kernel.cuh"
+#include "mmala_kernels.cuh"
 #include "tbuild_kernel.cuh"
 
 using namespace rmhmc;
@@ -82,6 +83,8 @@ struct rmhmc_handle {
     // chains
     int64_t n_chains = 0, c_pad = 0;
     bool is_hmc = false;
+    bool is_mmala = false;
+    int mmala_simplified = 0;
     std::vector<void*> chain_allocs;
     ChainArrays S{};
     EngineParams P{};
@@ -475,6 +478,7 @@ int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
     h->n_chains = C;
     h->c_pad = pad_up((int)C, kTbChains);
     h->is_hmc = hmc;
+    h->is_mmala = false;
     auto* tr = &h->chain_allocs;
     size_t c = (size_t)C, D = (size_t)h->dim;
     ChainArrays& S = h->S;
@@ -824,8 +828,48 @@ int hmc_round(rmhmc_handle* h) {
     return RMHMC_OK;
 }
 
-int run_until(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done, bool hmc) {
-    if (h->n_chains <= 0 || h->is_hmc != hmc) return fail(h, RMHMC_E_STATE, "chains not initialised for this sampler");
+// ---- manifold MALA (mmala_kernels.cuh): one round = one MCMC iteration of every chain
+int launch_mmala_turn(rmhmc_handle* h, int do_back, int do_front, int init) {
+    const unsigned C = (unsigned)h->n_chains;
+    const int simp = h->mmala_simplified;
+    {
+        Bracket b(h, 3);
+        switch (chain_order(h->dim)) {
+            case 8: k_mmala_turn<8><<<C, 32, 0, h->stream>>>(h->P, h->S, do_back, do_front, init, simp); break;
+            case 16: k_mmala_turn<16><<<C, 32, 0, h->stream>>>(h->P, h->S, do_back, do_front, init, simp); break;
+            case 25: k_mmala_turn<25><<<C, 32, 0, h->stream>>>(h->P, h->S, do_back, do_front, init, simp); break;
+            default: k_mmala_turn<32><<<C, 32, 0, h->stream>>>(h->P, h->S, do_back, do_front, init, simp);
+        }
+    }
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+// metric quantities at theta_w into the proposal (flip = 1) / current (flip = 0) slot's inputs
+int mmala_builds(rmhmc_handle* h, int flip) {
+    int rc = launch_metric<1>(h, closing_args(h, flip));
+    if (!rc) rc = reduce_build<1>(h);
+    if (!rc) rc = launch_factor(h, flip ? 0 : 1);
+    if (!rc && !h->mmala_simplified) {
+        rc = launch_leverage(h);
+        if (!rc) rc = launch_pass<kPassTrace>(h);
+        if (!rc) rc = allreduce_sum(h, h->S.trace_tmp, (size_t)h->n_chains * h->dim);
+    }
+    return rc;
+}
+int mmala_rounds(rmhmc_handle* h, int64_t n_rounds) {
+    if (n_rounds <= 0) return RMHMC_OK;
+    int rc = launch_mmala_turn(h, 0, 1, 0);
+    for (int64_t r = 0; r < n_rounds && !rc; ++r) {
+        rc = mmala_builds(h, 1);
+        if (!rc) rc = launch_mmala_turn(h, 1, r + 1 < n_rounds ? 1 : 0, 0);
+    }
+    return rc;
+}
+
+int run_until(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done, bool hmc, bool mmala = false) {
+    if (h->n_chains <= 0 || h->is_hmc != hmc || h->is_mmala != mmala)
+        return fail(h, RMHMC_E_STATE, "chains not initialised for this sampler");
     if (!h->configured || !h->rng_set) return fail(h, RMHMC_E_STATE, "configure and set a tape / philox seed first");
     h->P.it_stop = it_stop;
     int64_t total = 0;
@@ -843,6 +887,9 @@ int run_until(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done, bool hmc) 
                 int rc = hmc_round(h);
                 if (rc) return rc;
             }
+        } else if (mmala) {
+            int rc = mmala_rounds(h, chunk);
+            if (rc) return rc;
         } else {
             int rc = rmhmc_rounds(h, chunk);
             if (rc) return rc;
@@ -1253,7 +1300,7 @@ int rmhmc_set_trace(rmhmc_handle* h, int64_t n_iters, double* theta_steps, doubl
 
 int rmhmc_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop) {
     if (!h || n_rounds < 0) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_advance: bad arguments") : RMHMC_E_INVALID;
-    if (h->n_chains <= 0 || h->is_hmc) return fail(h, RMHMC_E_STATE, "rmhmc_advance: call rmhmc_chains_init first");
+    if (h->n_chains <= 0 || h->is_hmc || h->is_mmala) return fail(h, RMHMC_E_STATE, "rmhmc_advance: call rmhmc_chains_init first");
     if (!h->configured || !h->rng_set) return fail(h, RMHMC_E_STATE, "rmhmc_advance: configure and set a tape / philox seed first");
     CUDA_TRY(h, cudaSetDevice(h->device));
     h->P.it_stop = it_stop;
@@ -1269,6 +1316,47 @@ int hmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done) {
     if (!h) return RMHMC_E_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));
     return run_until(h, it_stop, rounds_done, true);
+}
+
+int mmala_chains_init(rmhmc_handle* h, int64_t C, const double* theta0, int simplified, double step_size) {
+    if (!h || C <= 0 || !(step_size > 0)) return h ? fail(h, RMHMC_E_INVALID, "mmala_chains_init: bad arguments") : RMHMC_E_INVALID;
+    if (h->dim > kMaxDimWarp) return fail(h, RMHMC_E_UNSUPPORTED, "mmala: dim > 32 is not supported");
+    if (!simplified && !h->kr2t) return fail(h, RMHMC_E_UNSUPPORTED, "mmala: the full drift needs the matrix-free partials (KR2(X)^T resident)");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const bool saved_mf = h->matrix_free;
+    if (!simplified) h->matrix_free = true;
+    int rc = alloc_chains(h, C, false);
+    if (rc) { h->matrix_free = saved_mf; return rc; }
+    h->is_mmala = true;
+    h->mmala_simplified = simplified ? 1 : 0;
+    h->P.step_size = step_size; h->P.n_leapfrog = 1; h->P.n_fixed = 0;       // the cached drift / proposal factor depend on eps
+    h->configured = true;
+    ChainArrays& S = h->S;
+    if (theta0)
+        CUDA_TRY(h, cudaMemcpyAsync(S.theta_w, theta0, (size_t)C * h->dim * 8, cudaMemcpyDeviceToDevice, h->stream));
+    else
+        CUDA_TRY(h, cudaMemsetAsync(S.theta_w, 0, (size_t)C * h->dim * 8, h->stream));      // w = zeros(D,1), BLR_mMALA.m:165
+    h->P.samples = nullptr; h->P.tr_theta_steps = nullptr; h->P.tr_mom_end = nullptr; h->P.tr_theta_end = nullptr;
+    h->P.tr_mom0 = nullptr; h->P.tr_hcur = nullptr; h->P.tr_hprop = nullptr; h->P.tr_flags = nullptr; h->P.tr_iters = 0;
+    h->rng_set = false;
+    rc = set_chain_smem_attrs(h);
+    if (!rc) rc = mmala_builds(h, 0);
+    if (!rc) rc = launch_mmala_turn(h, 1, 0, 1);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return RMHMC_OK;
+}
+int mmala_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const double* z, const double* u_acc) {
+    if (!h || n_window <= 0 || !z || !u_acc) return h ? fail(h, RMHMC_E_INVALID, "mmala_set_tape: bad arguments") : RMHMC_E_INVALID;
+    h->P.rng_mode = 0; h->P.tape_base = it_base; h->P.tape_z = z; h->P.tape_u_step = nullptr;
+    h->P.tape_z_dir = nullptr; h->P.tape_u_acc = u_acc;
+    h->rng_set = true;
+    return RMHMC_OK;
+}
+int mmala_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done) {
+    if (!h) return RMHMC_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return run_until(h, it_stop, rounds_done, false, true);
 }
 
 int rmhmc_leapfrog(rmhmc_handle* h, int64_t C, const double* theta, const double* mom, const int32_t* dir,

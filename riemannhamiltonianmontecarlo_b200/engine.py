@@ -160,7 +160,7 @@ class LogisticData:
 class _SamplerBase:
     _is_hmc = False
 
-    def __init__(self, data: LogisticData, n_chains: int, theta0=None):
+    def __init__(self, data: LogisticData, n_chains: int, theta0=None, _init=None):
         self.data = data
         self._lib = data._lib
         self.torch = data.torch
@@ -172,6 +172,9 @@ class _SamplerBase:
         self.burn_in = 0
         self.trace = None
         th0 = None if theta0 is None else data._dev(np.asarray(theta0, dtype=np.float64).reshape(self.n_chains, self.dim))
+        if _init is not None:
+            _capi.check(_init(th0), self.h, "chains_init")
+            return
         fn = self._lib.hmc_chains_init if self._is_hmc else self._lib.rmhmc_chains_init
         _capi.check(fn(self.h, self.n_chains, _ptr(th0)), self.h, "chains_init")
 
@@ -302,6 +305,35 @@ class HMCSampler(_SamplerBase):
     def run(self, it_stop: int) -> int:
         rounds = c_int64(0)
         _capi.check(self._lib.hmc_run(self.h, int(it_stop), ctypes.byref(rounds)), self.h, "hmc_run")
+        return rounds.value
+
+
+class MMALASampler(_SamplerBase):
+    """C independent (simplified) manifold-MALA chains; one round = one MCMC iteration of every chain.
+
+    MATLAB-only in the reference (BLR_mMALA.m / BLR_mMALA_Simp.m); see include/rmhmc_b200.h.
+    """
+
+    def __init__(self, data: LogisticData, n_chains: int, step_size: float = 1.0, simplified: bool = False, theta0=None):
+        lib, h, c = data._lib, data.handle, int(n_chains)
+        super().__init__(data, n_chains, theta0,
+                         _init=lambda th0: lib.mmala_chains_init(h, c, _ptr(th0), 1 if simplified else 0, float(step_size)))
+        self.step_size, self.simplified = float(step_size), bool(simplified)
+
+    def set_tape(self, z, u_acc, it_base: int = 0):
+        d = self.data
+        self._keep["tape"] = [d._dev(z), d._dev(u_acc)]
+        zt, ua = self._keep["tape"]
+        assert zt.shape == (zt.shape[0], self.n_chains, self.dim) and ua.shape == (zt.shape[0], self.n_chains)
+        _capi.check(self._lib.mmala_set_tape(self.h, int(it_base), int(zt.shape[0]), _ptr(zt), _ptr(ua)), self.h,
+                    "mmala_set_tape")
+
+    def set_trace(self, n_iters: int):          # noqa: D102
+        super().set_trace(n_iters, 1)
+
+    def run(self, it_stop: int) -> int:
+        rounds = c_int64(0)
+        _capi.check(self._lib.mmala_run(self.h, int(it_stop), ctypes.byref(rounds)), self.h, "mmala_run")
         return rounds.value
 
 

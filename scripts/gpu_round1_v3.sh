@@ -17,11 +17,10 @@ capture() {  # name regex skip
   ncu -i /tmp/prof_$1.ncu-rep --page raw --csv > gpurun_out/$1_raw.csv 2>/dev/null
   ncu -i /tmp/prof_$1.ncu-rep --page details --csv > gpurun_out/$1_details.csv 2>/dev/null
 }
-capture metric_fp k_metric 10
-capture metric_closing k_metric 7
-capture trace_pass k_metric 8
-capture quad_pass k_metric 9
-capture mom_fp k_mom_fp 2
+capture metric_fp k_metric 8
+capture metric_closing k_metric 12
+capture mom_fixed_point k_pass 3
+capture pair_pass k_pass 4
 capture leverage_gemm k_tbuild_pre 2
 capture chain_solve k_chain_solve 8
 capture chain_factor k_chain_factor 3

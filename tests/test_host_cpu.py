@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_symbols():
     text = open(os.path.join(ROOT, "include", "rmhmc_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:rmhmc|hmc|blr)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b((?:rmhmc|hmc|mmala|blr)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_header_symbol(built_library):
