@@ -383,6 +383,13 @@ def gpu_main(args):
         top, top_name = "metric_fp", "k_metric<MODE 0> (f = X theta, G = V . KR2(X), FP64 DMMA.8x8x4)"
         # F metric builds + leverage GEMM + (F + 1) quadratic-form passes + trace pass
         w_alg = 2.0 * N_FIXED * N * (P2 + D) + 2.0 * N * P2 + (N_FIXED + 1) * 4.0 * N * D + 2.0 * N * D
+    # DRAM traffic of the dominant kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    # `ncu --set full` captures of exactly these configurations; null for any other configuration
+    NCU_TRAFFIC = {
+        ("german", 65536, "matrix_free"): (13.44e6 + 117.75e6, "profiles/r01/ncu_v3_metric_fp_raw.csv"),
+        ("german", 65536, "tensor"): (539.19e6 + 1487.65e6, "profiles/r01/ncu_v2_tbuild_raw.csv"),
+    }
+    traffic, traffic_src = NCU_TRAFFIC.get((args.workload, C, args.partials), (None, None))
     top_ms, top_n = prof[top]
     flops_per_launch = alg_flops[top]
     achieved = flops_per_launch / (top_ms / max(top_n, 1) * 1e-3) / 1e12 if top_n else None
@@ -416,7 +423,7 @@ def gpu_main(args):
         "alg_flops_per_chain_leapfrog": w_alg,
         "roofline": {"bound": "tensor", "kernel": top_name,
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": "max(cuBLAS DGEMM 4096^3 measured live = %.1f, DMMA issue microbenchmark = %.1f); "
                                     "MEASURED_PEAKS.json has no FP64 entry" % (fp64_peak, microbench_peak),
                      "flops_per_launch": flops_per_launch},
