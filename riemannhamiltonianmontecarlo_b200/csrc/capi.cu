@@ -98,6 +98,8 @@ struct rmhmc_handle {
     ncclComm_t comm = nullptr;
     int shard_world = 1, shard_rank = 0;
     double* t_tmp = nullptr;        // [C][P3p] contiguous partials of the last build (sharded mode)
+    double* split_buf = nullptr;    // partial outputs of row-split metric builds / passes
+    size_t split_cap = 0;
     ProfSlot prof[8];
     mutable std::string err;
 };
@@ -348,9 +350,29 @@ FuseArgs fuse_args(rmhmc_handle* h, int mode, int is_last, int init) {
 }
 
 template <int MODE>
-int launch_metric(rmhmc_handle* h, const MetricArgs& a, const FuseArgs& fz = FuseArgs{}) {
+int launch_metric(rmhmc_handle* h, const MetricArgs& a_in, const FuseArgs& fz = FuseArgs{}) {
+    MetricArgs a = a_in;
     size_t smem = metric_smem_bytes(h->xs, h->p2p, fz.mode != kFuseNone);
     dim3 grid(blocks_for(a.n_chains, kMetricChains), MODE >= 2 ? (unsigned)((h->dim + 31) / 32) : (unsigned)h->col_ctas);
+    // Few chains and very many rows (BASELINE.json configs[4]: 64 chains, 1.25 M rows per GPU): the chain / column tiles
+    // alone leave most SMs idle, so the rows are split over gridDim.z and the partial sums added in split order.
+    const int n_blocks_all = h->n_rows_pad / kMetricRows;
+    int splits = 1;
+    if (fz.mode == kFuseNone && grid.x * grid.y < 74) splits = std::max(1, std::min((int)(296 / (grid.x * grid.y)), n_blocks_all / 16));
+    const size_t cg = (size_t)a.n_chains * h->p2p, cd = (size_t)a.n_chains * h->dim, cl = (size_t)a.n_chains;
+    if (splits > 1) {
+        const size_t need = (size_t)splits * (cg + cd + cl);
+        if (need > h->split_cap) {
+            if (h->split_buf) CUDA_TRY(h, cudaFree(h->split_buf));
+            h->split_buf = nullptr; h->split_cap = 0;
+            CUDA_TRY(h, cudaMalloc((void**)&h->split_buf, need * 8));
+            h->split_cap = need;
+        }
+        a.g_out = h->split_buf; a.split_g = cg;
+        a.grad_out = h->split_buf + (size_t)splits * cg; a.split_grad = cd;
+        a.loglik_out = a.grad_out + (size_t)splits * cd; a.split_ll = cl;
+        grid.z = (unsigned)splits;
+    }
     if (fz.mode != kFuseNone && grid.y != 1) return fail(h, RMHMC_E_UNSUPPORTED, "fused epilogues need a single column CTA");
     void (*kern)(MetricArgs, FuseArgs) = nullptr;
     int nt = MODE >= 2 ? 1 : h->nt;
@@ -367,6 +389,12 @@ int launch_metric(rmhmc_handle* h, const MetricArgs& a, const FuseArgs& fz = Fus
     {
         Bracket b(h, MODE == 0 ? 0 : (MODE == 3 ? 5 : (MODE == 4 ? 7 : 1)));
         kern<<<grid, kMetricThreads, smem, h->stream>>>(a, fz);
+        if (splits > 1) {
+            if (MODE <= 1 && a_in.g_out) k_reduce_splits<<<blocks_for(cg, 256), 256, 0, h->stream>>>(a.g_out, cg, splits, a_in.g_out, cg);
+            if (MODE >= 1 && a_in.grad_out) k_reduce_splits<<<blocks_for(cd, 256), 256, 0, h->stream>>>(a.grad_out, cd, splits, a_in.grad_out, cd);
+            if ((MODE == 1 || MODE == 2) && a_in.loglik_out) k_reduce_splits<<<blocks_for(cl, 256), 256, 0, h->stream>>>(a.loglik_out, cl, splits, a_in.loglik_out, cl);
+            h->launches += 3;
+        }
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -1045,7 +1073,7 @@ void rmhmc_destroy(rmhmc_handle* h) {
     drain_profile(h);
     free_chains(h);
     if (h->comm) nccl_api().CommDestroy(h->comm);
-    cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->kr2t); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
+    cudaFree(h->split_buf); cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->kr2t); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
     cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
     delete h;
 }

@@ -43,6 +43,9 @@ struct MetricArgs {
     const double* hbuf;       // [Cpad][Np] leverages (MODE 4)
     int n_chains, n_rows, n_rows_pad, dim, xs, p2, p2p;
     int extra_tile;           // n-tile split over the chain tiles of G-warps 0..3, or -1
+    // row splitting (gridDim.z > 1: few chains, very many rows): split z handles a contiguous range of row blocks and
+    // writes PARTIAL g / grad / loglik at offset z * split_* ; k_reduce_splits adds them in split order
+    size_t split_g, split_grad, split_ll;
     int tiles_per_cta;        // packed-column tiles owned by one CTA (blockIdx.y selects the range)
     int n_main_tiles;         // tiles distributed over the G-warps (all tiles except extra_tile)
     double alpha_inv;
@@ -190,7 +193,13 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int chain0 = blockIdx.x * MC;
     if (chain0 >= a.n_chains) return;
-    const int n_blocks = a.n_rows_pad / NB;
+    const int n_blocks_all = a.n_rows_pad / NB;
+    const int rb_begin = (int)((long long)n_blocks_all * blockIdx.z / gridDim.z);
+    const int n_blocks = (int)((long long)n_blocks_all * (blockIdx.z + 1) / gridDim.z) - rb_begin;      // this split's row blocks
+    if (gridDim.z > 1) {
+        a.g_out += blockIdx.z * a.split_g; a.grad_out += blockIdx.z * a.split_grad; a.loglik_out += blockIdx.z * a.split_ll;
+        if (blockIdx.z > 0) a.alpha_inv = 0.0;
+    }
     const uint32_t stage_bytes = (uint32_t)(NB * xs * 8);
 
     if (tid == 0) {
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
         if (fw == 0 && lane == 0) {
             for (int s = 0; s < ST && s < n_blocks; ++s) {
                 mbar_expect_tx(&x_full[s], stage_bytes);
-                tma_bulk_g2s(xs_ring + (size_t)s * NB * xs, a.x + (size_t)s * NB * xs, stage_bytes, &x_full[s]);
+                tma_bulk_g2s(xs_ring + (size_t)s * NB * xs, a.x + (size_t)(rb_begin + s) * NB * xs, stage_bytes, &x_full[s]);
             }
         }
         const int k_steps_f = WITH_F ? (a.dim + 3) / 4 : 0;
@@ -237,8 +246,8 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
             if (APPLY) {              // issued before the barrier waits: independent of the staged X block
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                    cwv[m] = *reinterpret_cast<const double2*>(cw_row[m] + rb * NB);
-                    if (MODE == 4) hv[m] = *reinterpret_cast<const double2*>(h_row[m] + rb * NB);
+                    cwv[m] = *reinterpret_cast<const double2*>(cw_row[m] + (size_t)(rb_begin + rb) * NB);
+                    if (MODE == 4) hv[m] = *reinterpret_cast<const double2*>(h_row[m] + (size_t)(rb_begin + rb) * NB);
                 }
             }
             // refill the stage freed two blocks ago (the G-warps have released it: see v_empty below)
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
                 const int nb = rb + ST - 2, ns = nb % ST;
                 mbar_wait(&x_empty[ns], (uint32_t)(((nb / ST) - 1) & 1));
                 mbar_expect_tx(&x_full[ns], stage_bytes);
-                tma_bulk_g2s(xs_ring + (size_t)ns * NB * xs, a.x + (size_t)nb * NB * xs, stage_bytes, &x_full[ns]);
+                tma_bulk_g2s(xs_ring + (size_t)ns * NB * xs, a.x + (size_t)(rb_begin + nb) * NB * xs, stage_bytes, &x_full[ns]);
             }
             mbar_wait(&x_full[stage], (uint32_t)((rb / ST) & 1));
             const double* xb = xs_ring + (size_t)stage * NB * xs;
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
                         bool ovf = fv > 709.782712893384;
                         rr[j] = ovf ? __longlong_as_double(0x7ff8000000000000LL) : t - p;
                         cc[j] = WITH_C ? vv[j] * (om - p) : 0.0;
-                        int row = rb * NB + r_local + j;
+                        int row = (rb_begin + rb) * NB + r_local + j;
                         if (row < a.n_rows) {
                             double l1pe = ovf ? __longlong_as_double(0x7ff0000000000000LL) : fmax(fv, 0.0) + fast_log1p_01(ev[i], log_tab);
                             ll_acc[m] += t * fv - l1pe;
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
                     int c = chain0 + m_local;
                     if (c < a.n_chains) {
                         const size_t slot = a.cw_cur ? (size_t)(a.cw_cur[c] ^ a.cw_flip) * a.cw_slot : 0;
-                        *reinterpret_cast<double2*>(a.cbuf + slot + (size_t)c * a.n_rows_pad + rb * NB + r_local) =
+                        *reinterpret_cast<double2*>(a.cbuf + slot + (size_t)c * a.n_rows_pad + (size_t)(rb_begin + rb) * NB + r_local) =
                             make_double2(cc[0], cc[1]);
                     }
                 }
@@ -503,6 +512,15 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
             }
         }
     }
+}
+
+// out[i] = sum over splits z (in order) of part[z * stride + i]
+__global__ void k_reduce_splits(const double* __restrict__ part, size_t stride, int n_splits, double* __restrict__ out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = part[i];
+    for (int z = 1; z < n_splits; ++z) s += part[(size_t)z * stride + i];
+    out[i] = s;
 }
 #endif  // __CUDACC__
 

@@ -358,6 +358,19 @@ def test_main_py_harness_runs_headless(pkg, tmp_path):
     assert out_h["results_beta"].shape == (3, 150, 6) and out_h["accept_rate"] > 0.3
 
 
+@pytest.mark.parametrize("dim,n_rows", [(15, 40_000), (40, 12_000)])
+def test_few_chains_many_rows_row_split_builds_match_oracle(pkg, dim, n_rows):
+    """BASELINE.json configs[4] regime (64 chains, millions of rows): the builds split the rows over gridDim.z and add the
+    partial sums in split order; checked against the oracle on a size it still finishes in seconds."""
+    xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 4300 + dim)
+    n_iter, burn, c = 4, 1, 3
+    tapes = [bo.make_tape(n_iter, dim, 9400 + i) for i in range(c)]
+    ref, infos = bo.rmhmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=3, step_size=0.1, n_fixed=4)
+    out, _, info = pkg.rmhmc_batched(xx, t, c, n_iter, burn, 3, 0.1, 4, draws=bo.stack_tapes(tapes))
+    assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
+    assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
+
+
 # ---- BASELINE.json configs[2] at full size (N = 100 000, D = 100): the oracle's D separate N x D x D partials are too
 # slow for a unit test there, so the CUDA seams are checked against plain torch FP64 on the same GPU and through
 # size-independent properties (the two partials modes agree; H at the start equals its definition).
