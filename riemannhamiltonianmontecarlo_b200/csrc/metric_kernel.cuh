@@ -21,7 +21,8 @@ namespace rmhmc {
 constexpr int kMetricChains = 32;    // chains per CTA
 constexpr int kMetricRows = 32;      // design-matrix rows per staged block
 constexpr int kMetricGWarps = 8;     // warps accumulating G (and X^T r).  16 (four per SM sub-partition, 3 tiles each, 96 registers) was
-                                     // measured slower twice (1.99 vs 1.78 ms per German-shaped build: spills + more A-fragment traffic)
+                                     // measured slower twice (1.99 vs 1.78 ms per German-shaped build: spills + more A-fragment traffic); 12 (4 tiles
+                                     // each, 128 registers): 1.98 ms.  Fewer, larger per-warp tiles win: A fragments are reused 5x
 constexpr int kMetricFWarps = 4;     // warps producing f = X theta and the logistic terms one block ahead
 constexpr int kMetricThreads = (kMetricGWarps + kMetricFWarps) * 32;
 constexpr int kMetricStages = 4;     // X ring depth
