@@ -42,8 +42,21 @@ WORKLOADS = {
                "RMHMC L=6 eps=0.5 F=6", 65536, 50),
     "australian": ("australian", "Australian-credit-shaped synthetic logistic regression N=690 D=15 (seed 1235), "
                    "RMHMC L=6 eps=0.5 F=6", 4096, 400),
+    # BASELINE.json configs[2]; a round takes ~0.46 s, so a step is 2 rounds (use --steps 8); the CPU arm is omitted
+    # (one reference iteration at this size takes ~20 s)
+    "cfg3": ("synthetic:100000:100:1236", "synthetic logistic regression N=100000 D=100 (seed 1236), RMHMC L=6 eps=0.5 F=6",
+             1024, 2),
 }
 N_LEAPFROG, STEP_SIZE, N_FIXED = 6, 0.5, 6
+
+
+def load_data(key):
+    """(XX, t) of a workload: a named shape or ``synthetic:N:D:seed`` (SURVEY.md 8d generator)."""
+    from riemannhamiltonianmontecarlo_b200 import datasets
+    if key.startswith("synthetic:"):
+        _, n, d, seed = key.split(":")
+        return datasets.synthetic_logistic(int(n), int(d), int(seed))
+    return datasets.shaped(key)
 METRIC = "min_ess_per_sec"
 UNIT = "ESS/s"
 
@@ -74,8 +87,7 @@ def _ref_worker(args):
     os.environ["OMP_NUM_THREADS"] = "1"
     import numpy as np
     from oracle import blr_oracle as bo
-    from riemannhamiltonianmontecarlo_b200 import datasets
-    xx, t = datasets.shaped(shape)
+    xx, t = load_data(shape)
     d = xx.shape[1]
     tape_w = bo.make_tape(max(warm_iters, 1), d, 50_000 + idx)
     _, info = bo.rmhmc_chain(xx, t, tape_w, n_iter=max(warm_iters, 1), burn_in=0, n_leapfrog=N_LEAPFROG,
@@ -231,7 +243,7 @@ def gpu_main(args):
     C = args.chains or c_default
     R = args.rounds_per_step or r_default
     K, W = args.steps, args.warmup
-    xx, t = r.datasets.shaped(shape)
+    xx, t = load_data(shape)
     N, D = xx.shape
     P2, P3 = D * (D + 1) // 2, D * (D + 1) * (D + 2) // 6
 
@@ -403,12 +415,13 @@ def gpu_main(args):
         kernels[name] = {"launches": n, "ms_total": ms, "ms_avg": ms / max(n, 1), "share_of_step": ms / wall_ms}
         if name in alg_flops and n:
             kernels[name]["tflops_alg"] = alg_flops[name] / (ms / n * 1e-3) / 1e12
+    NP = (N + 31) // 32 * 32
     if args.partials == "tensor":
         ws_note = "per-round working set (T slots + cbuf, %.1f GB) exceeds the 126 MB L2" % (
-            (2 * C * (P3 + 8) * 8 + C * 1024 * 8) / 1e9)
+            (2 * C * (P3 + 8) * 8 + C * NP * 8) / 1e9)
     else:
         ws_note = "per-round working set (c_n slots + leverages + G^-1/L per chain, %.1f GB) exceeds the 126 MB L2" % (
-            (3 * C * 1024 * 8 + 4 * C * D * D * 8) / 1e9)
+            (3 * C * NP * 8 + 4 * C * D * D * 8) / 1e9)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": seconds / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -432,7 +445,10 @@ def gpu_main(args):
         "clocks": clock_info,
         "e2e": e2e,
     }
-    if not args.no_cpu_baseline and world == 1:
+    if args.workload == "cfg3":
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                "sample": "omitted: one iteration of the reference at N=1e5, D=100 takes ~20 s"}
+    elif not args.no_cpu_baseline and world == 1:
         cb = run_cpu_arm(shape, 1, 1, args.cpu_baseline_iters // 2, 1)
         line["cpu_baseline"] = {"value": cb["min_ess_per_sec"], "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": cb["sample"], "leapfrog_steps_per_sec": cb["leapfrog_per_sec"],
