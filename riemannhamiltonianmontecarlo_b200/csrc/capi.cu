@@ -73,6 +73,8 @@ struct rmhmc_handle {
     double* x_pad = nullptr;
     double* kr3 = nullptr;          // [Np][P3p] KR3(X), only when it fits kKr3Budget (else formed on the fly)
     double* kr2t = nullptr;         // [P2k][Np] KR2(X)^T: B operand of the leverage GEMM (matrix-free partials)
+    double* kr2n = nullptr;         // [Np][P2p] KR2(X): B operand of the plain-GEMM metric build (32 < D only)
+    bool suppress_brackets = false; // a caller's Bracket spans several launches
     int p2k = 0;                    // P2 padded to the GEMM's K tile
     bool matrix_free = false;       // partials mode of the engine (rmhmc_set_partials_mode)
     uchar2* pair_tab = nullptr;
@@ -93,6 +95,7 @@ struct rmhmc_handle {
     int64_t launches = 0;
     bool profiling = false;
     bool fuse_epilogues = false;
+    bool metric_gemm = true;        // 32 < D: position-iterate metric builds as v-kernel + plain GEMM (RMHMC_METRIC_GEMM=0: fused kernel)
     int fuse_momentum = 1;          // implicit momentum half-step: 1 all iterates in one k_pass launch, 2 k_mom_fp, 0 unfused
     // row-sharded mode: this handle holds the rows of shard `shard_rank`; every build is all-reduced
     ncclComm_t comm = nullptr;
@@ -306,15 +309,16 @@ struct Bracket {
     rmhmc_handle* h;
     int kind;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    Bracket(rmhmc_handle* h_, int kind_) : h(h_), kind(kind_) {
-        if (h->profiling) {
+    bool on;
+    Bracket(rmhmc_handle* h_, int kind_) : h(h_), kind(kind_), on(h_->profiling && !h_->suppress_brackets) {
+        if (on) {
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
             cudaEventRecord(e0, h->stream);
         }
     }
     ~Bracket() {
-        if (h->profiling) {
+        if (on) {
             cudaEventRecord(e1, h->stream);
             h->prof[kind].ev.emplace_back(e0, e1);
         }
@@ -353,7 +357,7 @@ template <int MODE>
 int launch_metric(rmhmc_handle* h, const MetricArgs& a_in, const FuseArgs& fz = FuseArgs{}) {
     MetricArgs a = a_in;
     size_t smem = metric_smem_bytes(h->xs, h->p2p, fz.mode != kFuseNone);
-    dim3 grid(blocks_for(a.n_chains, kMetricChains), MODE >= 2 ? (unsigned)((h->dim + 31) / 32) : (unsigned)h->col_ctas);
+    dim3 grid(blocks_for(a.n_chains, kMetricChains), MODE == 5 ? 1u : (MODE >= 2 ? (unsigned)((h->dim + 31) / 32) : (unsigned)h->col_ctas));
     // Few chains and very many rows (BASELINE.json configs[4]: 64 chains, 1.25 M rows per GPU): the chain / column tiles
     // alone leave most SMs idle, so the rows are split over gridDim.z and the partial sums added in split order.
     const int n_blocks_all = h->n_rows_pad / kMetricRows;
@@ -387,12 +391,12 @@ int launch_metric(rmhmc_handle* h, const MetricArgs& a_in, const FuseArgs& fz = 
     }
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
-        Bracket b(h, MODE == 0 ? 0 : (MODE == 3 ? 5 : (MODE == 4 ? 7 : 1)));
+        Bracket b(h, MODE == 0 || MODE == 5 ? 0 : (MODE == 3 ? 5 : (MODE == 4 ? 7 : 1)));
         kern<<<grid, kMetricThreads, smem, h->stream>>>(a, fz);
         if (splits > 1) {
             if (MODE <= 1 && a_in.g_out) k_reduce_splits<<<blocks_for(cg, 256), 256, 0, h->stream>>>(a.g_out, cg, splits, a_in.g_out, cg);
             if (MODE >= 1 && a_in.grad_out) k_reduce_splits<<<blocks_for(cd, 256), 256, 0, h->stream>>>(a.grad_out, cd, splits, a_in.grad_out, cd);
-            if ((MODE == 1 || MODE == 2) && a_in.loglik_out) k_reduce_splits<<<blocks_for(cl, 256), 256, 0, h->stream>>>(a.loglik_out, cl, splits, a_in.loglik_out, cl);
+            if ((MODE == 1 || MODE == 2 || MODE == 6) && a_in.loglik_out) k_reduce_splits<<<blocks_for(cl, 256), 256, 0, h->stream>>>(a.loglik_out, cl, splits, a_in.loglik_out, cl);
             h->launches += 3;
         }
     }
@@ -783,6 +787,65 @@ int mf_closing_passes(rmhmc_handle* h, int init) {
     return rc;
 }
 
+// diagonal pairs of the packed metric += 1/alpha (the plain-GEMM build has no epilogue for it)
+__global__ void k_add_prior_diag(double* __restrict__ gp, int64_t C, int D, int p2p, double alpha_inv) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= C * D) return;
+    int64_t c = i / D;
+    int a = (int)(i - c * D);
+    gp[c * p2p + pair_index(a, a, D)] += alpha_inv;
+}
+// Metric of a position fixed-point iterate, G(theta_w) -> g_tmp.  32 < D with enough chain x column tiles to fill the GPU:
+// v -> hbuf (k_metric<5>), then the TMA-fed DMMA GEMM G = V . KR2(X) (k_tbuild_pre) -- the column CTAs of the fused
+// kernel would each recompute f and v (14x at D = 100).  Otherwise the fused kernel.
+bool use_metric_gemm(const rmhmc_handle* h) {
+    return h->metric_gemm && is_big(h) && h->kr2n && h->matrix_free &&
+           blocks_for(h->n_chains, kTbChains) * ((h->p2p + kTbCols - 1) / kTbCols) >= 148;
+}
+// g_tmp = hbuf . KR2(X) + I/alpha (no brackets of its own)
+int launch_metric_gemm(rmhmc_handle* h) {
+    ChainArrays& S = h->S;
+    const int64_t C = h->n_chains;
+    TBuildArgs t{};
+    t.kr3 = h->kr2n; t.cbuf = S.hbuf; t.tpack = S.g_tmp; t.cur = S.cur; t.flip = 0; t.slot_stride = 0;
+    t.n_chains = (int)C; t.n_rows_pad = h->n_rows_pad; t.p3 = h->p2; t.p3p = h->p2p;
+    dim3 grid((unsigned)((h->p2p + kTbCols - 1) / kTbCols), blocks_for(C, kTbChains));
+    size_t smem = tbuild_pre_smem_bytes();
+    CUDA_TRY(h, cudaFuncSetAttribute(k_tbuild_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tbuild_pre<<<grid, kTbThreads, smem, h->stream>>>(t);
+    k_add_prior_diag<<<blocks_for(C * h->dim, 256), 256, 0, h->stream>>>(S.g_tmp, C, h->dim, h->p2p,
+                                                                          h->shard_rank == 0 ? 1.0 / h->alpha : 0.0);
+    h->launches += 2;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+int build_metric_iterate(rmhmc_handle* h) {
+    ChainArrays& S = h->S;
+    const int64_t C = h->n_chains;
+    if (!use_metric_gemm(h)) return launch_metric<0>(h, metric_args(h, C, S.theta_w, S.g_tmp, nullptr, nullptr, nullptr));
+    Bracket b(h, 0);
+    h->suppress_brackets = true;
+    MetricArgs a = metric_args(h, C, S.theta_w, nullptr, nullptr, nullptr, nullptr);
+    a.vout = S.hbuf;
+    int rc = launch_metric<5>(h, a);
+    if (!rc) rc = launch_metric_gemm(h);
+    h->suppress_brackets = false;
+    return rc;
+}
+// closing build of a leapfrog step (G, X^T (t - p), log-likelihood, c_n), same split for 32 < D
+int build_metric_closing(rmhmc_handle* h, int flip) {
+    if (!use_metric_gemm(h)) return launch_metric<1>(h, closing_args(h, flip));
+    Bracket b(h, 1);
+    h->suppress_brackets = true;
+    MetricArgs a = closing_args(h, flip);
+    a.g_out = nullptr;
+    a.vout = h->S.hbuf;
+    int rc = launch_metric<6>(h, a);
+    if (!rc) rc = launch_metric_gemm(h);
+    h->suppress_brackets = false;
+    return rc;
+}
+
 // The builds of one RMHMC round (rmhmc.py:113-156 for every chain): F-1 position iterates, each a
 // metric build + per-chain solve, then the closing metric build, the partials build and the
 // per-chain factorisation of the new metric.  The
@@ -798,7 +861,7 @@ int rmhmc_round_builds(rmhmc_handle* h) {
     for (int fi = 2; fi <= h->P.n_fixed; ++fi) {
         const int last = fi == h->P.n_fixed ? 1 : 0;
         MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, nullptr, nullptr, nullptr);
-        int rc = fuse ? launch_metric<0>(h, a, fuse_args(h, kFuseSolve, last, 0)) : launch_metric<0>(h, a);
+        int rc = fuse ? launch_metric<0>(h, a, fuse_args(h, kFuseSolve, last, 0)) : build_metric_iterate(h);
         if (rc) return rc;
         if (!fuse) {
             rc = reduce_build<0>(h);            // row-sharded: one exchange per fixed-point iterate
@@ -807,8 +870,7 @@ int rmhmc_round_builds(rmhmc_handle* h) {
             if (rc) return rc;
         }
     }
-    MetricArgs a = closing_args(h, 1);
-    int rc = fuse ? launch_metric<1>(h, a, fuse_args(h, kFuseFactor, 0, 0)) : launch_metric<1>(h, a);
+    int rc = fuse ? launch_metric<1>(h, closing_args(h, 1), fuse_args(h, kFuseFactor, 0, 0)) : build_metric_closing(h, 1);
     if (rc) return rc;
     rc = reduce_build<1>(h);
     if (rc) return rc;
@@ -875,7 +937,7 @@ int launch_mmala_turn(rmhmc_handle* h, int do_back, int do_front, int init) {
 }
 // metric quantities at theta_w into the proposal (flip = 1) / current (flip = 0) slot's inputs
 int mmala_builds(rmhmc_handle* h, int flip) {
-    int rc = launch_metric<1>(h, closing_args(h, flip));
+    int rc = build_metric_closing(h, flip);
     if (!rc) rc = reduce_build<1>(h);
     if (!rc) rc = launch_factor(h, flip ? 0 : 1);
     if (!rc && !h->mmala_simplified) {
@@ -1057,11 +1119,21 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
             CREATE_TRY(cudaGetLastError());
             h->matrix_free = true;
         }
+        // 32 < D: KR2(X) itself (rows x pairs) for the plain-GEMM metric build
+        size_t bytes_n = (size_t)h->n_rows_pad * h->p2p * 8;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (dim > kMaxDimWarp && h->kr2t && bytes_n <= kKr2Budget && bytes_n < free_b / 3) {
+            CREATE_TRY(cudaMalloc((void**)&h->kr2n, bytes_n));
+            long long n = (long long)h->n_rows_pad * h->p2p;
+            k_form_kr2n<<<blocks_for(n, 256), 256>>>(h->x_pad, h->pair_tab, h->kr2n, h->n_rows_pad, h->xs, h->p2, h->p2p);
+            CREATE_TRY(cudaGetLastError());
+        }
     }
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
     h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
-    if (const char* e = std::getenv("RMHMC_FUSE_MOMENTUM")) h->fuse_momentum = std::atoi(e);      // A/B switch for profiling
+    if (const char* e = std::getenv("RMHMC_FUSE_MOMENTUM")) h->fuse_momentum = std::atoi(e);
+    if (const char* e = std::getenv("RMHMC_METRIC_GEMM")) h->metric_gemm = std::atoi(e) != 0;      // A/B switch for profiling
     h->P.it_stop = 0; h->P.burn_in = 0; h->P.sample_cap = 0;
     *out = h;
     return RMHMC_OK;
@@ -1073,7 +1145,7 @@ void rmhmc_destroy(rmhmc_handle* h) {
     drain_profile(h);
     free_chains(h);
     if (h->comm) nccl_api().CommDestroy(h->comm);
-    cudaFree(h->split_buf); cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->kr2t); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
+    cudaFree(h->split_buf); cudaFree(h->kr2n); cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->kr2t); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
     cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
     delete h;
 }
@@ -1092,6 +1164,11 @@ int rmhmc_update_data(rmhmc_handle* h, const double* xx_dev, const double* t_dev
     if (h->kr2t) {
         long long n = (long long)h->n_rows_pad * h->p2k;
         k_form_kr2t<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->x_pad, h->pair_tab, h->kr2t, h->n_rows_pad, h->xs, h->p2, h->p2k);
+        h->launches += 1;
+    }
+    if (h->kr2n) {
+        long long n = (long long)h->n_rows_pad * h->p2p;
+        k_form_kr2n<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->x_pad, h->pair_tab, h->kr2n, h->n_rows_pad, h->xs, h->p2, h->p2p);
         h->launches += 1;
     }
     CUDA_TRY(h, cudaGetLastError());
@@ -1247,7 +1324,7 @@ static int chains_init_common(rmhmc_handle* h, int64_t C, const double* theta0, 
     } else {
         rc = set_chain_smem_attrs(h);
         if (rc) return rc;
-        rc = launch_metric<1>(h, closing_args(h, 0));
+        rc = build_metric_closing(h, 0);
         if (rc) return rc;
         rc = reduce_build<1>(h);
         if (rc) return rc;

@@ -42,6 +42,7 @@ struct MetricArgs {
     size_t cw_slot;           // doubles between the two c_n slots
     const int* aslot;         // [C] or null
     const double* hbuf;       // [Cpad][Np] leverages (MODE 4)
+    double* vout;             // [Cpad][Np] v_n = p_n (1 - p_n) (MODE 5)
     int n_chains, n_rows, n_rows_pad, dim, xs, p2, p2p;
     int extra_tile;           // n-tile split over the chain tiles of G-warps 0..3, or -1
     // row splitting (gridDim.z > 1: few chains, very many rows): split z handles a contiguous range of row blocks and
@@ -160,6 +161,9 @@ __device__ __forceinline__ double fast_log1p_01(double e, const double* __restri
 //         (LastTerm of rmhmc.py:105-107 / :159-161 without the 0.5)
 // MODE 4: traces           out[c][d] = sum_n c_n h_n x_nd = tr(G^-1 dG_d), h = a.hbuf  (rmhmc.py:76-77,155-156)
 // Both reuse the gradient contraction R . X of the closing build with a different R.
+// MODE 5: v only, written to a.vout: the A operand of the plain-GEMM metric build G = V . KR2(X) used for 32 < D (one
+//         CTA cannot hold all packed columns there, and the column CTAs of MODE 0 would each recompute f and v).
+// MODE 6: the closing build without G: MODE 2 (gradient, log-likelihood) + c_n + v -> a.vout, again followed by the GEMM.
 //
 // Warp-specialised: 4 F-warps (one 8-row tile each, all 32 chains) compute f^T = Theta X^T on the
 // tensor cores, the logistic terms, and publish V (and R) for row block rb+1 while the 8 G-warps
@@ -171,8 +175,9 @@ __device__ __forceinline__ double fast_log1p_01(double e, const double* __restri
 // so that all four SM sub-partitions issue the same number of DMMAs.
 template <int NT, int MODE>
 __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(MetricArgs a, FuseArgs fz) {
-    constexpr bool CLOSING = MODE == 1 || MODE == 2, WITH_G = MODE <= 1, WITH_C = MODE == 1;
-    constexpr bool APPLY = MODE >= 3, WITH_R = MODE >= 1, WITH_F = MODE != 4;
+    constexpr bool CLOSING = MODE == 1 || MODE == 2 || MODE == 6, WITH_G = MODE <= 1, WITH_C = MODE == 1 || MODE == 6;
+    constexpr bool APPLY = MODE == 3 || MODE == 4, WITH_R = (MODE >= 1 && MODE <= 4) || MODE == 6, WITH_F = MODE != 4;
+    constexpr bool VOUT = MODE == 5 || MODE == 6;
     constexpr int MC = kMetricChains, NB = kMetricRows, VS = kMetricVS, ST = kMetricStages;
     constexpr int GW = kMetricGWarps, FW = kMetricFWarps;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -324,6 +329,9 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
                 }
                 const int m_local = m * 8 + g;
                 if (WITH_G) *reinterpret_cast<double2*>(vdst + (size_t)m_local * VS + r_local) = make_double2(vv[0], vv[1]);
+                if (VOUT && blockIdx.y == 0 && chain0 + m_local < a.n_chains)
+                    *reinterpret_cast<double2*>(a.vout + (size_t)(chain0 + m_local) * a.n_rows_pad + (size_t)(rb_begin + rb) * NB + r_local) =
+                        make_double2(vv[0], vv[1]);
                 if (WITH_R) *reinterpret_cast<double2*>(rdst + (size_t)m_local * VS + r_local) = make_double2(rr[0], rr[1]);
                 if (WITH_C && blockIdx.y == 0) {
                     int c = chain0 + m_local;

@@ -180,6 +180,21 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_tbuild(TBuildArgs a) {
 // ---- small problems: KR3(X) (N x P3 doubles; 23 MB for the German-shaped data) is formed once when the
 // data set is bound and stays L2-resident, so the partials build is a plain TMA-fed DMMA GEMM
 // T = Cw . KR3 with no FP64 multiplies competing for the tensor pipe.
+// KR2(X)[n, (a,b)] = x_na x_nb, [Np][P2p] row-major: B operand of the plain-GEMM metric build (32 < D)
+__global__ void k_form_kr2n(const double* __restrict__ x, const uchar2* __restrict__ pair_tab, double* __restrict__ kr2,
+                            long long n_rows_pad, int xs, int p2, int p2p) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_rows_pad * p2p) return;
+    long long r = i / p2p;
+    int col = (int)(i - r * p2p);
+    double v = 0.0;
+    if (col < p2) {
+        uchar2 ab = pair_tab[col];
+        v = x[r * xs + ab.x] * x[r * xs + ab.y];
+    }
+    kr2[i] = v;
+}
+
 __global__ void k_form_kr3(const double* __restrict__ x, const uchar4* __restrict__ tri_tab, double* __restrict__ kr3,
                            long long n_rows_pad, int xs, int p3p) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
