@@ -872,7 +872,7 @@ k_chain_turn(EngineParams P, ChainArrays S, int do_back, int do_front, int init)
 // ---------------------------------------------------------------- position fixed-point iterate (x (F-1))
 // solve G(theta_w) u = p, theta_w <- theta + s eps/2 (u0 + u)   (rmhmc.py:116-122)
 template <int N>
-__global__ void __launch_bounds__(32) k_chain_solve(EngineParams P, ChainArrays S, int is_last) {
+__global__ void __launch_bounds__(32, 16) k_chain_solve(EngineParams P, ChainArrays S, int is_last) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = blockIdx.x, lane = threadIdx.x, D = P.dim;
     if (c >= P.n_chains) return;
