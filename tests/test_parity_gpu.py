@@ -393,6 +393,24 @@ def test_large_dim_plain_gemm_metric_build_agrees_with_fused_kernel(pkg, monkeyp
     assert rel_err(res["1"][:2, 1:], ref[:, 1:]) < RTOL
 
 
+@pytest.mark.parametrize("partials", PARTIALS)
+@pytest.mark.parametrize("n_fixed", [0, 1, 2])
+def test_degenerate_fixed_point_counts_and_empty_trajectories(pkg, n_fixed, partials):
+    """NumOfNewtonSteps = 0 / 1 / 2 (no fixed-point iterates at all; the first position iterate is the last one and gets
+    the position clamp; the shortest fused momentum loop) and RandomStep = 0 (``rand()`` returning exactly 0: the
+    proposal is the current state, rmhmc.py:89,96) follow the reference as well."""
+    xx, t = pkg.datasets.shaped("australian")
+    d = xx.shape[1]
+    n_iter, burn = 6, 1
+    tapes = [bo.make_tape(n_iter, d, 9800 + i) for i in range(3)]
+    tapes[1].u_step[2] = 0.0
+    ref, infos = bo.rmhmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=4, step_size=0.3, n_fixed=n_fixed)
+    out, _, info = pkg.rmhmc_batched(xx, t, 3, n_iter, burn, 4, 0.3, n_fixed, draws=bo.stack_tapes(tapes), partials=partials)
+    assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
+    assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
+    assert np.array_equal(info["leapfrogs"], [i["steps"].sum() for i in infos])
+
+
 # ---- BASELINE.json configs[2] at full size (N = 100 000, D = 100): the oracle's D separate N x D x D partials are too
 # slow for a unit test there, so the CUDA seams are checked against plain torch FP64 on the same GPU and through
 # size-independent properties (the two partials modes agree; H at the start equals its definition).
