@@ -202,6 +202,12 @@ int blr_ess_ragged(int device, void* cuda_stream, const double* samples, int64_t
                    int64_t max_samples, int dim, int64_t chain_stride, int64_t row_stride,
                    const int64_t* starts, const int64_t* counts, double* ess);
 
+/* Gelman-Rubin Rhat per parameter over n_chains >= 2 chains of n_samples >= 2 samples (same layout as above); rhat (dim).
+ * Not in the reference (its main.py:70-79 only reports ESS); SURVEY.md 8c: classic estimator, W = mean of the chain
+ * variances (ddof 1), B/S = variance of the chain means (ddof 1), Rhat = sqrt(((S-1)/S W + B/S) / W). */
+int blr_rhat(int device, void* cuda_stream, const double* samples, int64_t n_chains, int64_t n_samples,
+             int dim, int64_t chain_stride, int64_t row_stride, double* rhat);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,7 @@ SIGNATURES = {
     "mmala_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     "blr_ess_batched": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p]),
     "blr_autocorr": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "blr_rhat": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p]),
     "blr_ess_ragged": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 

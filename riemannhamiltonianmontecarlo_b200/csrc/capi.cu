@@ -1578,6 +1578,15 @@ int blr_autocorr(int device, void* cuda_stream, const double* series, int64_t n_
     return cudaGetLastError() == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
 }
 
+int blr_rhat(int device, void* cuda_stream, const double* samples, int64_t n_chains, int64_t n_samples, int dim,
+             int64_t chain_stride, int64_t row_stride, double* rhat) {
+    if (!samples || !rhat || n_chains < 2 || n_samples < 2 || dim <= 0) return RMHMC_E_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return RMHMC_E_CUDA;
+    k_rhat<<<(unsigned)dim, kEssThreads, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+        samples, (size_t)chain_stride, (size_t)row_stride, (int)n_chains, (int)n_samples, rhat);
+    return cudaGetLastError() == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
+}
+
 int blr_ess_ragged(int device, void* cuda_stream, const double* samples, int64_t n_chains, int64_t max_samples,
                    int dim, int64_t chain_stride, int64_t row_stride, const int64_t* starts, const int64_t* counts,
                    double* ess) {

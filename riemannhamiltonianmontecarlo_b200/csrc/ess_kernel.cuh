@@ -118,6 +118,34 @@ __global__ void k_acf_lag0(double* acf, int n_lag, int n_series) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < n_series) acf[(size_t)s * (n_lag + 1)] = acf[(size_t)s * (n_lag + 1)] / acf[(size_t)s * (n_lag + 1)];
 }
+// Gelman-Rubin potential scale reduction per parameter over C chains of S samples (not part of the reference;
+// SURVEY.md 8c specifies the classic estimator: W = mean_c var_c (ddof = 1), B/S = var_c(mean_c) (ddof = 1),
+// Rhat = sqrt(((S-1)/S W + B/S) / W)).  One CTA per parameter; thread i takes chains i, i + 128, ...; sums in fixed order.
+__global__ void __launch_bounds__(kEssThreads) k_rhat(const double* __restrict__ samples, size_t chain_stride, size_t row_stride,
+                                                       int C, int S, double* __restrict__ rhat_out) {
+    __shared__ double sm[3][kEssThreads];
+    const int d = blockIdx.x, tid = threadIdx.x;
+    double s_mean = 0.0, s_mean2 = 0.0, s_var = 0.0;
+    for (int c = tid; c < C; c += kEssThreads) {
+        const double* y = samples + (size_t)c * chain_stride + d;
+        double m = 0.0;
+        for (int t = 0; t < S; ++t) m += y[(size_t)t * row_stride];
+        m /= S;
+        double v = 0.0;
+        for (int t = 0; t < S; ++t) { double e = y[(size_t)t * row_stride] - m; v += e * e; }
+        v /= (S - 1);
+        s_mean += m; s_mean2 += m * m; s_var += v;
+    }
+    sm[0][tid] = s_mean; sm[1][tid] = s_mean2; sm[2][tid] = s_var;
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0, w = 0.0;
+        for (int i = 0; i < kEssThreads; ++i) { a += sm[0][i]; b += sm[1][i]; w += sm[2][i]; }
+        w /= C;
+        const double b_over_s = (b - a * a / C) / (C - 1);
+        rhat_out[d] = sqrt(((double)(S - 1) / S * w + b_over_s) / w);
+    }
+}
 #endif
 
 }  // namespace rmhmc

@@ -359,6 +359,23 @@ def ess_batched(samples, max_lag: int | None = None):
     return out
 
 
+def rhat_batched(samples):
+    """Gelman-Rubin Rhat per parameter of a device or host array (C, S, D) -> device tensor (D,)."""
+    torch = _capi.require_cuda()
+    lib = _capi.load()
+    if isinstance(samples, np.ndarray):
+        samples = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)).cuda()
+    assert samples.dim() == 3 and samples.dtype == torch.float64 and samples.stride(2) == 1
+    c, s, d = samples.shape
+    out = torch.empty(d, dtype=torch.float64, device=samples.device)
+    stream = torch.cuda.current_stream(samples.device).cuda_stream
+    rc = lib.blr_rhat(samples.device.index or 0, c_void_p(stream), _ptr(samples), c, s, d, samples.stride(0), samples.stride(1),
+                      _ptr(out))
+    if rc != 0:
+        raise _capi.RmhmcError(f"blr_rhat failed (code {rc})")
+    return out
+
+
 def ess_ragged(samples, starts, counts):
     """ESS per (chain, parameter) over per-chain row windows of a device array (C, S, D).
 

@@ -411,6 +411,17 @@ def test_degenerate_fixed_point_counts_and_empty_trajectories(pkg, n_fixed, part
     assert np.array_equal(info["leapfrogs"], [i["steps"].sum() for i in infos])
 
 
+def test_rhat_matches_oracle(pkg):
+    rng = np.random.default_rng(8)
+    chains = rng.normal(0, 1, (300, 40, 7)) + rng.normal(0, 0.3, (300, 1, 7)) * np.arange(7)      # growing between-chain spread
+    got = pkg.rhat_batched(chains).cpu().numpy()
+    assert rel_err(got, bo.rhat(chains)) < 1e-12
+    view = np.ascontiguousarray(np.concatenate([chains, chains], axis=1))[:, 5:45]                  # strided window
+    import torch
+    t = torch.from_numpy(np.concatenate([chains, chains], axis=1)).cuda()[:, 5:45]
+    assert rel_err(pkg.rhat_batched(t).cpu().numpy(), bo.rhat(view)) < 1e-12
+
+
 # ---- BASELINE.json configs[2] at full size (N = 100 000, D = 100): the oracle's D separate N x D x D partials are too
 # slow for a unit test there, so the CUDA seams are checked against plain torch FP64 on the same GPU and through
 # size-independent properties (the two partials modes agree; H at the start equals its definition).
