@@ -422,6 +422,49 @@ def test_rhat_matches_oracle(pkg):
     assert rel_err(pkg.rhat_batched(t).cpu().numpy(), bo.rhat(view)) < 1e-12
 
 
+def test_update_data_rebinds_every_derived_array(pkg):
+    """rmhmc_update_data (what the e2e bench arm does every step): X, t and the derived KR2(X)^T / KR3(X) follow."""
+    import torch
+    xa, ta = pkg.datasets.synthetic_logistic(400, 12, 71)
+    xb, tb = pkg.datasets.synthetic_logistic(400, 12, 72)
+    n_iter, burn, c = 4, 1, 3
+    tapes = [bo.make_tape(n_iter, 12, 9600 + i) for i in range(c)]
+    st = bo.stack_tapes(tapes)
+    ref, infos = bo.rmhmc_chains(xb, tb, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=3, step_size=0.3, n_fixed=4)
+    for mode in PARTIALS:
+        data = pkg.LogisticData(xa, ta, partials=mode)
+        data.update(torch.from_numpy(xb).cuda(), torch.from_numpy(tb.reshape(-1)).cuda())
+        s = pkg.RMHMCSampler(data, c, 3, 0.3, 4)
+        s.set_tape(st["z"], st["u_step"], st["z_dir"], st["u_acc"])
+        s.set_samples(n_iter - burn, burn)
+        s.run(n_iter)
+        out = s.samples.cpu().numpy()
+        _, tr = data.metric_partials(np.full((1, 12), 0.05))
+        data.close()
+        assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
+        _, p, v, g = bo.fisher_metric(xb, np.full((12, 1), 0.05))
+        assert rel_err(tr[0], bo.metric_partials(xb, p, v, np.linalg.inv(g))[1][:, 0]) < 1e-10
+
+
+def test_partials_mode_can_be_switched_on_a_live_handle(pkg, golden):
+    fx = golden("rmhmc_australian_shaped")
+    data = pkg.LogisticData(fx["xx"], fx["t"])
+    assert data.partials_mode == "matrix_free"
+    outs = {}
+    for mode in ("tensor", "matrix_free", "tensor"):
+        data.set_partials_mode(mode)
+        assert data.partials_mode == mode
+        s = pkg.RMHMCSampler(data, 2, int(fx["n_leapfrog"]), float(fx["step_size"]), int(fx["n_fixed"]))
+        s.set_tape(fx["z"][:, :2], fx["u_step"][:, :2], fx["z_dir"][:, :2], fx["u_acc"][:, :2])
+        s.set_samples(int(fx["n_iter"]) - int(fx["burn_in"]), int(fx["burn_in"]))
+        s.run(int(fx["n_iter"]))
+        outs.setdefault(mode, []).append(s.samples.cpu().numpy())
+    data.close()
+    assert np.array_equal(outs["tensor"][0], outs["tensor"][1])            # bit-reproducible across re-initialisation
+    assert rel_err(outs["tensor"][0][:, 1:], fx["samples"][:2, 1:]) < RTOL
+    assert rel_err(outs["matrix_free"][0][:, 1:], fx["samples"][:2, 1:]) < RTOL
+
+
 # ---- BASELINE.json configs[2] at full size (N = 100 000, D = 100): the oracle's D separate N x D x D partials are too
 # slow for a unit test there, so the CUDA seams are checked against plain torch FP64 on the same GPU and through
 # size-independent properties (the two partials modes agree; H at the start equals its definition).
