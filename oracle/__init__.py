@@ -11,4 +11,5 @@ against the unmodified reference (``/root/reference/code/{rmhmc,hmc,tools}.py``)
 run under a host-supplied RNG tape (:mod:`oracle.ref_live`); the resulting vectors
 are committed under ``tests/golden/`` by ``tests/golden/make_golden.py``.  The
 reference ships no tests or golden vectors of its own.
+Exception: ``mmala_chain`` ports MATLAB-only code (BLR_mMALA.m) that cannot be run here -- parity unpinned.
 """

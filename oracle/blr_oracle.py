@@ -15,6 +15,8 @@ What it restates (reference = /root/reference/code, cited as file:line):
 * ``rmhmc_chain``                        rmhmc.py:37-191 (one chain, whole loop)
 * ``hmc_chain``                          hmc.py:38-89
 * ``rhat``                               not in the reference (classic Gelman-Rubin; own spec)
+* ``mmala_chain``                        MATLAB only: authors_code/Bayes_Log_Reg/MCMC/BLR_mMALA.m:159-330,
+                                         BLR_mMALA_Simp.m:170-290 -- PARITY UNPINNED (no MATLAB/Octave here)
 
 Unlike the reference, randomness is an explicit argument (a :class:`DrawTape`) so
 that the oracle, the live reference (``oracle/ref_live.py`` monkeypatches
