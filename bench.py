@@ -427,7 +427,10 @@ def gpu_main(args):
         "ms_per_step": seconds / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": descr, "chains_per_gpu": C, "chains_total": C * world, "rounds_per_step": R,
-                   "rng": "philox4x32-10 on device", "partials": args.partials, "l2": ws_note},
+                   "rng": "philox4x32-10 on device", "partials": args.partials, "l2": ws_note,
+                   "baseline_config": {"german": "BASELINE.json configs[3] at this GPU count (the shape the north_star target is "
+                                                 "quoted on; configs[0] is the same shape with 1 chain on the CPU)",
+                                       "australian": "BASELINE.json configs[1]", "cfg3": "BASELINE.json configs[2]"}[args.workload]},
         "leapfrog_steps_per_sec": leapfrogs / seconds,
         "iterations_per_sec": iters_done / seconds,
         "samples_in_timed_region": n_samples, "accept_rate": accept, "renorm_events": renorm,
