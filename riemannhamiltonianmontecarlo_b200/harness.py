@@ -17,6 +17,7 @@ import numpy as np
 
 from . import datasets
 from .hmc import hmc_batched
+from .mmala import mmala_batched
 from .rmhmc import rmhmc_batched
 from .tools import CalculateESS
 
@@ -34,12 +35,16 @@ def run_experiments(XX, t, sampler="rmhmc", n_experiments=10, NumOfIterations=60
     elif sampler == "hmc":
         samples, seconds, info = hmc_batched(XX, t, n_experiments, NumOfIterations, BurnIn, seed=seed, device=device,
                                              **sampler_kwargs)
+    elif sampler in ("mmala", "mmala_simp"):                 # the MATLAB originals' samplers (BLR_mMALA.m, BLR_mMALA_Simp.m)
+        samples, seconds, info = mmala_batched(XX, t, n_experiments, NumOfIterations, BurnIn, Simplified=sampler == "mmala_simp",
+                                               seed=seed, device=device, **sampler_kwargs)
     else:
-        raise ValueError("sampler must be 'rmhmc' or 'hmc'")
+        raise ValueError("sampler must be 'rmhmc', 'hmc', 'mmala' or 'mmala_simp'")
+    first = 0 if sampler.startswith("mmala") else 1          # RMHMC / HMC never write row 0 (rmhmc.py:190, hmc.py:83)
     results_beta = samples                                   # (n_experiments, NumOfIterations-BurnIn, D), main.py:46
     avg_beta_posterior = results_beta.mean(axis=0)           # main.py:54
     ess = CalculateESS(avg_beta_posterior, avg_beta_posterior.shape[0] - 1)      # main.py:71
-    per_chain = np.stack([CalculateESS(results_beta[i, 1:], results_beta.shape[1] - 2)[:, 0]
+    per_chain = np.stack([CalculateESS(results_beta[i, first:], results_beta.shape[1] - 1 - first)[:, 0]
                           for i in range(n_experiments)])
     out = {
         "results_beta": results_beta, "avg_beta_posterior": avg_beta_posterior, "avg_time_taken": seconds,
@@ -62,7 +67,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("csv")
     ap.add_argument("--relabel-12", action="store_true", help="labels {1,2} -> {0,1} (heart, german)")
-    ap.add_argument("--sampler", default="rmhmc", choices=["rmhmc", "hmc"])
+    ap.add_argument("--sampler", default="rmhmc", choices=["rmhmc", "hmc", "mmala", "mmala_simp"])
     ap.add_argument("--experiments", type=int, default=10)
     ap.add_argument("--iterations", type=int, default=6000)
     ap.add_argument("--burn-in", type=int, default=1000)

@@ -356,6 +356,9 @@ def test_main_py_harness_runs_headless(pkg, tmp_path):
     out_h = harness.run_experiments(XX, t, "hmc", n_experiments=3, NumOfIterations=200, BurnIn=50, verbose=False,
                                     StepSize=0.1, NumOfLeapFrogSteps=30)
     assert out_h["results_beta"].shape == (3, 150, 6) and out_h["accept_rate"] > 0.3
+    out_m = harness.run_experiments(XX, t, "mmala", n_experiments=4, NumOfIterations=400, BurnIn=100, verbose=False)
+    assert out_m["results_beta"].shape == (4, 300, 6) and 0.3 < out_m["accept_rate"] < 0.95 and out_m["Min"] > 5
+    assert np.abs(out_m["results_beta"].mean(axis=(0, 1)) - out["results_beta"][:, 1:].mean(axis=(0, 1))).max() < 0.15
 
 
 @pytest.mark.parametrize("dim,n_rows", [(15, 40_000), (40, 12_000)])
