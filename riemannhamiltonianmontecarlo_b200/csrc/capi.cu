@@ -380,14 +380,18 @@ int launch_metric(rmhmc_handle* h, const MetricArgs& a_in, const FuseArgs& fz = 
     if (fz.mode != kFuseNone && grid.y != 1) return fail(h, RMHMC_E_UNSUPPORTED, "fused epilogues need a single column CTA");
     void (*kern)(MetricArgs, FuseArgs) = nullptr;
     int nt = MODE >= 2 ? 1 : h->nt;
-    switch (nt) {
-        case 1: kern = k_metric<1, MODE>; break;
-        case 2: kern = k_metric<2, MODE>; break;
-        case 3: kern = k_metric<3, MODE>; break;
-        case 4: kern = k_metric<4, MODE>; break;
-        case 5: kern = k_metric<5, MODE>; break;
-        case 6: kern = k_metric<6, MODE>; break;
-        default: return fail(h, RMHMC_E_UNSUPPORTED, "metric kernel: dim too large");
+    if constexpr (MODE >= 2) {
+        kern = k_metric<1, MODE>;            // no G accumulators: one instantiation
+    } else {
+        switch (nt) {
+            case 1: kern = k_metric<1, MODE>; break;
+            case 2: kern = k_metric<2, MODE>; break;
+            case 3: kern = k_metric<3, MODE>; break;
+            case 4: kern = k_metric<4, MODE>; break;
+            case 5: kern = k_metric<5, MODE>; break;
+            case 6: kern = k_metric<6, MODE>; break;
+            default: return fail(h, RMHMC_E_UNSUPPORTED, "metric kernel: dim too large");
+        }
     }
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
