@@ -2,7 +2,9 @@
 // (D <= 32).  Everything that is O(D^3) per chain lives here: Cholesky / inverse / log-det of G,
 // tr(G^-1 dG_d), the quadratic forms of the implicit momentum update, the position solves, the
 // Hamiltonian and the Metropolis accept.  The O(N D^2) and O(N D^3) contractions over the data are
-// the two tensor-core kernels (metric_kernel.cuh, tbuild_kernel.cuh).
+// the tensor-core kernels (metric_kernel.cuh, tbuild_kernel.cuh, pass_kernel.cuh).  k_chain_turn and the
+// tensor contractions below belong to the TENSOR partials mode; the MATRIX_FREE mode (default) uses
+// mf_kernels.cuh for the per-chain halves and shares k_chain_factor / k_chain_solve.
 //
 // Chains run asynchronously: every "round" advances each chain by one leapfrog step of whatever
 // trajectory it is on (rmhmc.py:96-163); a chain that finishes its trajectory does its accept/reject

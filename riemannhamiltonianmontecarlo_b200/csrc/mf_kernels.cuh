@@ -6,14 +6,17 @@
 //   p^T G^-1 dG_d G^-1 p         = sum_n c_n x_nd (x_n . u)^2,  u = G^-1 p      (rmhmc.py:105-107,159-161)
 // Both right-hand sides are passes over the data with O(N D^2) resp. O(N D) work per chain instead of
 // the O(N D^3) of the tensor build, so in this mode the tensor T is never formed:
-//   leverages  h = KR2(X) . q, q = packed G^-1 (off-diagonals doubled): one DMMA GEMM per leapfrog step
-//   k_metric<MODE 4>   tr_d   = sum_n c_n h_n x_nd
-//   k_metric<MODE 3>   quad_d = sum_n c_n (x_n . u)^2 x_nd         (F + 1 times per leapfrog step)
+//   leverages  h = KR2(X) . q, q = packed G^-1 (off-diagonals doubled): one DMMA GEMM per leapfrog step (k_tbuild_pre)
+//   trace pass tr_d   = sum_n c_n h_n x_nd
+//   quad pass  quad_d = sum_n c_n (x_n . u)^2 x_nd         (F + 1 times per leapfrog step)
+// (pass kernels: pass_kernel.cuh for D <= 32, k_metric<MODE 3/4> for 32 < D <= 128).
 // What is left per chain is O(D^2): the mat-vecs with G^-1 and L, the fixed-point updates, the
 // Hamiltonian and the accept -- the kernels below, one thread per parameter, NTHR = 32 (D <= 32, one
 // warp per chain) or 128 (D <= 128).  Round schedule (capi.cu: rmhmc_rounds):
-//   k_mf_turn(front) | F x { quad pass, k_mf_mom_iter } | (F-1) x { metric, solve } | closing metric |
-//   factor (+ q, u) | leverage GEMM | trace pass | quad pass | k_mf_turn(back + front) | ...
+//   k_mf_turn(front) | momentum fixed point | (F-1) x { metric, solve } | closing metric |
+//   factor (+ q, u) | leverage GEMM | trace + quad pass | k_mf_turn(back + front) | ...
+// where the momentum fixed point is ONE launch (k_pass<MOMFP> / k_mom_fp: F x { quad pass, update }) unless the data
+// are row-sharded, F <= 1 or D > 32: then F x { quad pass, [all-reduce,] k_mf_mom_iter }.
 #pragma once
 #include "chain_kernels.cuh"
 #include "common.cuh"
