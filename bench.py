@@ -256,7 +256,13 @@ def gpu_main(args):
     data = r.LogisticData(xx, t, device=device, partials=args.partials)
     sampler = r.RMHMCSampler(data, C, N_LEAPFROG, STEP_SIZE, N_FIXED)
     sampler.set_philox(20261018, chain_offset=rank * C)
-    total_rounds = (W + K * (1 if args.no_e2e else 2)) * R
+    # the sample store holds every iteration of the run: bound it (ESS kernel: <= 24000 rows; HBM) by shortening the
+    # step when many steps are requested
+    passes = W + K * (1 if args.no_e2e else 2)
+    max_rows = 6000
+    if passes * R / 3.5 * 1.12 + 96 > max_rows:
+        R = max(1, int((max_rows - 96) * 3.5 / 1.12 / passes))
+    total_rounds = passes * R
     cap = int(total_rounds / 3.5 * 1.12) + 96           # E[RandomStep] = 3.5 rounds per iteration
     samples = sampler.set_samples(cap, 0)                # row it = state after iteration it
 
