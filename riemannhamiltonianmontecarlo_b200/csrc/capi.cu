@@ -95,6 +95,7 @@ struct rmhmc_handle {
     int64_t launches = 0;
     bool profiling = false;
     bool fuse_epilogues = false;
+    bool gemm_split_k = true;       // plain-GEMM metric build: split K against wave quantisation (RMHMC_GEMM_SPLITK=0 disables)
     bool metric_gemm = true;        // 32 < D: position-iterate metric builds as v-kernel + plain GEMM (RMHMC_METRIC_GEMM=0: fused kernel)
     int fuse_momentum = 1;          // implicit momentum half-step: 1 all iterates in one k_pass launch, 2 k_mom_fp, 0 unfused
     // row-sharded mode: this handle holds the rows of shard `shard_rank`; every build is all-reduced
@@ -814,9 +815,36 @@ int launch_metric_gemm(rmhmc_handle* h) {
     t.kr3 = h->kr2n; t.cbuf = S.hbuf; t.tpack = S.g_tmp; t.cur = S.cur; t.flip = 0; t.slot_stride = 0;
     t.n_chains = (int)C; t.n_rows_pad = h->n_rows_pad; t.p3 = h->p2; t.p3p = h->p2p;
     dim3 grid((unsigned)((h->p2p + kTbCols - 1) / kTbCols), blocks_for(C, kTbChains));
+    // wave quantisation: a few hundred tiles on 148 SMs (cfg3: 320 = 2.16 waves) waste up to a third of the last wave;
+    // split K so that the tail is at most ~5 % (partial products added in split order)
+    const int tiles = (int)(grid.x * grid.y);
+    int splits = 1;
+    if (h->gemm_split_k) {
+        double best = 1e30;
+        for (int s = 1; s <= 4 && (h->n_rows_pad / kTbRows) / s >= 64; ++s) {
+            const double waves = (double)tiles * s / 148.0, cost = std::ceil(waves) / s;      // time in units of a full tile
+            if (cost < best * 0.97) { best = cost; splits = s; }
+        }
+    }
+    const size_t cg = (size_t)C * h->p2p;
+    if (splits > 1) {
+        const size_t need = (size_t)splits * cg;
+        if (need > h->split_cap) {
+            if (h->split_buf) CUDA_TRY(h, cudaFree(h->split_buf));
+            h->split_buf = nullptr; h->split_cap = 0;
+            CUDA_TRY(h, cudaMalloc((void**)&h->split_buf, need * 8));
+            h->split_cap = need;
+        }
+        t.tpack = h->split_buf; t.split_stride = cg;
+        grid.z = (unsigned)splits;
+    }
     size_t smem = tbuild_pre_smem_bytes();
     CUDA_TRY(h, cudaFuncSetAttribute(k_tbuild_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_tbuild_pre<<<grid, kTbThreads, smem, h->stream>>>(t);
+    if (splits > 1) {
+        k_reduce_splits<<<blocks_for(cg, 256), 256, 0, h->stream>>>(h->split_buf, cg, splits, S.g_tmp, cg);
+        h->launches += 1;
+    }
     k_add_prior_diag<<<blocks_for(C * h->dim, 256), 256, 0, h->stream>>>(S.g_tmp, C, h->dim, h->p2p,
                                                                           h->shard_rank == 0 ? 1.0 / h->alpha : 0.0);
     h->launches += 2;
@@ -1137,7 +1165,8 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
 #undef CREATE_TRY
     h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
     if (const char* e = std::getenv("RMHMC_FUSE_MOMENTUM")) h->fuse_momentum = std::atoi(e);
-    if (const char* e = std::getenv("RMHMC_METRIC_GEMM")) h->metric_gemm = std::atoi(e) != 0;      // A/B switch for profiling
+    if (const char* e = std::getenv("RMHMC_METRIC_GEMM")) h->metric_gemm = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RMHMC_GEMM_SPLITK")) h->gemm_split_k = std::atoi(e) != 0;      // A/B switch for profiling
     h->P.it_stop = 0; h->P.burn_in = 0; h->P.sample_cap = 0;
     *out = h;
     return RMHMC_OK;

@@ -38,6 +38,9 @@ struct TBuildArgs {
     int flip;                 // write to slot cur ^ flip
     size_t slot_stride;       // doubles between the two T slots
     int n_chains, n_rows_pad, xs, p3, p3p;
+    // k_tbuild_pre only: gridDim.z > 1 splits K (the rows) over z; split z writes its PARTIAL product at
+    // tpack + z * split_stride (no slot addressing), to be added in split order by k_reduce_splits
+    size_t split_stride;
 };
 
 __host__ inline size_t tbuild_smem_bytes(int xs, int stages) {
@@ -221,7 +224,9 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_tbuild_pre(TBuildArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int chain0 = blockIdx.y * MC;
     if (chain0 >= a.n_chains) return;
-    const int n_blocks = a.n_rows_pad / KB;
+    const int n_blocks_all = a.n_rows_pad / KB;
+    const int rb_begin = (int)((long long)n_blocks_all * blockIdx.z / gridDim.z);
+    const int n_blocks = (int)((long long)n_blocks_all * (blockIdx.z + 1) / gridDim.z) - rb_begin;       // this split's K blocks
     const int colbase = blockIdx.x * kTbCols;
     const int ncols = min(kTbCols, a.p3p - colbase);                     // multiple of 8
     const uint32_t stage_bytes = (uint32_t)(MC * KB * 8 + KB * ncols * 8);
@@ -239,11 +244,11 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_tbuild_pre(TBuildArgs a) {
         if (lane < MC / NW) {
             const int m = warp * (MC / NW) + lane;
             tma_bulk_g2s(a_ring + ((size_t)stage * MC + m) * AS,
-                         a.cbuf + (size_t)(chain0 + m) * a.n_rows_pad + (size_t)rb * KB, (uint32_t)(KB * 8), &full[stage]);
+                         a.cbuf + (size_t)(chain0 + m) * a.n_rows_pad + (size_t)(rb_begin + rb) * KB, (uint32_t)(KB * 8), &full[stage]);
         } else if (lane < MC / NW + KB / NW) {
             const int r = warp * (KB / NW) + (lane - MC / NW);
             tma_bulk_g2s(k_ring + ((size_t)stage * KB + r) * KS,
-                         a.kr3 + (size_t)(rb * KB + r) * a.p3p + colbase, (uint32_t)(ncols * 8), &full[stage]);
+                         a.kr3 + (size_t)((rb_begin + rb) * KB + r) * a.p3p + colbase, (uint32_t)(ncols * 8), &full[stage]);
         }
     };
     for (int s = 0; s < ST - 1 && s < n_blocks; ++s) issue(s);
@@ -286,7 +291,8 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_tbuild_pre(TBuildArgs a) {
     for (int m = 0; m < 4; ++m) {
         int c = chain0 + wm * 32 + m * 8 + g;
         if (c >= a.n_chains) continue;
-        double* out = a.tpack + (size_t)(a.cur[c] ^ a.flip) * a.slot_stride + (size_t)c * a.p3p;
+        double* out = gridDim.z > 1 ? a.tpack + blockIdx.z * a.split_stride + (size_t)c * a.p3p
+                                    : a.tpack + (size_t)(a.cur[c] ^ a.flip) * a.slot_stride + (size_t)c * a.p3p;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             int col = col0 + nt * 8 + 2 * q;

@@ -378,7 +378,7 @@ def test_large_dim_plain_gemm_metric_build_agrees_with_fused_kernel(pkg, monkeyp
     """32 < D with many chains: the position-iterate metric builds run as v-kernel + TMA-fed DMMA GEMM (G = V . KR2(X));
     the same Philox run through the fused kernel (RMHMC_METRIC_GEMM=0) must give the same chains, and a few of them
     are checked against the oracle."""
-    dim, n_rows, c = 40, 500, 3072
+    dim, n_rows, c = 40, 4200, 3072          # 168 GEMM tiles on 148 SMs and 132 K blocks: the split-K variant is taken
     xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 4400)
     n_iter, burn = 3, 0
     tapes = [bo.make_tape(n_iter, dim, 9500 + i) for i in range(2)]
