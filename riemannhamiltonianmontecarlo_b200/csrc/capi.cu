@@ -358,7 +358,7 @@ template <int MODE>
 int launch_metric(rmhmc_handle* h, const MetricArgs& a_in, const FuseArgs& fz = FuseArgs{}) {
     MetricArgs a = a_in;
     size_t smem = metric_smem_bytes(h->xs, h->p2p, fz.mode != kFuseNone);
-    dim3 grid(blocks_for(a.n_chains, kMetricChains), MODE == 5 ? 1u : (MODE >= 2 ? (unsigned)((h->dim + 31) / 32) : (unsigned)h->col_ctas));
+    dim3 grid(blocks_for(a.n_chains, kMetricChains), MODE >= 2 ? 1u : (unsigned)h->col_ctas);
     // Few chains and very many rows (BASELINE.json configs[4]: 64 chains, 1.25 M rows per GPU): the chain / column tiles
     // alone leave most SMs idle, so the rows are split over gridDim.z and the partial sums added in split order.
     const int n_blocks_all = h->n_rows_pad / kMetricRows;

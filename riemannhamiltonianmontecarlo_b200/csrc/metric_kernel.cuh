@@ -384,7 +384,11 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
             for (int m = 0; m < 4; ++m) acc[j][m][0] = acc[j][m][1] = 0.0;
         double eacc[2] = {0.0, 0.0};
         // closing: gradient tiles (chain tile mt, parameter tile dt) = flattened index gw, gw + GW, ...
-        constexpr int GT = 16 / GW;
+        // MODE 0/1: blockIdx.y (the column CTA) owns 4 parameter tiles = 16 (chain, parameter) tiles, 2 per G-warp.
+        // The modes without G run ONE CTA per chain tile (f / v are formed once, not once per parameter-tile group):
+        // up to 16 parameter tiles (D <= 128) = 64 tiles, 8 per G-warp.
+        constexpr int GT = MODE <= 1 ? 16 / GW : 64 / GW;
+        const int dt_base = MODE <= 1 ? 4 * blockIdx.y : 0;
         const int d_tiles = (a.dim + 7) / 8;
         double gacc[GT][2];
 #pragma unroll
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
 #pragma unroll
                     for (int h = 0; h < GT; ++h) {
                         int tix = gw + h * GW;
-                        int mt = tix & 3, dt = (tix >> 2) + 4 * blockIdx.y;
+                        int mt = tix & 3, dt = (tix >> 2) + dt_base;
                         if (dt < d_tiles) {
                             double ar = rs[(size_t)(mt * 8 + g) * VS + ks * 4 + q];
                             int dcol = dt * 8 + g;
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(kMetricThreads, MODE >= 2 ? 2 : 1) k_metric(Me
 #pragma unroll
             for (int h = 0; h < GT; ++h) {
                 int tix = gw + h * GW;
-                int mt = tix & 3, dt = (tix >> 2) + 4 * blockIdx.y;
+                int mt = tix & 3, dt = (tix >> 2) + dt_base;
                 int c = chain0 + mt * 8 + g;
                 if (dt < d_tiles && c < a.n_chains) {
                     int dcol = dt * 8 + 2 * q;
