@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--rounds-per-step", type=int, default=0)
     ap.add_argument("--partials", default="matrix_free", choices=["matrix_free", "tensor"],
                     help="how the engine evaluates the metric partials (include/rmhmc_b200.h)")
+    ap.add_argument("--metric", default=None, choices=["dmma", "i8"],
+                    help="metric build: FP64 DMMA kernel or INT8-slice tcgen05 build (default: the library's)")
     ap.add_argument("--ref-iters-per-step", type=int, default=30)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -253,7 +255,7 @@ def gpu_main(args):
     xx_dev = torch.empty_like(xx_host, device=device)
     t_dev = torch.empty_like(t_host, device=device)
 
-    data = r.LogisticData(xx, t, device=device, partials=args.partials)
+    data = r.LogisticData(xx, t, device=device, partials=args.partials, metric=args.metric)
     sampler = r.RMHMCSampler(data, C, N_LEAPFROG, STEP_SIZE, N_FIXED)
     sampler.set_philox(20261018, chain_offset=rank * C)
     # the sample store holds every iteration of the run: bound it (ESS kernel: <= 24000 rows; HBM) by shortening the

@@ -61,6 +61,24 @@ const char* rmhmc_last_error(const rmhmc_handle* h);
 enum { RMHMC_PARTIALS_TENSOR = 0, RMHMC_PARTIALS_MATRIX_FREE = 1 };
 int rmhmc_set_partials_mode(rmhmc_handle* h, int mode);
 int rmhmc_get_partials_mode(const rmhmc_handle* h);
+/* How the engine contracts the Fisher metric G = X^T diag(v) X + I/alpha of every chain (rmhmc.py:51-57,
+ * :116-119, :134-137; the position fixed-point iterates and the closing build of a leapfrog step):
+ *   FP64_DMMA      fused FP64 kernel on the legacy tensor path (mma.sync DMMA.8x8x4), summation in FP64;
+ *   INT8_TCGEN05   Blackwell tensor cores: v and KR2(X) are split into 5 (RMHMC_I8_SLICES=6: 6) balanced base-256
+ *                  digits, the digit products accumulate EXACTLY in int32 TMEM accumulators (tcgen05.mma.kind::i8,
+ *                  operands staged by tensor-map TMA) and are recombined in int64 / FP64.  Same G up to the digit
+ *                  truncation (max relative error 1-5e-12 with 5 digits, 1e-14 with 6); gradient, log-likelihood and
+ *                  c_n are evaluated in FP64 as before.  dim <= 32 and at most 16384 rows per rank.
+ * Frees the handle's chains (call before *_chains_init).  The seam rmhmc_metric follows the mode. */
+enum { RMHMC_METRIC_FP64_DMMA = 0, RMHMC_METRIC_INT8_TCGEN05 = 1 };
+int rmhmc_set_metric_mode(rmhmc_handle* h, int mode);
+int rmhmc_get_metric_mode(const rmhmc_handle* h);
+/* Several stages have two kernel variants chosen by the chain count (few chains: variants that fill the SMs with
+ * smaller tiles / row splits; many chains: the throughput variants the benchmark runs).  AUTO picks by count; SMALL /
+ * LARGE pin the choice, e.g. to run the benchmark's kernels on a test-sized batch.  A chain's trajectory is
+ * bit-reproducible within one regime; across regimes it differs by summation order (~1e-15). */
+enum { RMHMC_REGIME_AUTO = 0, RMHMC_REGIME_SMALL = 1, RMHMC_REGIME_LARGE = 2 };
+int rmhmc_set_launch_regime(rmhmc_handle* h, int regime);
 /* Row-sharded data (very large N): every rank binds ITS rows with rmhmc_create and runs ALL chains;
  * each metric / partials build then ends in one NCCL all-reduce (sum) of the partial
  * G | X^T(t-p) | log-likelihood block resp. of T, after which the per-chain stages run replicated

@@ -23,6 +23,9 @@ SIGNATURES = {
     "rmhmc_update_data": (c_int, [c_void_p, c_void_p, c_void_p]),
     "rmhmc_set_partials_mode": (c_int, [c_void_p, c_int]),
     "rmhmc_get_partials_mode": (c_int, [c_void_p]),
+    "rmhmc_set_metric_mode": (c_int, [c_void_p, c_int]),
+    "rmhmc_get_metric_mode": (c_int, [c_void_p]),
+    "rmhmc_set_launch_regime": (c_int, [c_void_p, c_int]),
     "rmhmc_comm_unique_id": (c_int, [c_char_p]),
     "rmhmc_comm_init": (c_int, [c_void_p, c_int, c_int, c_char_p]),
     "rmhmc_set_stream": (c_int, [c_void_p, c_void_p]),

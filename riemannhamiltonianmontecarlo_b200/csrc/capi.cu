@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "ess_kernel.cuh"
 #include "hmc_kernels.cuh"
+#include "i8_metric.cuh"
 #include "metric_kernel.cuh"
 #include "mf_kernels.cuh"
 #include "momfp_kernel.cuh"
@@ -105,6 +106,20 @@ struct rmhmc_handle {
     double* split_buf = nullptr;    // partial outputs of row-split metric builds / passes
     size_t split_cap = 0;
     ProfSlot prof[8];
+    // INT8-slice metric build on tcgen05 (i8_metric.cuh): digit planes of KR2(X)^T per data set, of V per chain set
+    int metric_mode = RMHMC_METRIC_FP64_DMMA;
+    int i8_slices = 5;              // digits per operand (RMHMC_I8_SLICES = 5 | 6)
+    bool i8_ok = false;             // B planes formed (dim <= 32, rows <= kI8MaxRows, tensor-map encoder available)
+    signed char* b8 = nullptr;      // [S][b_rows][kp]
+    double2* colinfo = nullptr;     // [b_rows]
+    double* colmax = nullptr;       // [P2p]
+    int i8_kp = 0, i8_b_rows = 0;
+    CUtensorMap map_b;
+    signed char* a8 = nullptr;      // [S][c_pad][kp] (with the chains)
+    CUtensorMap map_a;
+    // kernel-variant selection that depends on the chain count (few chains: SM-filling variants); tests pin it
+    int launch_regime = RMHMC_REGIME_AUTO;
+    int64_t tape_base = 0, tape_window = 0;      // iterations covered by the host tape (rng_mode 0)
     mutable std::string err;
 };
 
@@ -123,6 +138,15 @@ int fail(rmhmc_handle* h, int code, const std::string& msg) {
     h->err = msg;
     return code;
 }
+
+// true: take the kernel variants meant for batches that do not fill the GPU with the throughput tiles
+// (rmhmc_set_launch_regime pins the choice)
+bool few_chains(const rmhmc_handle* h, int64_t threshold) {
+    if (h->launch_regime == RMHMC_REGIME_SMALL) return true;
+    if (h->launch_regime == RMHMC_REGIME_LARGE) return false;
+    return h->n_chains < threshold;
+}
+bool use_i8(const rmhmc_handle* h) { return h->metric_mode == RMHMC_METRIC_INT8_TCGEN05 && h->i8_ok; }
 
 // ------------------------------------------------------------------ small layout kernels
 __global__ void k_pad_design(const double* __restrict__ xx, const double* __restrict__ t, double* __restrict__ xp,
@@ -363,7 +387,7 @@ int launch_metric(rmhmc_handle* h, const MetricArgs& a_in, const FuseArgs& fz = 
     // alone leave most SMs idle, so the rows are split over gridDim.z and the partial sums added in split order.
     const int n_blocks_all = h->n_rows_pad / kMetricRows;
     int splits = 1;
-    if (fz.mode == kFuseNone && grid.x * grid.y < 74) splits = std::max(1, std::min((int)(296 / (grid.x * grid.y)), n_blocks_all / 16));
+    if (fz.mode == kFuseNone && h->launch_regime != RMHMC_REGIME_LARGE && grid.x * grid.y < 74) splits = std::max(1, std::min((int)(296 / (grid.x * grid.y)), n_blocks_all / 16));
     const size_t cg = (size_t)a.n_chains * h->p2p, cd = (size_t)a.n_chains * h->dim, cl = (size_t)a.n_chains;
     if (splits > 1) {
         const size_t need = (size_t)splits * (cg + cd + cl);
@@ -496,6 +520,7 @@ void free_chains(rmhmc_handle* h) {
     h->chain_allocs.clear();
     h->S = ChainArrays{};
     h->t_tmp = nullptr;
+    h->a8 = nullptr;
     h->n_chains = 0;
 }
 
@@ -551,6 +576,14 @@ int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
         S.g_tmp = hmc ? nullptr : build;
         S.grad_tmp = build + g_len;
         S.loglik_tmp = S.grad_tmp + c * D;
+    }
+    h->a8 = nullptr;
+    if (!hmc && use_i8(h)) {
+        rc |= dev_alloc(h, &h->a8, (size_t)h->i8_slices * h->c_pad * h->i8_kp, tr);
+        if (!rc && !make_tensor_map_u8_k64(&h->map_a, h->a8, (uint64_t)h->i8_slices * h->c_pad, (uint64_t)h->i8_kp, kI8TileM)) {
+            free_chains(h);
+            return fail(h, RMHMC_E_CUDA, "cuTensorMapEncodeTiled failed for the V digit planes");
+        }
     }
     rc |= dev_alloc(h, &S.mom, c * D, tr);
     rc |= dev_alloc(h, &S.theta_w, c * D, tr);
@@ -737,10 +770,14 @@ int build_partials(rmhmc_handle* h, int flip) {
 template <int KIND>
 int launch_pass(rmhmc_handle* h) {
     // 64 chains per CTA; 16 when that grid would leave SMs idle (BASELINE.json configs[1]: 4096 chains)
-    const bool small = h->n_chains < (int64_t)148 * 2 * kPassWarps * 8;
+    // (the fused momentum fixed point has its own few-chains formulation, k_mom_fp: mf_momentum_fixed_point)
+    const bool small = KIND != kPassMomFp && few_chains(h, (int64_t)148 * 2 * kPassWarps * 8);
     const int warps = small ? kPassWarpsSmall : kPassWarps;
     const size_t smem = pass_smem_bytes(h->xs, warps);
-    auto kern = small ? k_pass<KIND, kPassWarpsSmall> : k_pass<KIND, kPassWarps>;
+    void (*kern)(EngineParams, ChainArrays, const double*, int) = k_pass<KIND, kPassWarps>;
+    if constexpr (KIND != kPassMomFp) {
+        if (small) kern = k_pass<KIND, kPassWarpsSmall>;
+    }
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         Bracket b(h, KIND == kPassTrace || KIND == kPassPair ? 7 : 5);
@@ -758,9 +795,9 @@ int mf_momentum_fixed_point(rmhmc_handle* h) {
     // (pass_kernel.cuh; 2.58 vs 3.02 ms at 65 536 German-shaped chains) or 12 cooperating warps per 32 chains
     // (momfp_kernel.cuh; shorter dependent chains, 0.08 vs 0.23 ms when 4096 chains leave most of the GPU idle)
     const bool fusable = !is_big(h) && !h->comm && h->P.n_fixed >= 2;
-    const bool few_chains = h->n_chains < (int64_t)148 * 2 * kPassWarps * 8;
-    if (fusable && (h->fuse_momentum == 1 && !few_chains)) return launch_pass<kPassMomFp>(h);
-    if (fusable && (h->fuse_momentum == 2 || (h->fuse_momentum == 1 && few_chains))) {
+    const bool few = few_chains(h, (int64_t)148 * 2 * kPassWarps * 8);
+    if (fusable && (h->fuse_momentum == 1 && !few)) return launch_pass<kPassMomFp>(h);
+    if (fusable && (h->fuse_momentum == 2 || (h->fuse_momentum == 1 && few))) {
         const size_t smem = momfp_smem_bytes(h->xs);
         CUDA_TRY(h, cudaFuncSetAttribute(k_mom_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
@@ -851,9 +888,76 @@ int launch_metric_gemm(rmhmc_handle* h) {
     CUDA_TRY(h, cudaGetLastError());
     return RMHMC_OK;
 }
+// ---- INT8-slice metric build on tcgen05 (i8_metric.cuh)
+template <int S>
+int i8_form_b_planes(rmhmc_handle* h, cudaStream_t st) {
+    k_i8_colmax<<<(unsigned)h->p2, 256, 0, st>>>(h->x_pad, h->pair_tab, h->colmax, h->n_rows_pad, h->xs);
+    const long long n = (long long)h->i8_b_rows * h->i8_kp;
+    k_i8_form_b<S><<<blocks_for(n, 256), 256, 0, st>>>(h->x_pad, h->pair_tab, h->colmax, h->b8, h->colinfo, h->n_rows_pad,
+                                                       h->xs, h->p2, h->i8_b_rows, h->i8_kp);
+    h->launches += 2;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+int i8_form_b(rmhmc_handle* h, cudaStream_t st) { return h->i8_slices == 6 ? i8_form_b_planes<6>(h, st) : i8_form_b_planes<5>(h, st); }
+
+// digit planes of KR2(X)^T + their tensor map; leaves i8_ok false when the shape is outside the kernel's range
+int i8_setup(rmhmc_handle* h) {
+    if (h->dim > kMaxDimWarp || h->n_rows_pad > kI8MaxRows || !tensor_map_encoder()) return RMHMC_OK;
+    const int S = h->i8_slices, nc = S == 6 ? I8Shape<6>::NC : I8Shape<5>::NC;
+    h->i8_kp = i8_kp(h->n_rows_pad);
+    h->i8_b_rows = (h->p2 + nc - 1) / nc * nc;
+    CUDA_TRY(h, cudaMalloc((void**)&h->b8, (size_t)S * h->i8_b_rows * h->i8_kp));
+    CUDA_TRY(h, cudaMalloc((void**)&h->colinfo, (size_t)h->i8_b_rows * sizeof(double2)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->colmax, (size_t)h->p2p * 8));
+    int rc = i8_form_b(h, h->stream);
+    if (rc) return rc;
+    if (!make_tensor_map_u8_k64(&h->map_b, h->b8, (uint64_t)S * h->i8_b_rows, (uint64_t)h->i8_kp, (uint32_t)nc))
+        return fail(h, RMHMC_E_CUDA, "cuTensorMapEncodeTiled failed for the KR2(X) digit planes");
+    h->i8_ok = true;
+    return RMHMC_OK;
+}
+
+struct I8Closing {              // outputs of the closing build besides G (null: position-iterate build)
+    double* grad_out; double* loglik_out; double* cbuf; const int* cw_cur; int cw_flip; size_t cw_slot;
+};
+template <int S>
+int i8_build_s(rmhmc_handle* h, int64_t C, const double* theta, signed char* a8, int64_t a_rows, const CUtensorMap& map_a,
+               double* g_out, const I8Closing* cl) {
+    I8VsArgs v{};
+    v.x = h->x_pad; v.theta = theta; v.a8 = a8; v.plane_stride = (size_t)a_rows * h->i8_kp; v.kp = h->i8_kp;
+    v.n_chains = (int)C; v.n_rows = (int)h->n_rows; v.n_rows_pad = h->n_rows_pad; v.dim = h->dim; v.xs = h->xs;
+    cudaError_t e;
+    if (cl) {
+        v.grad_out = cl->grad_out; v.loglik_out = cl->loglik_out; v.cbuf = cl->cbuf;
+        v.cw_cur = cl->cw_cur; v.cw_flip = cl->cw_flip; v.cw_slot = cl->cw_slot;
+        e = i8_launch_vslice<S, true>(v, h->stream);
+    } else {
+        e = i8_launch_vslice<S, false>(v, h->stream);
+    }
+    if (e != cudaSuccess) return fail(h, RMHMC_E_CUDA, std::string("k_i8_vslice: ") + cudaGetErrorString(e));
+    I8GemmArgs g{};
+    g.g_out = g_out; g.colinfo = h->colinfo; g.alpha_inv = h->shard_rank == 0 ? 1.0 / h->alpha : 0.0;
+    g.n_chains = (int)C; g.p2 = h->p2; g.p2p = h->p2p; g.k_blocks = h->i8_kp / kI8BlockK;
+    g.a_rows = (int)a_rows; g.b_rows = h->i8_b_rows; g.debug_class = -1;
+    e = i8_launch_gemm<S>(map_a, h->map_b, g, h->stream);
+    if (e != cudaSuccess) return fail(h, RMHMC_E_CUDA, std::string("k_i8_gemm: ") + cudaGetErrorString(e));
+    h->launches += 2;
+    return RMHMC_OK;
+}
+int i8_build(rmhmc_handle* h, int64_t C, const double* theta, signed char* a8, int64_t a_rows, const CUtensorMap& map_a,
+             double* g_out, const I8Closing* cl) {
+    return h->i8_slices == 6 ? i8_build_s<6>(h, C, theta, a8, a_rows, map_a, g_out, cl)
+                             : i8_build_s<5>(h, C, theta, a8, a_rows, map_a, g_out, cl);
+}
+
 int build_metric_iterate(rmhmc_handle* h) {
     ChainArrays& S = h->S;
     const int64_t C = h->n_chains;
+    if (use_i8(h)) {
+        Bracket b(h, 0);
+        return i8_build(h, C, S.theta_w, h->a8, h->c_pad, h->map_a, S.g_tmp, nullptr);
+    }
     if (!use_metric_gemm(h)) return launch_metric<0>(h, metric_args(h, C, S.theta_w, S.g_tmp, nullptr, nullptr, nullptr));
     Bracket b(h, 0);
     h->suppress_brackets = true;
@@ -866,6 +970,13 @@ int build_metric_iterate(rmhmc_handle* h) {
 }
 // closing build of a leapfrog step (G, X^T (t - p), log-likelihood, c_n), same split for 32 < D
 int build_metric_closing(rmhmc_handle* h, int flip) {
+    if (use_i8(h)) {
+        ChainArrays& S = h->S;
+        I8Closing cl{S.grad_tmp, S.loglik_tmp, h->matrix_free ? S.cw : S.cbuf, h->matrix_free ? S.cur : nullptr, flip,
+                     h->matrix_free ? h->P.slot_cw : 0};
+        Bracket b(h, 1);
+        return i8_build(h, h->n_chains, S.theta_w, h->a8, h->c_pad, h->map_a, S.g_tmp, &cl);
+    }
     if (!use_metric_gemm(h)) return launch_metric<1>(h, closing_args(h, flip));
     Bracket b(h, 1);
     h->suppress_brackets = true;
@@ -889,7 +1000,7 @@ int rmhmc_round_builds(rmhmc_handle* h) {
     // SLOWER on B200 (metric 1.78 -> 2.95 ms per launch vs 0.62 ms for the stand-alone solve kernel at
     // 65536 chains: 12 warps per SM of straight-line code are instruction-fetch bound while the tensor
     // pipe idles), so it is off by default and kept for small chain counts / experiments.
-    const bool fuse = h->fuse_epilogues && !h->comm && h->col_ctas == 1 && !h->matrix_free;
+    const bool fuse = h->fuse_epilogues && !h->comm && h->col_ctas == 1 && !h->matrix_free && !use_i8(h);
     for (int fi = 2; fi <= h->P.n_fixed; ++fi) {
         const int last = fi == h->P.n_fixed ? 1 : 0;
         MetricArgs a = metric_args(h, C, S.theta_w, S.g_tmp, nullptr, nullptr, nullptr);
@@ -993,6 +1104,17 @@ int run_until(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done, bool hmc, 
     if (h->n_chains <= 0 || h->is_hmc != hmc || h->is_mmala != mmala)
         return fail(h, RMHMC_E_STATE, "chains not initialised for this sampler");
     if (!h->configured || !h->rng_set) return fail(h, RMHMC_E_STATE, "configure and set a tape / philox seed first");
+    if (h->P.rng_mode == 0) {
+        // a host tape covers iterations [tape_base, tape_base + tape_window): never index outside it
+        if (it_stop > h->tape_base + h->tape_window)
+            return fail(h, RMHMC_E_INVALID, "it_stop lies beyond the iterations covered by the tape (set_tape window)");
+        long long behind = 0;
+        CUDA_TRY(h, cudaMemsetAsync(h->d_remaining, 0, sizeof(long long), h->stream));
+        k_remaining<<<64, 256, 0, h->stream>>>(h->S.iter, h->n_chains, h->tape_base, h->d_remaining);
+        CUDA_TRY(h, cudaMemcpyAsync(&behind, h->d_remaining, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (behind > 0) return fail(h, RMHMC_E_STATE, "a chain has completed fewer iterations than the tape's first iteration");
+    }
     h->P.it_stop = it_stop;
     int64_t total = 0;
     for (;;) {
@@ -1027,7 +1149,7 @@ int run_until(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done, bool hmc, 
 // ====================================================================== extern "C"
 extern "C" {
 
-const char* rmhmc_version(void) { return "rmhmc_b200 0.2 (sm_100a, fp64 dmma)"; }
+const char* rmhmc_version(void) { return "rmhmc_b200 0.3 (sm_100a: fp64 dmma + int8-slice tcgen05 metric build)"; }
 
 const char* rmhmc_last_error(const rmhmc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -1161,12 +1283,22 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
             CREATE_TRY(cudaGetLastError());
         }
     }
+    if (const char* e = std::getenv("RMHMC_I8_SLICES")) h->i8_slices = std::atoi(e) == 6 ? 6 : 5;
+    if (i8_setup(h) != RMHMC_OK) return bail(RMHMC_E_CUDA);
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
     h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
     if (const char* e = std::getenv("RMHMC_FUSE_MOMENTUM")) h->fuse_momentum = std::atoi(e);
     if (const char* e = std::getenv("RMHMC_METRIC_GEMM")) h->metric_gemm = std::atoi(e) != 0;
     if (const char* e = std::getenv("RMHMC_GEMM_SPLITK")) h->gemm_split_k = std::atoi(e) != 0;      // A/B switch for profiling
+    if (const char* e = std::getenv("RMHMC_METRIC_MODE")) {
+        if (std::string(e) == "i8" && h->i8_ok) h->metric_mode = RMHMC_METRIC_INT8_TCGEN05;
+        if (std::string(e) == "dmma") h->metric_mode = RMHMC_METRIC_FP64_DMMA;
+    }
+    if (const char* e = std::getenv("RMHMC_LAUNCH_REGIME")) {
+        const std::string r(e);
+        h->launch_regime = r == "small" ? RMHMC_REGIME_SMALL : (r == "large" ? RMHMC_REGIME_LARGE : RMHMC_REGIME_AUTO);
+    }
     h->P.it_stop = 0; h->P.burn_in = 0; h->P.sample_cap = 0;
     *out = h;
     return RMHMC_OK;
@@ -1178,7 +1310,7 @@ void rmhmc_destroy(rmhmc_handle* h) {
     drain_profile(h);
     free_chains(h);
     if (h->comm) nccl_api().CommDestroy(h->comm);
-    cudaFree(h->split_buf); cudaFree(h->kr2n); cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->kr2t); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
+    cudaFree(h->b8); cudaFree(h->colinfo); cudaFree(h->colmax); cudaFree(h->split_buf); cudaFree(h->kr2n); cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->kr2t); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
     cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
     delete h;
 }
@@ -1204,6 +1336,10 @@ int rmhmc_update_data(rmhmc_handle* h, const double* xx_dev, const double* t_dev
         k_form_kr2n<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->x_pad, h->pair_tab, h->kr2n, h->n_rows_pad, h->xs, h->p2, h->p2p);
         h->launches += 1;
     }
+    if (h->i8_ok) {
+        int rc = i8_form_b(h, h->stream);
+        if (rc) return rc;
+    }
     CUDA_TRY(h, cudaGetLastError());
     return RMHMC_OK;
 }
@@ -1220,6 +1356,22 @@ int rmhmc_set_partials_mode(rmhmc_handle* h, int mode) {
 int rmhmc_get_partials_mode(const rmhmc_handle* h) {
     if (!h) return RMHMC_E_INVALID;
     return h->matrix_free ? (int)RMHMC_PARTIALS_MATRIX_FREE : (int)RMHMC_PARTIALS_TENSOR;
+}
+
+int rmhmc_set_metric_mode(rmhmc_handle* h, int mode) {
+    if (!h || (mode != RMHMC_METRIC_FP64_DMMA && mode != RMHMC_METRIC_INT8_TCGEN05))
+        return h ? fail(h, RMHMC_E_INVALID, "rmhmc_set_metric_mode: bad arguments") : RMHMC_E_INVALID;
+    if (mode == RMHMC_METRIC_INT8_TCGEN05 && !h->i8_ok)
+        return fail(h, RMHMC_E_UNSUPPORTED, "rmhmc_set_metric_mode: the INT8 tcgen05 build needs dim <= 32 and at most 16384 rows");
+    if (h->n_chains > 0) free_chains(h);
+    h->metric_mode = mode;
+    return RMHMC_OK;
+}
+int rmhmc_get_metric_mode(const rmhmc_handle* h) { return h ? h->metric_mode : RMHMC_E_INVALID; }
+int rmhmc_set_launch_regime(rmhmc_handle* h, int regime) {
+    if (!h || regime < RMHMC_REGIME_AUTO || regime > RMHMC_REGIME_LARGE) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_set_launch_regime: bad arguments") : RMHMC_E_INVALID;
+    h->launch_regime = regime;
+    return RMHMC_OK;
 }
 
 int rmhmc_comm_unique_id(char* out128) {
@@ -1264,7 +1416,15 @@ int rmhmc_metric(rmhmc_handle* h, int64_t C, const double* theta, double* G, dou
     if (!rc) {
         MetricArgs a = metric_args(h, C, theta, gp, graw, ll, nullptr);
         rc = launch_metric<2>(h, a);                       // gradient + log-likelihood
-        if (!rc) { a.grad_out = nullptr; a.loglik_out = nullptr; rc = launch_metric<0>(h, a); }   // G
+        if (!rc && use_i8(h)) {                            // G through the digit planes, as the engine builds it
+            signed char* a8 = nullptr;
+            const int64_t a_rows = pad_up((int)C, kI8TileM);
+            CUtensorMap map_a;
+            rc = dev_alloc(h, &a8, (size_t)h->i8_slices * a_rows * h->i8_kp, &tmp);
+            if (!rc && !make_tensor_map_u8_k64(&map_a, a8, (uint64_t)h->i8_slices * a_rows, (uint64_t)h->i8_kp, kI8TileM))
+                rc = fail(h, RMHMC_E_CUDA, "cuTensorMapEncodeTiled failed");
+            if (!rc) rc = i8_build(h, C, theta, a8, a_rows, map_a, gp, nullptr);
+        } else if (!rc) { a.grad_out = nullptr; a.loglik_out = nullptr; rc = launch_metric<0>(h, a); }   // G
     }
     if (!rc) {
         if (G) k_unpack_g<<<blocks_for(C * h->dim * h->dim, 256), 256, 0, h->stream>>>(gp, G, C, h->dim, h->p2p);
@@ -1399,6 +1559,7 @@ int rmhmc_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const dou
     if (!h || n_window <= 0 || !z || !u_step || !z_dir || !u_acc) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_set_tape: bad arguments") : RMHMC_E_INVALID;
     h->P.rng_mode = 0; h->P.tape_base = it_base; h->P.tape_z = z; h->P.tape_u_step = u_step;
     h->P.tape_z_dir = z_dir; h->P.tape_u_acc = u_acc;
+    h->tape_base = it_base; h->tape_window = n_window;
     h->rng_set = true;
     return RMHMC_OK;
 }
@@ -1407,12 +1568,14 @@ int hmc_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const doubl
     if (!h || n_window <= 0 || !z || !u_step || !u_acc) return h ? fail(h, RMHMC_E_INVALID, "hmc_set_tape: bad arguments") : RMHMC_E_INVALID;
     h->P.rng_mode = 0; h->P.tape_base = it_base; h->P.tape_z = z; h->P.tape_u_step = u_step;
     h->P.tape_z_dir = nullptr; h->P.tape_u_acc = u_acc;
+    h->tape_base = it_base; h->tape_window = n_window;
     h->rng_set = true;
     return RMHMC_OK;
 }
 int rmhmc_set_philox(rmhmc_handle* h, uint64_t seed, int64_t chain_offset) {
     if (!h) return RMHMC_E_INVALID;
     h->P.rng_mode = 1; h->P.seed = seed; h->P.chain_offset = chain_offset;
+    h->tape_window = 0;
     h->rng_set = true;
     return RMHMC_OK;
 }
@@ -1441,6 +1604,8 @@ int rmhmc_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop) {
     if (h->n_chains <= 0 || h->is_hmc || h->is_mmala) return fail(h, RMHMC_E_STATE, "rmhmc_advance: call rmhmc_chains_init first");
     if (!h->configured || !h->rng_set) return fail(h, RMHMC_E_STATE, "rmhmc_advance: configure and set a tape / philox seed first");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    // a host tape bounds the iterations that may run: chains idle once they reach its end
+    if (h->P.rng_mode == 0 && it_stop > h->tape_base + h->tape_window) it_stop = h->tape_base + h->tape_window;
     h->P.it_stop = it_stop;
     return rmhmc_rounds(h, n_rounds);
 }
@@ -1488,6 +1653,7 @@ int mmala_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const dou
     if (!h || n_window <= 0 || !z || !u_acc) return h ? fail(h, RMHMC_E_INVALID, "mmala_set_tape: bad arguments") : RMHMC_E_INVALID;
     h->P.rng_mode = 0; h->P.tape_base = it_base; h->P.tape_z = z; h->P.tape_u_step = nullptr;
     h->P.tape_z_dir = nullptr; h->P.tape_u_acc = u_acc;
+    h->tape_base = it_base; h->tape_window = n_window;
     h->rng_set = true;
     return RMHMC_OK;
 }

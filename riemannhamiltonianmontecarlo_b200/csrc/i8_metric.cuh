@@ -1,0 +1,456 @@
+// INT8-slice metric build on the Blackwell tensor cores (tcgen05.mma.kind::i8, TMEM int32 accumulators).
+//
+// The Fisher metric of every chain, G = X^T diag(v) X + I/alpha (rmhmc.py:51-57, :116-119, :134-137), is the
+// chain-batched contraction
+//     G[chains x pairs] = V[chains x rows] . KR2(X)[rows x pairs],   KR2(X)[n, (a,b)] = x_na x_nb  (a <= b).
+// tcgen05 has no FP64 kind, so both operands are split into S balanced base-256 digits (an Ozaki scheme):
+//     v_cn   = sA        * sum_i a_i 256^-i  (a_i in [-128, 127], i = 0..S-1; sA fixed: 0 <= v <= 1/4)
+//     k_n,ab = sB[ab]    * sum_j b_j 256^-j  (sB per packed column)
+// Every digit product is exact in the int32 TMEM accumulators (|a b| <= 2^14, K <= 16384 rows, <= S products per
+// accumulator), products of equal weight i + j = w share accumulator `class w`, and the classes w < S are recombined
+// exactly in int64 and rounded ONCE to FP64 in the epilogue.  The dropped classes (w >= S) and the operand truncation
+// are ~2^-(8S-1) relative to the operand scales: measured max relative error of G 1-4e-12 for S = 5 (15 MMAs per K
+// step) and 1e-14 for S = 6 (21 MMAs) on the German- / Australian-shaped data (scripts/ozaki_feasibility.py).
+//
+// Two launches per build:
+//   k_i8_vslice   f = X theta, p = sigma(f), v = p (1 - p) in FP64 on the CUDA cores (thread = chain, X broadcast from
+//                 shared memory), digits of v -> A planes [S][Cpad][Kp] int8 (K-major).  CLOSING: also X^T (t - p),
+//                 log-likelihood and c_n = v (1 - 2p)  (rmhmc.py:140, :148-149, :167-168).
+//   k_i8_gemm     one CTA = 128 chains x NC packed columns: TMA (tensor maps, SWIZZLE_64B) -> 3-stage shared-memory
+//                 ring -> tcgen05.mma (one elected thread) -> S accumulators of NC columns in TMEM -> tcgen05.ld ->
+//                 int64 recombination -> FP64 scale (+ I/alpha on the diagonal pairs) -> packed G.
+// The B planes [S][columns][Kp] (digits of KR2(X)^T, 2 MB German-shaped) are formed once per data set.
+#pragma once
+#include "metric_kernel.cuh"
+#include "umma_common.cuh"
+
+namespace rmhmc {
+
+constexpr double kI8ScaleA = 0.26;        // v / sA <= 0.962: inside the balanced-digit range (|y| < 0.996)
+constexpr int kI8TileM = 128;             // chains per GEMM CTA (= TMEM lanes)
+constexpr int kI8BlockK = 64;             // bytes of K per pipeline stage (one SWIZZLE_64B row)
+constexpr int kI8GemmThreads = 192;       // warp 0: TMA producer, warp 1: TMEM allocation + MMA issue, warps 2-5: epilogue
+constexpr int kI8MaxRows = 16384;         // S * K * 2^14 < 2^31
+constexpr int kI8VsThreads = 128;         // chains per k_i8_vslice CTA
+constexpr int kI8VsRows = 32;             // rows per staged X block
+
+template <int S> struct I8Shape {
+    static_assert(S == 5 || S == 6, "5 or 6 digits");
+    static constexpr int NC = S == 5 ? 96 : 80;            // packed columns per CTA: S * NC <= 512 TMEM columns
+    static constexpr int STAGES = S == 5 ? 3 : 2;
+    static constexpr int BITS = 8 * S - 1;                 // operand = rint(y * 2^BITS), |y| < 1
+    static constexpr uint32_t A_SLICE = kI8TileM * kI8BlockK, B_SLICE = NC * kI8BlockK;
+    static constexpr uint32_t STAGE_BYTES = S * (A_SLICE + B_SLICE);
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128;
+};
+
+// 2^52 + 2^51 + sum_k 128 * 256^k: adding it to rint-able y * 2^BITS leaves, in the low mantissa bytes, the digits
+// biased by +128 (the carries of the balanced representation are done by the adder)
+__host__ __device__ constexpr double i8_magic(int s) {
+    double b = 0.0;
+    for (int k = 0; k < s; ++k) b = b * 256.0 + 128.0;
+    return 6755399441055744.0 + b;
+}
+
+struct I8GemmArgs {
+    double* g_out;              // [C][P2p] packed metric
+    const double2* colinfo;     // [columns] {sA sB[col] 2^(8(S-1) - 2 BITS), 1 if diagonal pair else 0}; {0, 0} for padding
+    double alpha_inv;
+    int n_chains, p2, p2p, k_blocks;
+    int a_rows, b_rows;         // rows per digit plane in the A / B tensor maps
+    int debug_class;            // >= 0: write accumulator `class` alone (self-test)
+};
+
+struct I8VsArgs {
+    const double* x;            // [Np][XS]
+    const double* theta;        // [C][D]
+    signed char* a8;            // [S][a_rows][kp]
+    size_t plane_stride;        // a_rows * kp
+    int kp;
+    int n_chains, n_rows, n_rows_pad, dim, xs;
+    // closing build
+    double* grad_out; double* loglik_out; double* cbuf;
+    const int* cw_cur; int cw_flip; size_t cw_slot;
+};
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------ B planes
+// max_n |x_na x_nb| per packed column (one CTA per column)
+__global__ void k_i8_colmax(const double* __restrict__ x, const uchar2* __restrict__ pair_tab, double* __restrict__ colmax,
+                            int n_rows_pad, int xs) {
+    const int col = blockIdx.x;
+    const uchar2 ab = pair_tab[col];
+    double m = 0.0;
+    for (int n = threadIdx.x; n < n_rows_pad; n += blockDim.x) m = fmax(m, fabs(x[(size_t)n * xs + ab.x] * x[(size_t)n * xs + ab.y]));
+    __shared__ double red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        colmax[col] = m;
+    }
+}
+// digits of KR2(X)^T: b8[s][col][n], zero for col >= p2 and n >= n_rows_pad; colinfo[col]
+template <int S>
+__global__ void k_i8_form_b(const double* __restrict__ x, const uchar2* __restrict__ pair_tab, const double* __restrict__ colmax,
+                            signed char* __restrict__ b8, double2* __restrict__ colinfo, int n_rows_pad, int xs, int p2,
+                            int b_rows, int kp) {
+    constexpr int BITS = I8Shape<S>::BITS;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)b_rows * kp) return;
+    const int col = (int)(i / kp), n = (int)(i - (long long)col * kp);
+    long long I = 0;
+    double sb = 1.0;
+    if (col < p2) {
+        const uchar2 ab = pair_tab[col];
+        const double m = colmax[col];
+        sb = m > 0.0 ? m / 0.99 : 1.0;
+        if (n < n_rows_pad) {
+            const double k = x[(size_t)n * xs + ab.x] * x[(size_t)n * xs + ab.y];
+            I = __double2ll_rn(k / sb * exp2((double)BITS));
+        }
+        if (n == 0) colinfo[col] = make_double2(kI8ScaleA * sb * exp2((double)(8 * (S - 1) - 2 * BITS)), ab.x == ab.y ? 1.0 : 0.0);
+    } else if (n == 0) {
+        colinfo[col] = make_double2(0.0, 0.0);
+    }
+    long long bias = 0;
+#pragma unroll
+    for (int k = 0; k < S; ++k) bias = bias * 256 + 128;
+    const unsigned long long u = (unsigned long long)(I + bias);
+#pragma unroll
+    for (int s = 0; s < S; ++s)      // digit s has weight 256^(S-1-s)
+        b8[((size_t)s * b_rows + col) * kp + n] = (signed char)(((u >> (8 * (S - 1 - s))) & 0xFF) ^ 0x80);
+}
+
+// ------------------------------------------------------------------------------------------------ A planes
+// biased digit bytes of one v: returns the S bytes u_{S-1} (least significant) .. u_0 in lo (bytes 0..3) and hi
+template <int S>
+__device__ __forceinline__ void i8_digits(double v, unsigned& lo, unsigned& hi) {
+    const double t = fma(v, (1.0 / kI8ScaleA) * (double)(1ull << 31) * (double)(1ull << (I8Shape<S>::BITS - 31)), i8_magic(S));
+    lo = (unsigned)__double2loint(t);
+    hi = (unsigned)__double2hiint(t);
+}
+
+// thread = chain; the CTA's 128 chains sweep the design matrix in 32-row blocks (cp.async double buffer, X rows are
+// broadcast reads).  DP = parameters rounded up to the unroll bound (even).  blockIdx.y splits the rows (iterate builds).
+template <int S, int DP, bool CLOSING>
+__global__ void __launch_bounds__(kI8VsThreads) k_i8_vslice(I8VsArgs a) {
+    constexpr int NB = kI8VsRows, GR = CLOSING ? 8 : 16;      // rows per register group
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int xs = a.xs;
+    double* xbuf = reinterpret_cast<double*>(smem_raw);                   // [2][NB][xs]
+    double* exp_tab = xbuf + 2 * (size_t)NB * xs;                         // [256]
+    double* log_tab = exp_tab + 256;                                      // [128][2]
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x * kI8VsThreads + tid;
+    const bool live = c < a.n_chains;
+    const int n_blocks_all = a.n_rows_pad / NB;
+    const int rb_begin = (int)((long long)n_blocks_all * blockIdx.y / gridDim.y);
+    const int n_blocks = (int)((long long)n_blocks_all * (blockIdx.y + 1) / gridDim.y) - rb_begin;
+
+    exp_tab[tid] = exp_table_entry(tid);
+    exp_tab[tid + 128] = exp_table_entry(tid + 128);
+    if (CLOSING) log_table_entry(tid, log_tab[2 * tid], log_tab[2 * tid + 1]);
+
+    double th[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) th[d] = (live && d < a.dim) ? a.theta[(size_t)c * a.dim + d] : 0.0;
+    double grad[CLOSING ? DP : 1];
+    double ll = 0.0;
+    if (CLOSING) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) grad[d] = 0.0;
+    }
+    const int tcol = xs - 1;
+    double* crow = nullptr;
+    if (CLOSING && live) {
+        const size_t slot = a.cw_cur ? (size_t)(a.cw_cur[c] ^ a.cw_flip) * a.cw_slot : 0;
+        crow = a.cbuf + slot + (size_t)c * a.n_rows_pad;
+    }
+    signed char* arow = a.a8 + (size_t)c * a.kp;
+
+    const int chunks = NB * xs / 2;       // 16-byte chunks per X block
+    auto stage = [&](int rb, int buf) {
+        const double* src = a.x + (size_t)(rb_begin + rb) * NB * xs;
+        double* dst = xbuf + (size_t)buf * NB * xs;
+        for (int i = tid; i < chunks; i += kI8VsThreads) cp_async16(dst + 2 * i, src + 2 * i);
+        cp_async_commit();
+    };
+    stage(0, 0);
+    for (int rb = 0; rb < n_blocks; ++rb) {
+        if (rb + 1 < n_blocks) { stage(rb + 1, (rb + 1) & 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const double* xb = xbuf + (size_t)(rb & 1) * NB * xs;
+#pragma unroll 1
+        for (int r0 = 0; r0 < NB; r0 += GR) {
+            double f[GR];
+#pragma unroll
+            for (int r = 0; r < GR; ++r) f[r] = 0.0;
+#pragma unroll
+            for (int dp = 0; dp < DP / 2; ++dp) {
+                if (2 * dp < a.dim) {
+#pragma unroll
+                    for (int r = 0; r < GR; ++r) {
+                        const double2 xv = *reinterpret_cast<const double2*>(xb + (size_t)(r0 + r) * xs + 2 * dp);
+                        f[r] = fma(xv.x, th[2 * dp], f[r]);
+                        f[r] = fma(xv.y, th[2 * dp + 1], f[r]);
+                    }
+                }
+            }
+            unsigned lo[GR], hi[GR];
+            double rr[CLOSING ? GR : 1], cc[CLOSING ? GR : 1];
+#pragma unroll
+            for (int r4 = 0; r4 < GR; r4 += 4) {
+                double ev[4], qq[4], eq[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ev[i] = fast_exp_nonpos(-fabs(f[r4 + i]), exp_tab);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) qq[i] = fast_rcp_1to2(1.0 + ev[i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) eq[i] = ev[i] * qq[i];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r4 + i;
+                    const double vv = eq[i] * qq[i];                 // p (1 - p)
+                    i8_digits<S>(vv, lo[r], hi[r]);
+                    if (CLOSING) {
+                        const double fv = f[r];
+                        const bool pos = fv >= 0.0;
+                        const double p = pos ? qq[i] : eq[i];
+                        const double om = pos ? eq[i] : qq[i];       // 1 - p
+                        const double t = xb[(size_t)(r0 + r) * xs + tcol];
+                        const bool ovf = fv > 709.782712893384;      // the reference's exp(f) overflows: NaN gradient, -inf log-likelihood
+                        rr[r] = ovf ? __longlong_as_double(0x7ff8000000000000LL) : t - p;
+                        cc[r] = vv * (om - p);
+                        const int row = (rb_begin + rb) * NB + r0 + r;
+                        if (row < a.n_rows) {
+                            const double l1pe = ovf ? __longlong_as_double(0x7ff0000000000000LL) : fmax(fv, 0.0) + fast_log1p_01(ev[i], log_tab);
+                            ll += t * fv - l1pe;
+                        }
+                    }
+                }
+            }
+            if (CLOSING) {
+#pragma unroll
+                for (int dp = 0; dp < DP / 2; ++dp) {
+                    if (2 * dp < a.dim) {
+#pragma unroll
+                        for (int r = 0; r < GR; ++r) {
+                            const double2 xv = *reinterpret_cast<const double2*>(xb + (size_t)(r0 + r) * xs + 2 * dp);
+                            grad[2 * dp] = fma(rr[r], xv.x, grad[2 * dp]);
+                            grad[2 * dp + 1] = fma(rr[r], xv.y, grad[2 * dp + 1]);
+                        }
+                    }
+                }
+            }
+            if (live) {
+                const int row0 = (rb_begin + rb) * NB + r0;
+                // digit s (weight 256^(S-1-s)) is byte S-1-s of (hi:lo); bytes of 4 consecutive rows -> one word
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    const int byte = S - 1 - s;
+                    unsigned w[GR / 4];
+#pragma unroll
+                    for (int j = 0; j < GR / 4; ++j) {
+                        unsigned v0, v1, v2, v3;
+                        if (byte < 4) { v0 = lo[4 * j]; v1 = lo[4 * j + 1]; v2 = lo[4 * j + 2]; v3 = lo[4 * j + 3]; }
+                        else { v0 = hi[4 * j]; v1 = hi[4 * j + 1]; v2 = hi[4 * j + 2]; v3 = hi[4 * j + 3]; }
+                        const unsigned b = byte & 3;
+                        const unsigned p01 = __byte_perm(v0, v1, b | ((4 + b) << 4));            // bytes: v0[b], v1[b]
+                        const unsigned p23 = __byte_perm(v2, v3, b | ((4 + b) << 4));
+                        w[j] = __byte_perm(p01, p23, 0x5410) ^ 0x80808080u;
+                    }
+                    signed char* dst = arow + (size_t)s * a.plane_stride + row0;
+                    if constexpr (GR == 16) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                    else *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+                }
+                if (CLOSING) {
+#pragma unroll
+                    for (int r = 0; r < GR; r += 2) *reinterpret_cast<double2*>(crow + row0 + r) = make_double2(cc[r], cc[r + 1]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (CLOSING && live) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d)
+            if (d < a.dim) a.grad_out[(size_t)c * a.dim + d] = grad[d];
+        a.loglik_out[c] = ll;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the GEMM
+template <int S>
+__global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_constant__ CUtensorMap map_a,
+                                                               const __grid_constant__ CUtensorMap map_b, I8GemmArgs a) {
+    using Sh = I8Shape<S>;
+    constexpr int NC = Sh::NC, ST = Sh::STAGES;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)ST * Sh::STAGE_BYTES);
+    uint64_t* full = bars;              // [ST] TMA -> MMA
+    uint64_t* empty = bars + ST;        // [ST] MMA -> TMA (tcgen05.commit)
+    uint64_t* acc_full = bars + 2 * ST; // MMA -> epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * NC;                 // first packed column
+    const int m0 = blockIdx.y * kI8TileM;           // first chain
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < a.k_blocks; ++kb) {
+                const int st = kb % ST;
+                if (kb >= ST) mbar_wait_or_trap(&empty[st], (uint32_t)(((kb / ST) - 1) & 1));
+                unsigned char* sa = base + (size_t)st * Sh::STAGE_BYTES;
+                unsigned char* sb = sa + S * Sh::A_SLICE;
+                mbar_expect_tx(&full[st], Sh::STAGE_BYTES);
+#pragma unroll
+                for (int s = 0; s < S; ++s) tma_load_2d(sa + s * Sh::A_SLICE, &map_a, kb * kI8BlockK, s * a.a_rows + m0, &full[st]);
+#pragma unroll
+                for (int s = 0; s < S; ++s) tma_load_2d(sb + s * Sh::B_SLICE, &map_b, kb * kI8BlockK, s * a.b_rows + n0, &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_s8(kI8TileM, NC);
+            for (int kb = 0; kb < a.k_blocks; ++kb) {
+                const int st = kb % ST;
+                mbar_wait_or_trap(&full[st], (uint32_t)((kb / ST) & 1));
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(base + (size_t)st * Sh::STAGE_BYTES);
+                const uint32_t sb = sa + S * Sh::A_SLICE;
+#pragma unroll
+                for (int ks = 0; ks < kI8BlockK / 32; ++ks) {
+#pragma unroll
+                    for (int w = 0; w < S; ++w) {
+#pragma unroll
+                        for (int i = 0; i <= w; ++i) {
+                            const uint64_t da = umma_desc_k_sw64(sa + i * Sh::A_SLICE + ks * 32);
+                            const uint64_t db = umma_desc_k_sw64(sb + (w - i) * Sh::B_SLICE + ks * 32);
+                            umma_i8_ss(tmem_base + w * NC, da, db, idesc, (kb | ks | i) != 0 ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(&empty[st]);          // frees the stage when its MMAs have read it
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ---- epilogue: warp w owns TMEM lanes 32 (w % 4) .. + 31 = chains m0 + 32 (w % 4) + lane
+        const int quarter = warp & 3;
+        const int c = m0 + quarter * 32 + lane;
+        mbar_wait_or_trap(acc_full, 0);
+        tcgen05_fence_after();
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int cg = 0; cg < NC / 16; ++cg) {
+            uint32_t r[S][16];
+#pragma unroll
+            for (int w = 0; w < S; ++w) tmem_ld16(lane_base + w * NC + cg * 16, r[w]);
+            tmem_ld_wait();
+            double out[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                // classes 0..S-1 -> sum_w 256^(S-1-w) acc_w.  |acc_w| < 2^27, so five classes fit int64 exactly (< 2^59);
+                // with six the upper three (< 2^43) and lower three are combined separately and joined by one FMA
+                constexpr int SH = S <= 5 ? S : 3;
+                long long th = (int)r[0][j];
+#pragma unroll
+                for (int w = 1; w < SH; ++w) th = th * 256 + (int)r[w][j];
+                long long tl = 0;
+#pragma unroll
+                for (int w = SH; w < S; ++w) tl = tl * 256 + (int)r[w][j];
+                if (a.debug_class >= 0) {
+                    th = 0; tl = 0;
+#pragma unroll
+                    for (int w = 0; w < S; ++w) if (w == a.debug_class) th = (int)r[w][j];
+                }
+                double t = (double)th;
+                if (S > 5 && a.debug_class < 0) t = fma(t, 16777216.0, (double)tl);
+                const int col = n0 + cg * 16 + j;
+                const double2 ci = a.colinfo[col];
+                out[j] = col < a.p2 ? fma(t, ci.x, ci.y * a.alpha_inv) : 0.0;
+            }
+            if (c < a.n_chains) {
+                double* dst = a.g_out + (size_t)c * a.p2p + n0 + cg * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2)
+                    if (n0 + cg * 16 + j < a.p2p) *reinterpret_cast<double2*>(dst + j) = make_double2(out[j], out[j + 1]);
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------------------------ host side
+struct I8Planes {               // digit planes of one operand + its tensor map
+    signed char* ptr = nullptr;
+    int rows = 0;               // rows per digit plane
+    CUtensorMap map;
+};
+
+inline int i8_kp(int n_rows_pad) { return pad_up(n_rows_pad, kI8BlockK); }
+inline int i8_dp(int dim) { return dim <= 8 ? 8 : (dim <= 16 ? 16 : (dim <= 26 ? 26 : 32)); }
+template <int S> inline int i8_chunks(int p2) { return (p2 + I8Shape<S>::NC - 1) / I8Shape<S>::NC; }
+inline size_t i8_vslice_smem(int xs) { return (size_t)2 * kI8VsRows * xs * 8 + 256 * 8 + 256 * 8; }
+
+#ifdef __CUDACC__
+template <int S, bool CLOSING>
+inline cudaError_t i8_launch_vslice(const I8VsArgs& a, cudaStream_t stream) {
+    // iterate builds: split the rows in two when that is needed to give every SM at least ~3 CTAs
+    const unsigned gx = (unsigned)((a.n_chains + kI8VsThreads - 1) / kI8VsThreads);
+    unsigned gy = 1;
+    if (!CLOSING) {
+        const int blocks = a.n_rows_pad / kI8VsRows;
+        while (gx * gy < 148 * 4 && (int)gy * 2 <= blocks && gy < 16) gy *= 2;
+    }
+    const dim3 grid(gx, gy);
+    const size_t smem = i8_vslice_smem(a.xs);
+    switch (i8_dp(a.dim)) {
+        case 8: k_i8_vslice<S, 8, CLOSING><<<grid, kI8VsThreads, smem, stream>>>(a); break;
+        case 16: k_i8_vslice<S, 16, CLOSING><<<grid, kI8VsThreads, smem, stream>>>(a); break;
+        case 26: k_i8_vslice<S, 26, CLOSING><<<grid, kI8VsThreads, smem, stream>>>(a); break;
+        default: k_i8_vslice<S, 32, CLOSING><<<grid, kI8VsThreads, smem, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+template <int S>
+inline cudaError_t i8_launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const I8GemmArgs& a, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_i8_gemm<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Shape<S>::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const dim3 grid((unsigned)i8_chunks<S>(a.p2), (unsigned)((a.n_chains + kI8TileM - 1) / kI8TileM));
+    k_i8_gemm<S><<<grid, kI8GemmThreads, I8Shape<S>::SMEM, stream>>>(map_a, map_b, a);
+    return cudaGetLastError();
+}
+#endif
+
+}  // namespace rmhmc

@@ -40,8 +40,11 @@ class LogisticData:
     """
 
     PARTIALS = {"tensor": 0, "matrix_free": 1}
+    METRIC = {"dmma": 0, "i8": 1}
+    REGIME = {"auto": 0, "small": 1, "large": 2}
 
-    def __init__(self, xx, t, alpha: float = 100.0, device: str | int = "cuda:0", row_shard=None, partials=None):
+    def __init__(self, xx, t, alpha: float = 100.0, device: str | int = "cuda:0", row_shard=None, partials=None,
+                 metric=None, regime=None):
         torch = _capi.require_cuda()
         self._lib = _capi.load()
         self.torch = torch
@@ -67,6 +70,24 @@ class LogisticData:
         _capi.check(self._lib.rmhmc_set_stream(self.handle, c_void_p(stream)), self.handle, "rmhmc_set_stream")
         if partials is not None:
             self.set_partials_mode(partials)
+        if metric is not None:
+            self.set_metric_mode(metric)
+        if regime is not None:
+            self.set_launch_regime(regime)
+
+    def set_metric_mode(self, mode: str):
+        """``"dmma"``: fused FP64 kernel (legacy tensor path); ``"i8"``: INT8-slice build on the tcgen05 tensor cores
+        (include/rmhmc_b200.h).  Drops the handle's chains: call before creating a sampler."""
+        _capi.check(self._lib.rmhmc_set_metric_mode(self.handle, self.METRIC[mode]), self.handle, "rmhmc_set_metric_mode")
+
+    @property
+    def metric_mode(self) -> str:
+        return "i8" if self._lib.rmhmc_get_metric_mode(self.handle) == 1 else "dmma"
+
+    def set_launch_regime(self, regime: str):
+        """Pin the chain-count dependent kernel variants: ``"small"`` / ``"large"`` / ``"auto"``."""
+        _capi.check(self._lib.rmhmc_set_launch_regime(self.handle, self.REGIME[regime]), self.handle,
+                    "rmhmc_set_launch_regime")
 
     def set_partials_mode(self, mode: str):
         """``"tensor"``: build the packed partials tensor per chain (the reference's formulation);

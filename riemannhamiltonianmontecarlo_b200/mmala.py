@@ -25,10 +25,10 @@ ALPHA = 100  # BLR_mMALA.m:16
 
 
 def mmala_batched(XX, t, n_chains, NumOfIterations=10000, BurnIn=5000, StepSize=1.0, Simplified=False, *, seed=0,
-                  chain_offset=0, device="cuda:0", draws=None, trace=False):
+                  chain_offset=0, device="cuda:0", draws=None, trace=False, metric=None):
     """``n_chains`` independent chains -> ``(samples (C, n-b, D), seconds, info)``; ``draws`` = dict(z (W,C,D),
     u_acc (W,C)) replays a host tape.  ``trace=True`` adds the per-iteration proposals / ratios / flags to ``info``."""
-    data = LogisticData(XX, t, alpha=ALPHA, device=device)
+    data = LogisticData(XX, t, alpha=ALPHA, device=device, metric=metric)
     sampler = MMALASampler(data, n_chains, StepSize, Simplified)
     if draws is not None:
         sampler.set_tape(draws["z"], draws["u_acc"])

@@ -110,15 +110,16 @@ def _set_trace_base(sampler, it_base):
 
 def rmhmc_batched(XX, t, n_chains, NumOfIterations=6000, BurnIn=1000, NumOfLeapFrogSteps=6, StepSize=0.5,
                   NumOfNewtonSteps=4, *, seed=0, chain_offset=0, device="cuda:0", draws=None, return_device=False,
-                  partials=None):
+                  partials=None, metric=None, regime=None):
     """``n_chains`` independent RMHMC chains -> ``(samples (C, n-b, D), seconds, info)``.
 
     ``draws`` = dict(z, u_step, z_dir, u_acc) in the (W, C, ...) layout replays a host tape
     (parity mode); otherwise Philox(seed, chain_offset + chain) draws are generated on the device.
     Row 0 of every chain's samples is never written (zeros), as in the reference.
     ``partials``: ``"tensor"`` / ``"matrix_free"`` (see ``LogisticData.set_partials_mode``); None = library default.
+    ``metric``: ``"dmma"`` / ``"i8"`` (``LogisticData.set_metric_mode``); ``regime``: kernel-variant pin (tests).
     """
-    data = LogisticData(XX, t, alpha=ALPHA, device=device, partials=partials)
+    data = LogisticData(XX, t, alpha=ALPHA, device=device, partials=partials, metric=metric, regime=regime)
     sampler = RMHMCSampler(data, n_chains, NumOfLeapFrogSteps, StepSize, NumOfNewtonSteps)
     if draws is not None:
         sampler.set_tape(draws["z"], draws["u_step"], draws["z_dir"], draws["u_acc"])

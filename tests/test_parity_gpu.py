@@ -31,17 +31,25 @@ def _thetas(d, n, seed):
     return th
 
 
+METRIC = ["dmma", "i8"]                   # FP64 DMMA kernel / INT8-slice tcgen05 build (include/rmhmc_b200.h)
+G_TOL = {"dmma": 1e-12, "i8": 1e-11}      # five balanced base-256 digits per operand: ~2^-39 of the operand scales
+
+
+@pytest.mark.parametrize("metric", METRIC)
 @pytest.mark.parametrize("shape", ["australian", "german"])
-def test_metric_seam_matches_oracle(pkg, shape):
+def test_metric_seam_matches_oracle(pkg, shape, metric):
     xx, t = pkg.datasets.shaped(shape)
     d = xx.shape[1]
     thetas = _thetas(d, 37, 11)      # 37: a ragged last tile of chains
-    data = pkg.LogisticData(xx, t)
+    thetas[1] = 0.0                  # f = 0 everywhere: v = 1/4 exactly, the largest digit value of the INT8 build
+    thetas[2] *= 8.0                 # |f| up to ~50: most v_n tiny, a few near 1/4
+    data = pkg.LogisticData(xx, t, metric=metric)
+    assert data.metric_mode == metric
     g, grad, lj = data.metric(thetas)
     for c in range(thetas.shape[0]):
         w = thetas[c].reshape(-1, 1)
         _, _, _, g_ref = bo.fisher_metric(xx, w)
-        assert rel_err(g[c], g_ref) < 1e-12
+        assert rel_err(g[c], g_ref) < G_TOL[metric]
         assert rel_err(grad[c], bo.likelihood_gradient(xx, t, w)[:, 0]) < 1e-11
         assert abs(lj[c] - bo._scalar(bo.log_joint(xx, t, w))) < 1e-11 * abs(lj[c])
     data.close()
@@ -81,15 +89,19 @@ def test_chol_seam_matches_numpy(pkg):
 PARTIALS = ["matrix_free", "tensor"]      # both evaluations of the metric partials (include/rmhmc_b200.h)
 
 
-def _run_tape_fixture(pkg, fx, n_chains=None, partials=None):
+def _run_tape_fixture(pkg, fx, n_chains=None, partials=None, metric=None, regime=None):
+    """Run the fixture's tape; n_chains beyond the fixture's chain count replicates the tapes cyclically."""
     xx, t = fx["xx"], fx["t"]
     n_iter, burn_in = int(fx["n_iter"]), int(fx["burn_in"])
     c = fx["z"].shape[1] if n_chains is None else n_chains
-    data = pkg.LogisticData(xx, t, partials=partials)
+    data = pkg.LogisticData(xx, t, partials=partials, metric=metric, regime=regime)
     if partials is not None:
         assert data.partials_mode == partials
+    if metric is not None:
+        assert data.metric_mode == metric
     s = pkg.RMHMCSampler(data, c, int(fx["n_leapfrog"]), float(fx["step_size"]), int(fx["n_fixed"]))
-    s.set_tape(fx["z"][:, :c], fx["u_step"][:, :c], fx["z_dir"][:, :c], fx["u_acc"][:, :c])
+    idx = np.arange(c) % fx["z"].shape[1]
+    s.set_tape(fx["z"][:, idx], fx["u_step"][:, idx], fx["z_dir"][:, idx], fx["u_acc"][:, idx])
     s.set_samples(n_iter - burn_in, burn_in)
     s.set_trace(n_iter)
     s.run(n_iter)
@@ -100,13 +112,105 @@ def _run_tape_fixture(pkg, fx, n_chains=None, partials=None):
     return tr, samples, st
 
 
+def _assert_trace_matches_fixture(fx, tr, samples, st, chains=None):
+    """Per-step theta, end momentum, H within RTOL and bit-exact decisions for the given chain indices of the run
+    (chain j of the run replays fixture chain j mod c)."""
+    c_fx, n_iter = fx["n_steps"].shape
+    chains = range(c_fx) if chains is None else chains
+    worst = 0.0
+    for cj in chains:
+        ci = cj % c_fx
+        assert np.array_equal(tr["n_steps"][cj], fx["n_steps"][ci])
+        assert np.array_equal(tr["direction"][cj], fx["direction"][ci])
+        assert np.array_equal(tr["accepted"][cj], fx["accepted"][ci])
+        assert np.array_equal(tr["used_uniform"][cj], fx["used_uniform"][ci])
+        assert st["iters"][cj] == n_iter and st["accepted"][cj] == fx["accepted"][ci].sum()
+        assert st["leapfrogs"][cj] == fx["n_steps"][ci].sum()
+        for it in range(n_iter):
+            ns = int(fx["n_steps"][ci, it])
+            for s_ in range(ns):
+                worst = max(worst, rel_err(tr["theta_steps"][cj, it, s_], fx["theta_steps"][ci, it, s_]))
+            worst = max(worst, rel_err(tr["mom_end"][cj, it], fx["mom_end"][ci, it]))
+            worst = max(worst, rel_err(tr["mom0"][cj, it], fx["mom0"][ci, it]))
+            worst = max(worst, abs(tr["h_current"][cj, it] - fx["h_current"][ci, it]) / abs(fx["h_current"][ci, it]))
+            worst = max(worst, abs(tr["h_proposed"][cj, it] - fx["h_proposed"][ci, it]) / abs(fx["h_proposed"][ci, it]))
+        assert rel_err(samples[cj, 1:], fx["samples"][ci, 1:]) < RTOL
+    assert worst < RTOL, worst
+    return worst
+
+
+BENCH_SCALE_CHAINS = 20480 + 37       # >= 148 * 2 * 8 * 8 = 18 944: the kernel variants bench.py runs; ragged last tile
+
+
+@pytest.mark.parametrize("metric", METRIC)
+@pytest.mark.parametrize("partials", PARTIALS)
+@pytest.mark.parametrize("name", ["rmhmc_german_shaped", "rmhmc_australian_shaped"])
+def test_bench_scale_batch_matches_reference(pkg, golden, name, partials, metric):
+    """The golden tapes inside a batch as large as the benchmark's kernel regime (k_pass<MOMFP, 8>, k_pass<PAIR, 8>,
+    64-chain pass tiles, unsplit metric builds): every replica of a fixture chain -- at warp, CTA and GEMM-tile boundaries
+    and in the ragged last tile -- is bit-identical to the first, and the first follows the reference step by step."""
+    fx = golden(name)
+    c_fx = fx["z"].shape[1]
+    tr, samples, st = _run_tape_fixture(pkg, fx, n_chains=BENCH_SCALE_CHAINS, partials=partials, metric=metric)
+    idx = np.arange(BENCH_SCALE_CHAINS) % c_fx
+    for key in ("theta_steps", "mom_end", "mom0", "h_current", "h_proposed", "flags"):
+        assert np.array_equal(tr[key], tr[key][idx], equal_nan=True), key
+    assert np.array_equal(samples, samples[idx])
+    assert np.array_equal(st["leapfrogs"], st["leapfrogs"][idx]) and np.array_equal(st["accepted"], st["accepted"][idx])
+    picks = list(range(c_fx)) + [31, 32, 63, 64, 127, 128, 255, 256, 18943, 18944, BENCH_SCALE_CHAINS - 1]
+    _assert_trace_matches_fixture(fx, tr, samples, st, chains=picks)
+
+
+@pytest.mark.parametrize("metric", METRIC)
+@pytest.mark.parametrize("partials", PARTIALS)
+def test_large_regime_kernels_on_a_small_batch(pkg, golden, partials, metric):
+    """rmhmc_set_launch_regime(LARGE) runs the many-chain kernel variants on the fixture's handful of chains: same
+    trajectories as the reference, and bit-identical to the same chains inside a benchmark-sized batch."""
+    fx = golden("rmhmc_australian_shaped")
+    tr_s, s_s, st_s = _run_tape_fixture(pkg, fx, partials=partials, metric=metric, regime="large")
+    _assert_trace_matches_fixture(fx, tr_s, s_s, st_s)
+    tr_b, s_b, _ = _run_tape_fixture(pkg, fx, n_chains=BENCH_SCALE_CHAINS, partials=partials, metric=metric)
+    c_fx = fx["z"].shape[1]
+    assert np.array_equal(s_s, s_b[:c_fx])
+    assert np.array_equal(tr_s["h_proposed"], tr_b["h_proposed"][:c_fx])
+    assert np.array_equal(tr_s["theta_steps"], tr_b["theta_steps"][:c_fx], equal_nan=True)
+
+
+def test_tape_window_is_enforced(pkg, golden):
+    """A host tape covers a window of iterations; running past it (or starting before it) is an error, not a read
+    beyond the tape buffers."""
+    fx = golden("rmhmc_pima_real")
+    w = 5
+    data = pkg.LogisticData(fx["xx"], fx["t"])
+    s = pkg.RMHMCSampler(data, 2, int(fx["n_leapfrog"]), float(fx["step_size"]), int(fx["n_fixed"]))
+    s.set_tape(fx["z"][:w, :2], fx["u_step"][:w, :2], fx["z_dir"][:w, :2], fx["u_acc"][:w, :2])
+    s.set_samples(2 * w, 0)
+    with pytest.raises(pkg.RmhmcError):
+        s.run(w + 1)
+    s.run(w)
+    s.advance(50)                     # free-running rounds stop at the end of the tape
+    assert np.array_equal(s.state()["iters"], [w, w])
+    s.set_tape(fx["z"][:w, :2], fx["u_step"][:w, :2], fx["z_dir"][:w, :2], fx["u_acc"][:w, :2], it_base=w + 2)
+    with pytest.raises(pkg.RmhmcError):
+        s.run(w + 3)                  # the chains are at iteration w, the tape starts at w + 2
+    s.set_tape(fx["z"][w:2 * w, :2], fx["u_step"][w:2 * w, :2], fx["z_dir"][w:2 * w, :2], fx["u_acc"][w:2 * w, :2], it_base=w)
+    s.run(2 * w)
+    got = s.samples.cpu().numpy()
+    assert np.array_equal(s.state()["iters"], [2 * w, 2 * w])
+    data.close()
+    b = int(fx["burn_in"])            # fixture row r = state after iteration r + burn_in; this run stores iteration it in row it
+    assert b < 2 * w - 1
+    assert rel_err(got[:, b + 1:2 * w], fx["samples"][:2, 1:2 * w - b]) < RTOL
+
+
+@pytest.mark.parametrize("metric", METRIC)
 @pytest.mark.parametrize("partials", PARTIALS)
 @pytest.mark.parametrize("name", ["rmhmc_australian_shaped", "rmhmc_german_shaped", "rmhmc_german_real",
                                   "rmhmc_pima_real"])
-def test_rmhmc_trajectories_match_reference(pkg, golden, name, partials):
+def test_rmhmc_trajectories_match_reference(pkg, golden, name, partials, metric):
     """Same data, same host draws: per-step theta, end momentum, H and the accept decisions."""
     fx = golden(name)
-    tr, samples, st = _run_tape_fixture(pkg, fx, partials=partials)
+    tr, samples, st = _run_tape_fixture(pkg, fx, partials=partials, metric=metric)
     c, n_iter = fx["n_steps"].shape
     # decisions and integer draws: bit-exact
     assert np.array_equal(tr["n_steps"], fx["n_steps"])
@@ -317,8 +421,9 @@ def test_row_sharded_matches_unsharded_on_two_gpus(pkg):
     assert res["ok"], res
 
 
+@pytest.mark.parametrize("metric", METRIC)
 @pytest.mark.parametrize("shape", ["australian", "german"])
-def test_leapfrog_seam_matches_oracle(pkg, shape):
+def test_leapfrog_seam_matches_oracle(pkg, shape, metric):
     """rmhmc_leapfrog: deterministic generalized leapfrog from given (theta, p), both directions."""
     xx, t = pkg.datasets.shaped(shape)
     d = xx.shape[1]
@@ -328,7 +433,7 @@ def test_leapfrog_seam_matches_oracle(pkg, shape):
     mom = rng.normal(0, 4.0, (c, d))
     direction = np.array([1, -1, 1, -1, 1, -1])
     n_steps = np.array([1, 2, 3, 4, 5, 6])
-    data = pkg.LogisticData(xx, t)
+    data = pkg.LogisticData(xx, t, metric=metric)
     th, mo, h0, h1 = data.leapfrog(theta, mom, direction, n_steps, 0.5, 6)
     data.close()
     for i in range(c):
@@ -532,9 +637,10 @@ def test_cfg3_full_size_leapfrog_modes_agree(pkg, cfg3):
 
 # ---- manifold MALA.  The oracle is a port of the MATLAB original (parity unpinned: no
 # MATLAB/Octave here); the CUDA path is checked against it under a host tape and against the RMHMC posterior.
+@pytest.mark.parametrize("metric", METRIC)
 @pytest.mark.parametrize("simplified", [False, True])
 @pytest.mark.parametrize("shape", ["australian", "german"])
-def test_mmala_matches_oracle_under_a_tape(pkg, shape, simplified):
+def test_mmala_matches_oracle_under_a_tape(pkg, shape, simplified, metric):
     xx, t = pkg.datasets.shaped(shape)
     d = xx.shape[1]
     n_iter, burn, c = 12, 4, 5
@@ -542,7 +648,7 @@ def test_mmala_matches_oracle_under_a_tape(pkg, shape, simplified):
     ref, infos = bo.mmala_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, step_size=1.0, simplified=simplified,
                                  record=True)
     st = bo.stack_tapes(tapes)
-    out, _, info = pkg.mmala_batched(xx, t, c, n_iter, burn, 1.0, simplified, draws=st, trace=True)
+    out, _, info = pkg.mmala_batched(xx, t, c, n_iter, burn, 1.0, simplified, draws=st, trace=True, metric=metric)
     for ci in range(c):
         rec = infos[ci]["records"]
         assert np.array_equal(info["accepted_flags"][ci], [r["accepted"] for r in rec])
