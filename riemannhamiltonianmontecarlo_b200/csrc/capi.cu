@@ -933,7 +933,7 @@ int i8_build_s(rmhmc_handle* h, int64_t C, const double* theta, signed char* a8,
         v.cw_cur = cl->cw_cur; v.cw_flip = cl->cw_flip; v.cw_slot = cl->cw_slot;
         e = i8_launch_vslice<S, true>(v, h->stream);
     } else {
-        e = i8_launch_vslice<S, false>(v, h->stream);
+        e = i8_launch_vslice_mma<S>(v, h->stream);
     }
     if (e != cudaSuccess) return fail(h, RMHMC_E_CUDA, std::string("k_i8_vslice: ") + cudaGetErrorString(e));
     I8GemmArgs g{};

@@ -21,6 +21,8 @@
 //                 int64 recombination -> FP64 scale (+ I/alpha on the diagonal pairs) -> packed G.
 // The B planes [S][columns][Kp] (digits of KR2(X)^T, 2 MB German-shaped) are formed once per data set.
 #pragma once
+#include <type_traits>
+
 #include "metric_kernel.cuh"
 #include "umma_common.cuh"
 
@@ -29,7 +31,7 @@ namespace rmhmc {
 constexpr double kI8ScaleA = 0.26;        // v / sA <= 0.962: inside the balanced-digit range (|y| < 0.996)
 constexpr int kI8TileM = 128;             // chains per GEMM CTA (= TMEM lanes)
 constexpr int kI8BlockK = 64;             // bytes of K per pipeline stage (one SWIZZLE_64B row)
-constexpr int kI8GemmThreads = 192;       // warp 0: TMA producer, warp 1: TMEM allocation + MMA issue, warps 2-5: epilogue
+constexpr int kI8GemmThreads = 320;       // warp 0: TMA producer, warp 1: TMEM allocation + MMA issue, warps 2-9: epilogue
 constexpr int kI8MaxRows = 16384;         // S * K * 2^14 < 2^31
 constexpr int kI8VsThreads = 128;         // chains per k_i8_vslice CTA
 constexpr int kI8VsRows = 32;             // rows per staged X block
@@ -41,7 +43,7 @@ template <int S> struct I8Shape {
     static constexpr int BITS = 8 * S - 1;                 // operand = rint(y * 2^BITS), |y| < 1
     static constexpr uint32_t A_SLICE = kI8TileM * kI8BlockK, B_SLICE = NC * kI8BlockK;
     static constexpr uint32_t STAGE_BYTES = S * (A_SLICE + B_SLICE);
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */ + NC * 16 /* column scales */;
 };
 
 // 2^52 + 2^51 + sum_k 128 * 256^k: adding it to rint-able y * 2^BITS leaves, in the low mantissa bytes, the digits
@@ -283,6 +285,99 @@ __global__ void __launch_bounds__(kI8VsThreads) k_i8_vslice(I8VsArgs a) {
     }
 }
 
+// Position-iterate variant on the FP64 tensor path: f^T = Theta . X^T as DMMA.8x8x4 (Theta fragments in registers, X
+// fragments straight from global memory / L1: X is 200 KB and every CTA sweeps it once), the logistic terms on the
+// 8 (chain, row) pairs of each lane, digits through a warp-private shared-memory transpose so that the planes are
+// written as 16-byte row runs.  One warp = 32 chains x 16 rows per step; no CTA-wide synchronisation.
+constexpr int kI8VmWarps = 8;
+template <int S, int KS>
+__global__ void __launch_bounds__(kI8VmWarps * 32, 2) k_i8_vslice_mma(I8VsArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* exp_tab = reinterpret_cast<double*>(smem_raw);                                   // [256]
+    unsigned char* out_all = smem_raw + 256 * 8;                                             // [warps][S][32][16]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int chain0 = blockIdx.x * 32;
+    const int xs = a.xs;
+    exp_tab[tid] = exp_table_entry(tid);
+    __syncthreads();
+    unsigned char* out_w = out_all + (size_t)warp * S * 32 * 16;
+
+    // Theta fragments: a[m][ks] = theta[chain0 + 8 m + g][4 ks + q]
+    double th[4][KS];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int c = chain0 + m * 8 + g;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int d = ks * 4 + q;
+            th[m][ks] = (c < a.n_chains && d < a.dim) ? a.theta[(size_t)c * a.dim + d] : 0.0;
+        }
+    }
+    // rows of this CTA (blockIdx.y splits them in 16-row units), 16 rows per warp and step
+    const int units_all = a.n_rows_pad / 16;
+    const int u_begin = (int)((long long)units_all * blockIdx.y / gridDim.y);
+    const int u_end = (int)((long long)units_all * (blockIdx.y + 1) / gridDim.y);
+    auto load_b = [&](int row0, double (&b)[KS]) {
+        const double* xr = a.x + (size_t)(row0 + g) * xs + q;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) b[ks] = ks * 4 < xs ? __ldg(xr + ks * 4) : 0.0;
+    };
+    double bnext[KS];
+    int u = u_begin + warp;
+    if (u < u_end) load_b(u * 16, bnext);
+    for (; u < u_end; u += kI8VmWarps) {
+        const int row0 = u * 16;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            double b[KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) b[ks] = bnext[ks];
+            // prefetch the next 8-row tile of this warp
+            if (nt == 0) load_b(row0 + 8, bnext);
+            else if (u + kI8VmWarps < u_end) load_b((u + kI8VmWarps) * 16, bnext);
+            double f[4][2];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) f[m][0] = f[m][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) dmma884(f[m][0], f[m][1], th[m][ks], b[ks]);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                double ev[4], qq[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ev[i] = fast_exp_nonpos(-fabs(f[2 * half + (i >> 1)][i & 1]), exp_tab);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) qq[i] = fast_rcp_1to2(1.0 + ev[i]);
+#pragma unroll
+                for (int mm = 0; mm < 2; ++mm) {
+                    const int m = 2 * half + mm;
+                    unsigned lo0, hi0, lo1, hi1;
+                    i8_digits<S>(ev[2 * mm] * qq[2 * mm] * qq[2 * mm], lo0, hi0);                // v = e / (1 + e)^2
+                    i8_digits<S>(ev[2 * mm + 1] * qq[2 * mm + 1] * qq[2 * mm + 1], lo1, hi1);
+                    unsigned char* dst = out_w + (size_t)(m * 8 + g) * 16 + nt * 8 + 2 * q;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const int byte = S - 1 - s;
+                        const unsigned bsel = byte & 3;
+                        const unsigned pr = __byte_perm(byte < 4 ? lo0 : hi0, byte < 4 ? lo1 : hi1, bsel | ((4 + bsel) << 4));
+                        *reinterpret_cast<unsigned short*>(dst + (size_t)s * 32 * 16) = (unsigned short)((pr & 0xFFFFu) ^ 0x8080u);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        const int c = chain0 + lane;
+        if (c < a.n_chains) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                *reinterpret_cast<uint4*>(a.a8 + (size_t)s * a.plane_stride + (size_t)c * a.kp + row0) =
+                    *reinterpret_cast<const uint4*>(out_w + ((size_t)s * 32 + lane) * 16);
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the GEMM
 template <int S>
 __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_constant__ CUtensorMap map_a,
@@ -330,7 +425,10 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_s8(kI8TileM, NC);
+            // Digit i of V times digits j = 0 .. S-1-i of KR2(X) go to the classes i .. S-1, which are adjacent TMEM
+            // column blocks, and the B digit tiles are adjacent in shared memory: one MMA of N = MB * NC columns covers
+            // MB consecutive digits j (fewer, wider MMAs: the A tile is fetched 9 instead of 15 times per K step).
+            constexpr int MB = 256 / NC;          // digit tiles per MMA (N <= 256)
             for (int kb = 0; kb < a.k_blocks; ++kb) {
                 const int st = kb % ST;
                 mbar_wait_or_trap(&full[st], (uint32_t)((kb / ST) & 1));
@@ -340,12 +438,14 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
 #pragma unroll
                 for (int ks = 0; ks < kI8BlockK / 32; ++ks) {
 #pragma unroll
-                    for (int w = 0; w < S; ++w) {
+                    for (int i = 0; i < S; ++i) {
+                        const uint64_t da = umma_desc_k_sw64(sa + i * Sh::A_SLICE + ks * 32);
 #pragma unroll
-                        for (int i = 0; i <= w; ++i) {
-                            const uint64_t da = umma_desc_k_sw64(sa + i * Sh::A_SLICE + ks * 32);
-                            const uint64_t db = umma_desc_k_sw64(sb + (w - i) * Sh::B_SLICE + ks * 32);
-                            umma_i8_ss(tmem_base + w * NC, da, db, idesc, (kb | ks | i) != 0 ? 1u : 0u);
+                        for (int j0 = 0; j0 < S - i; j0 += MB) {
+                            const int take = S - i - j0 < MB ? S - i - j0 : MB;
+                            const uint64_t db = umma_desc_k_sw64(sb + j0 * Sh::B_SLICE + ks * 32);
+                            umma_i8_ss(tmem_base + (i + j0) * NC, da, db, umma_idesc_s8(kI8TileM, take * NC),
+                                       (kb | ks | i) != 0 ? 1u : 0u);
                         }
                     }
                 }
@@ -354,48 +454,60 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
             umma_commit(acc_full);
         }
     } else {
-        // ---- epilogue: warp w owns TMEM lanes 32 (w % 4) .. + 31 = chains m0 + 32 (w % 4) + lane
-        const int quarter = warp & 3;
-        const int c = m0 + quarter * 32 + lane;
-        mbar_wait_or_trap(acc_full, 0);
+        // ---- epilogue (8 warps): warp w reads TMEM lanes 32 (w % 4) .. + 31 = chains m0 + 32 (w % 4) + lane, the two
+        // warps of a lane quarter split the column groups.  int32 classes -> FP64 exactly (magic-number conversion on
+        // the integer pipe + one DADD), classes recombined with exact FMAs and ONE rounding, scaled, staged through the
+        // (now idle) operand ring so that the global stores are contiguous 256-byte row segments.
+        const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+        constexpr int G0 = 3;                                   // column groups of the first warp of a quarter
+        const int cg_begin = half ? G0 : 0, cg_end = half ? NC / 16 : G0;
+        const int ncols = (cg_end - cg_begin) * 16;
+        constexpr int OS = G0 * 16 + 1;                         // staging row stride (doubles): odd -> conflict-free
+        double2* ci_s = reinterpret_cast<double2*>(bars + 16);              // [NC] column scales of this CTA
+        for (int i = threadIdx.x - 64; i < NC; i += kI8GemmThreads - 64) ci_s[i] = a.colinfo[n0 + i];
+        asm volatile("bar.sync 1, %0;" ::"n"(kI8GemmThreads - 64) : "memory");
+        mbar_wait_or_trap(acc_full, 0);          // all MMAs done: accumulators final, the operand ring is free
         tcgen05_fence_after();
+        double* out_s = reinterpret_cast<double*>(base) + (size_t)ew * 32 * OS;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-        for (int cg = 0; cg < NC / 16; ++cg) {
+        for (int cg = cg_begin; cg < cg_end; ++cg) {
             uint32_t r[S][16];
 #pragma unroll
             for (int w = 0; w < S; ++w) tmem_ld16(lane_base + w * NC + cg * 16, r[w]);
             tmem_ld_wait();
-            double out[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                // classes 0..S-1 -> sum_w 256^(S-1-w) acc_w.  |acc_w| < 2^27, so five classes fit int64 exactly (< 2^59);
-                // with six the upper three (< 2^43) and lower three are combined separately and joined by one FMA
-                constexpr int SH = S <= 5 ? S : 3;
-                long long th = (int)r[0][j];
+                double x[S];
 #pragma unroll
-                for (int w = 1; w < SH; ++w) th = th * 256 + (int)r[w][j];
-                long long tl = 0;
+                for (int w = 0; w < S; ++w)      // (double)(int32): 2^52 + 2^31 + x is exact, subtract the offset
+                    x[w] = __hiloint2double(0x43300000, (int)(r[w][j] ^ 0x80000000u)) - 4503601774854144.0;
+                // sum_w 256^(S-1-w) x_w: upper three and lower (S - 3) classes are exact in FP64 (< 2^44), one FMA joins them
+                double hi = fma(fma(x[0], 256.0, x[1]), 256.0, x[2]);
+                double lo = x[3];
 #pragma unroll
-                for (int w = SH; w < S; ++w) tl = tl * 256 + (int)r[w][j];
+                for (int w = 4; w < S; ++w) lo = fma(lo, 256.0, x[w]);
+                double t = fma(hi, S == 5 ? 65536.0 : 16777216.0, lo);
                 if (a.debug_class >= 0) {
-                    th = 0; tl = 0;
 #pragma unroll
-                    for (int w = 0; w < S; ++w) if (w == a.debug_class) th = (int)r[w][j];
+                    for (int w = 0; w < S; ++w) if (w == a.debug_class) t = x[w];
                 }
-                double t = (double)th;
-                if (S > 5 && a.debug_class < 0) t = fma(t, 16777216.0, (double)tl);
-                const int col = n0 + cg * 16 + j;
-                const double2 ci = a.colinfo[col];
-                out[j] = col < a.p2 ? fma(t, ci.x, ci.y * a.alpha_inv) : 0.0;
-            }
-            if (c < a.n_chains) {
-                double* dst = a.g_out + (size_t)c * a.p2p + n0 + cg * 16;
-#pragma unroll
-                for (int j = 0; j < 16; j += 2)
-                    if (n0 + cg * 16 + j < a.p2p) *reinterpret_cast<double2*>(dst + j) = make_double2(out[j], out[j + 1]);
+                const double2 ci = ci_s[cg * 16 + j];
+                out_s[lane * OS + (cg - cg_begin) * 16 + j] = n0 + cg * 16 + j < a.p2 ? fma(t, ci.x, ci.y * a.alpha_inv) : 0.0;
             }
         }
+        __syncwarp();
+        const int col0 = n0 + cg_begin * 16;
+        auto copy_out = [&](auto n_tag) {
+            constexpr int n = decltype(n_tag)::value;
+            for (int idx = lane; idx < 32 * n; idx += 32) {
+                const int row = idx / n, col = idx - row * n;
+                const int c = m0 + quarter * 32 + row;
+                if (c < a.n_chains && col0 + col < a.p2p) a.g_out[(size_t)c * a.p2p + col0 + col] = out_s[row * OS + col];
+            }
+        };
+        if (ncols == 48) copy_out(std::integral_constant<int, 48>{});
+        else copy_out(std::integral_constant<int, 32>{});
         tcgen05_fence_before();
     }
     __syncthreads();
@@ -420,6 +532,23 @@ template <int S> inline int i8_chunks(int p2) { return (p2 + I8Shape<S>::NC - 1)
 inline size_t i8_vslice_smem(int xs) { return (size_t)2 * kI8VsRows * xs * 8 + 256 * 8 + 256 * 8; }
 
 #ifdef __CUDACC__
+inline size_t i8_vslice_mma_smem(int s) { return 256 * 8 + (size_t)kI8VmWarps * s * 32 * 16; }
+// position-iterate builds: DMMA variant (KS = k-steps of 4 parameters)
+template <int S>
+inline cudaError_t i8_launch_vslice_mma(const I8VsArgs& a, cudaStream_t stream) {
+    const unsigned gx = (unsigned)((a.n_chains + 31) / 32);
+    unsigned gy = 1;
+    const int units = a.n_rows_pad / 16;
+    while (gx * gy < 148 * 4 && (int)gy * 2 * kI8VmWarps <= units) gy *= 2;      // few chains: split the rows too
+    const dim3 grid(gx, gy);
+    const size_t smem = i8_vslice_mma_smem(S);
+    const int ks = (a.dim + 3) / 4;
+    if (ks <= 2) k_i8_vslice_mma<S, 2><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
+    else if (ks <= 4) k_i8_vslice_mma<S, 4><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
+    else if (ks <= 7) k_i8_vslice_mma<S, 7><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
+    else k_i8_vslice_mma<S, 8><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
+    return cudaGetLastError();
+}
 template <int S, bool CLOSING>
 inline cudaError_t i8_launch_vslice(const I8VsArgs& a, cudaStream_t stream) {
     // iterate builds: split the rows in two when that is needed to give every SM at least ~3 CTAs

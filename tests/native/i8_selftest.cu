@@ -184,15 +184,17 @@ static int test_end_to_end(int n_rows, int dim, int n_chains, double theta_sd, b
 
     int bad = 0;
     const int n_check = n_chains < 24 ? n_chains : 24;
-    for (int closing = 0; closing < 2; ++closing) {
+    for (int closing = 0; closing < 3; ++closing) {       // 0 scalar iterate kernel, 1 closing kernel, 2 DMMA iterate kernel
         CK(cudaMemset(dg, 0xff, (size_t)n_chains * P.p2p * 8));
-        if (closing) CK((i8_launch_vslice<S, true>(v, 0)));
-        else CK((i8_launch_vslice<S, false>(v, 0)));
+        CK(cudaMemset(da, 0x55, (size_t)S * a_rows * kp));
+        if (closing == 1) CK((i8_launch_vslice<S, true>(v, 0)));
+        else if (closing == 0) CK((i8_launch_vslice<S, false>(v, 0)));
+        else CK((i8_launch_vslice_mma<S>(v, 0)));
         CK(i8_launch_gemm<S>(ma, mb, g, 0));
         CK(cudaDeviceSynchronize());
         std::vector<double> hg((size_t)n_chains * P.p2p), hgrad((size_t)n_chains * dim), hll(n_chains), hcb;
         CK(cudaMemcpy(hg.data(), dg, hg.size() * 8, cudaMemcpyDeviceToHost));
-        if (closing) {
+        if (closing == 1) {
             hcb.resize((size_t)a_rows * P.n_rows_pad);
             CK(cudaMemcpy(hgrad.data(), dgrad, hgrad.size() * 8, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(hll.data(), dll, hll.size() * 8, cudaMemcpyDeviceToHost));
@@ -212,7 +214,7 @@ static int test_end_to_end(int n_rows, int dim, int n_chains, double theta_sd, b
                     for (int b = a; b < dim; ++b) G[pair_index(a, b, dim)] += vv * r[a] * r[b];
                 for (int d = 0; d < dim; ++d) gr[d] += (t - p) * r[d];
                 ll += t * f - (std::fmax(f, 0.0) + std::log1p(std::exp(-std::fabs(f))));
-                if (closing) {
+                if (closing == 1) {
                     const double cw = vv * (1.0 - 2.0 * p);
                     cbmax = std::fmax(cbmax, std::fabs(cw));
                     cberr = std::fmax(cberr, std::fabs(cw - hcb[(size_t)c * P.n_rows_pad + n]));
@@ -222,7 +224,7 @@ static int test_end_to_end(int n_rows, int dim, int n_chains, double theta_sd, b
             double err = 0.0;
             for (int k = 0; k < P.p2; ++k) { gmax = std::fmax(gmax, std::fabs(G[k])); err = std::fmax(err, std::fabs(G[k] - hg[(size_t)c * P.p2p + k])); }
             eg = std::fmax(eg, err / gmax);
-            if (closing) {
+            if (closing == 1) {
                 double m = 0, e = 0;
                 for (int d = 0; d < dim; ++d) { m = std::fmax(m, std::fabs(gr[d])); e = std::fmax(e, std::fabs(gr[d] - hgrad[(size_t)c * dim + d])); }
                 egr = std::fmax(egr, e / m);
@@ -232,11 +234,11 @@ static int test_end_to_end(int n_rows, int dim, int n_chains, double theta_sd, b
         }
         const double tol_g = S == 5 ? 2e-11 : 1e-12;
         std::printf("end-to-end S=%d N=%d D=%d C=%d theta_sd=%.2f %s: max rel err G %.3g (tol %.1g)", S, n_rows, dim, n_chains, theta_sd,
-                    closing ? "closing" : "iterate", eg, tol_g);
-        if (closing) std::printf(", grad %.3g, loglik %.3g, c_n %.3g", egr, ell, ecb);
+                    closing == 1 ? "closing" : (closing == 0 ? "iterate" : "iterate(dmma)"), eg, tol_g);
+        if (closing == 1) std::printf(", grad %.3g, loglik %.3g, c_n %.3g", egr, ell, ecb);
         std::printf("\n");
         if (!(eg < tol_g)) ++bad;
-        if (closing && !(egr < 1e-12 && ell < 1e-12 && ecb < 1e-12)) ++bad;
+        if (closing == 1 && !(egr < 1e-12 && ell < 1e-12 && ecb < 1e-12)) ++bad;
     }
     if (time_it) {
         cudaEvent_t e0, e1;
@@ -256,9 +258,10 @@ static int test_end_to_end(int n_rows, int dim, int n_chains, double theta_sd, b
         };
         const double el = (double)n_chains * P.n_rows_pad;
         timeit("vslice", [&]() { CK((i8_launch_vslice<S, false>(v, 0))); }, el * 2.0 * (dim + 20));
+        timeit("vslice_mma", [&]() { CK((i8_launch_vslice_mma<S>(v, 0))); }, el * 2.0 * (dim + 20));
         timeit("vslice_closing", [&]() { CK((i8_launch_vslice<S, true>(v, 0))); }, el * 2.0 * (2 * dim + 32));
         timeit("gemm", [&]() { CK(i8_launch_gemm<S>(ma, mb, g, 0)); }, 2.0 * (S * (S + 1) / 2) * (double)a_rows * kp * b_rows);
-        timeit("vslice+gemm", [&]() { CK((i8_launch_vslice<S, false>(v, 0))); CK(i8_launch_gemm<S>(ma, mb, g, 0)); }, 2.0 * (double)n_chains * P.n_rows * (P.p2 + dim));
+        timeit("vslice_mma+gemm", [&]() { CK((i8_launch_vslice_mma<S>(v, 0))); CK(i8_launch_gemm<S>(ma, mb, g, 0)); }, 2.0 * (double)n_chains * P.n_rows * (P.p2 + dim));
     }
     cudaFree(dx); cudaFree(dth); cudaFree(dcolmax); cudaFree(dg); cudaFree(dgrad); cudaFree(dll); cudaFree(dcb); cudaFree(dpt);
     cudaFree(da); cudaFree(db); cudaFree(dci);
