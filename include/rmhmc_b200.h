@@ -87,6 +87,19 @@ int rmhmc_set_launch_regime(rmhmc_handle* h, int regime);
  * NCCL (libnccl.so.2) is loaded at run time; not needed otherwise. */
 int rmhmc_comm_unique_id(char* out128);
 int rmhmc_comm_init(rmhmc_handle* h, int world, int rank, const char* id128);
+/* Chain-sharded runs (BASELINE.json configs[3]: every rank owns its share of the chains, X replicated, no collective
+ * on the data path): a communicator used ONLY to combine the end-of-run statistics.  Same id protocol as above. */
+int rmhmc_stats_comm_init(rmhmc_handle* h, int world, int rank, const char* id128);
+/* Combine statistics over all ranks of the statistics communicator (one ncclAllReduce; purely local without one):
+ *   ess       (n_chains x dim, from blr_ess_batched / blr_ess_ragged; NaN = frozen chain counts as 0)
+ *             -> ess_sum (dim): sum over ALL chains of all ranks (main.py:70-79 reports min/median/max of it)
+ *   samples   (n_chains x n_samples x dim, strides in doubles) -> rhat (dim): Gelman-Rubin over ALL chains of all
+ *             ranks (every rank passes the same n_samples)
+ *   scalars   (n_scalars doubles, may be NULL): summed in place (leapfrog / iteration counters)
+ * All pointers are device pointers; outputs are identical on every rank.  Synchronises the stream. */
+int rmhmc_stats_gather(rmhmc_handle* h, const double* ess, int64_t n_chains, const double* samples, int64_t n_samples,
+                       int64_t chain_stride, int64_t row_stride, double* ess_sum, double* rhat, double* scalars,
+                       int n_scalars);
 /* cudaStream_t to enqueue on (0 = legacy default stream). */
 int rmhmc_set_stream(rmhmc_handle* h, void* cuda_stream);
 
@@ -173,7 +186,8 @@ int64_t rmhmc_launch_count(const rmhmc_handle* h);
  * bracketed by events on the handle's stream.  kind: 0 metric build (position iterates),
  * 1 metric build (closing), 2 partials build (tensor mode), 3 per-chain turn (end of one leapfrog step +
  * start of the next; matrix-free: also the momentum iterates), 4 per-chain position solve / factorisation,
- * 5 quadratic-form pass, 6 leverage GEMM, 7 trace pass (matrix-free mode).  Returns accumulated
+ * 5 quadratic-form pass, 6 leverage GEMM, 7 trace pass (matrix-free mode), 8 / 9 the two kernels of the INT8 metric
+ * build (v digits, tcgen05 GEMM; their sum is also counted under 0 / 1).  Returns accumulated
  * milliseconds and launch count since the last reset; synchronises. */
 int rmhmc_profile_enable(rmhmc_handle* h, int enable);
 int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches);
@@ -185,6 +199,8 @@ int hmc_configure(rmhmc_handle* h, int n_leapfrog, double step_size);
 int hmc_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const double* z,
                  const double* u_step, const double* u_acc);
 int hmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
+/* n_rounds free-running rounds without synchronising; one HMC round = one leapfrog step (hmc.py:51-62) of every chain. */
+int hmc_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop);
 
 /* ---- manifold MALA / simplified manifold MALA -------------------------------------------------
  * MATLAB-only in the reference: code/authors_code/Bayes_Log_Reg/MCMC/BLR_mMALA.m:159-330 and
@@ -200,6 +216,7 @@ int hmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
 int mmala_chains_init(rmhmc_handle* h, int64_t n_chains, const double* theta0, int simplified, double step_size);
 int mmala_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const double* z, const double* u_acc);
 int mmala_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
+int mmala_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop);     /* one round = one iteration of every chain */
 
 /* ---- tools.py:32-74 batched ------------------------------------------------------------------ */
 /* ESS of every (chain, parameter) series: samples (n_chains x n_samples x dim) with the given
@@ -219,6 +236,11 @@ int blr_autocorr(int device, void* cuda_stream, const double* series, int64_t n_
 int blr_ess_ragged(int device, void* cuda_stream, const double* samples, int64_t n_chains,
                    int64_t max_samples, int dim, int64_t chain_stride, int64_t row_stride,
                    const int64_t* starts, const int64_t* counts, double* ess);
+
+/* Issue peaks of the two tensor paths of this library, measured live on `device` (host pointers, either may be NULL):
+ * FP64 DMMA.8x8x4 in TFLOP/s and tcgen05.mma.kind::i8 (128x256x32, TMEM accumulators) in TOP/s.  bench.py's roofline
+ * denominators (MEASURED_PEAKS.json has neither).  Synchronises. */
+int blr_device_peaks(int device, void* cuda_stream, double* fp64_dmma_tflops, double* int8_tcgen05_tops);
 
 /* Gelman-Rubin Rhat per parameter over n_chains >= 2 chains of n_samples >= 2 samples (same layout as above); rhat (dim).
  * Not in the reference (its main.py:70-79 only reports ESS); SURVEY.md 8c: classic estimator, W = mean of the chain

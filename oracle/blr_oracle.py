@@ -394,7 +394,7 @@ def rmhmc_chain(xx, t, tape: DrawTape, n_iter=6000, burn_in=1000, n_leapfrog=6,
 
 # --------------------------------------------------------------------------- HMC
 def hmc_chain(xx, t, tape: DrawTape, n_iter=6000, burn_in=1000, n_leapfrog=100,
-              step_size=0.14, alpha=ALPHA, record=False):
+              step_size=0.14, alpha=ALPHA, record=False, w0=None):
     """One Euclidean-HMC chain under a draw tape; restates hmc.py:12-99.
 
     ``tape.z_dir`` is unused (HMC has no direction draw).  Row 0 of ``samples`` is
@@ -403,7 +403,7 @@ def hmc_chain(xx, t, tape: DrawTape, n_iter=6000, burn_in=1000, n_leapfrog=100,
     n, d = xx.shape
     mass = np.eye(d)
     inv_mass = np.linalg.inv(mass)
-    w = np.zeros((d, 1))
+    w = np.zeros((d, 1)) if w0 is None else np.array(w0, dtype=float).reshape(d, 1)      # w0: continue a chain (bench.py)
     samples = np.zeros((n_iter - burn_in, d))
     cur_ljl = log_joint(xx, t, w, alpha)
     accepted = np.zeros(n_iter, dtype=bool)
@@ -465,7 +465,7 @@ def _mmala_terms(xx, t, w, alpha, simplified):
 
 
 def mmala_chain(xx, t, tape: DrawTape, n_iter=10000, burn_in=5000, step_size=1.0, alpha=ALPHA, simplified=False,
-                record=False):
+                record=False, w0=None):
     """One (simplified) manifold-MALA chain under a draw tape; restates the MATLAB original
     ``code/authors_code/Bayes_Log_Reg/MCMC/BLR_mMALA.m:159-330`` (``BLR_mMALA_Simp.m:170-290``).
 
@@ -477,7 +477,7 @@ def mmala_chain(xx, t, tape: DrawTape, n_iter=10000, burn_in=5000, step_size=1.0
     ``(randn(1,D) * chol(S))'`` is ``L z`` with the lower factor ``L = R'``.
     """
     n, d = xx.shape
-    w = np.zeros((d, 1))                                                   # :165
+    w = np.zeros((d, 1)) if w0 is None else np.array(w0, dtype=float).reshape(d, 1)   # :165 (w0: continue a chain)
     samples = np.zeros((n_iter - burn_in, d))
     cur_ljl = log_joint(xx, t, w, alpha)                                   # :169-172
     cur_g, cur_inv_g, cur_first, cur_second, cur_third = _mmala_terms(xx, t, w, alpha, simplified)

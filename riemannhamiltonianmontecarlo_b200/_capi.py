@@ -29,6 +29,10 @@ SIGNATURES = {
     "rmhmc_comm_unique_id": (c_int, [c_char_p]),
     "rmhmc_comm_init": (c_int, [c_void_p, c_int, c_int, c_char_p]),
     "rmhmc_set_stream": (c_int, [c_void_p, c_void_p]),
+    "rmhmc_stats_comm_init": (c_int, [c_void_p, c_int, c_int, c_char_p]),
+    "rmhmc_stats_gather": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                   c_void_p, c_int]),
+    "blr_device_peaks": (c_int, [c_int, c_void_p, POINTER(c_double), POINTER(c_double)]),
     "rmhmc_metric": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rmhmc_metric_partials": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "rmhmc_chol_logdet": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -50,9 +54,11 @@ SIGNATURES = {
     "hmc_configure": (c_int, [c_void_p, c_int, c_double]),
     "hmc_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "hmc_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
+    "hmc_advance": (c_int, [c_void_p, c_int64, c_int64]),
     "mmala_chains_init": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_double]),
     "mmala_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "mmala_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
+    "mmala_advance": (c_int, [c_void_p, c_int64, c_int64]),
     "blr_ess_batched": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p]),
     "blr_autocorr": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "blr_rhat": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p]),

@@ -22,6 +22,7 @@
 #include "momfp_kernel.cuh"
 #include "pass_kernel.cuh"
 #include "mmala_kernels.cuh"
+#include "peaks.cuh"
 #include "tbuild_kernel.cuh"
 
 using namespace rmhmc;
@@ -105,7 +106,9 @@ struct rmhmc_handle {
     double* t_tmp = nullptr;        // [C][P3p] contiguous partials of the last build (sharded mode)
     double* split_buf = nullptr;    // partial outputs of row-split metric builds / passes
     size_t split_cap = 0;
-    ProfSlot prof[8];
+    ProfSlot prof[10];
+    ncclComm_t stats_comm = nullptr;   // chain-sharded runs: end-of-run statistics only (rmhmc_stats_comm_init)
+    int stats_world = 1;
     // INT8-slice metric build on tcgen05 (i8_metric.cuh): digit planes of KR2(X)^T per data set, of V per chain set
     int metric_mode = RMHMC_METRIC_FP64_DMMA;
     int i8_slices = 5;              // digits per operand (RMHMC_I8_SLICES = 5 | 6)
@@ -928,14 +931,18 @@ int i8_build_s(rmhmc_handle* h, int64_t C, const double* theta, signed char* a8,
     v.x = h->x_pad; v.theta = theta; v.a8 = a8; v.plane_stride = (size_t)a_rows * h->i8_kp; v.kp = h->i8_kp;
     v.n_chains = (int)C; v.n_rows = (int)h->n_rows; v.n_rows_pad = h->n_rows_pad; v.dim = h->dim; v.xs = h->xs;
     cudaError_t e;
-    if (cl) {
-        v.grad_out = cl->grad_out; v.loglik_out = cl->loglik_out; v.cbuf = cl->cbuf;
-        v.cw_cur = cl->cw_cur; v.cw_flip = cl->cw_flip; v.cw_slot = cl->cw_slot;
-        e = i8_launch_vslice<S, true>(v, h->stream);
-    } else {
-        e = i8_launch_vslice_mma<S>(v, h->stream);
+    {
+        Bracket bv(h, 8);
+        if (cl) {
+            v.grad_out = cl->grad_out; v.loglik_out = cl->loglik_out; v.cbuf = cl->cbuf;
+            v.cw_cur = cl->cw_cur; v.cw_flip = cl->cw_flip; v.cw_slot = cl->cw_slot;
+            e = i8_launch_vslice_mma_closing<S>(v, h->stream);
+        } else {
+            e = i8_launch_vslice_mma<S>(v, h->stream);
+        }
     }
     if (e != cudaSuccess) return fail(h, RMHMC_E_CUDA, std::string("k_i8_vslice: ") + cudaGetErrorString(e));
+    Bracket bg(h, 9);
     I8GemmArgs g{};
     g.g_out = g_out; g.colinfo = h->colinfo; g.alpha_inv = h->shard_rank == 0 ? 1.0 / h->alpha : 0.0;
     g.n_chains = (int)C; g.p2 = h->p2; g.p2p = h->p2p; g.k_blocks = h->i8_kp / kI8BlockK;
@@ -1285,6 +1292,7 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
     }
     if (const char* e = std::getenv("RMHMC_I8_SLICES")) h->i8_slices = std::atoi(e) == 6 ? 6 : 5;
     if (i8_setup(h) != RMHMC_OK) return bail(RMHMC_E_CUDA);
+    if (h->i8_ok) h->metric_mode = RMHMC_METRIC_INT8_TCGEN05;       // default where the shape allows it (RMHMC_METRIC_MODE=dmma overrides)
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
     h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
@@ -1310,6 +1318,7 @@ void rmhmc_destroy(rmhmc_handle* h) {
     drain_profile(h);
     free_chains(h);
     if (h->comm) nccl_api().CommDestroy(h->comm);
+    if (h->stats_comm) nccl_api().CommDestroy(h->stats_comm);
     cudaFree(h->b8); cudaFree(h->colinfo); cudaFree(h->colmax); cudaFree(h->split_buf); cudaFree(h->kr2n); cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->kr2t); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
     cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
     delete h;
@@ -1397,6 +1406,61 @@ int rmhmc_comm_init(rmhmc_handle* h, int world, int rank, const char* id128) {
     if (r != ncclSuccess) { h->comm = nullptr; return fail(h, RMHMC_E_CUDA, std::string("ncclCommInitRank: ") + api.GetErrorString(r)); }
     h->shard_world = world; h->shard_rank = rank;
     return RMHMC_OK;
+}
+
+int rmhmc_stats_comm_init(rmhmc_handle* h, int world, int rank, const char* id128) {
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_stats_comm_init: bad arguments") : RMHMC_E_INVALID;
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(h, RMHMC_E_UNSUPPORTED, "rmhmc_stats_comm_init: libnccl.so.2 not available");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->stats_comm) { api.CommDestroy(h->stats_comm); h->stats_comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclResult_t r = api.CommInitRank(&h->stats_comm, world, id, rank);
+    if (r != ncclSuccess) { h->stats_comm = nullptr; return fail(h, RMHMC_E_CUDA, std::string("ncclCommInitRank: ") + api.GetErrorString(r)); }
+    h->stats_world = world;
+    return RMHMC_OK;
+}
+
+int rmhmc_stats_gather(rmhmc_handle* h, const double* ess, int64_t n_chains, const double* samples, int64_t n_samples,
+                       int64_t chain_stride, int64_t row_stride, double* ess_sum, double* rhat, double* scalars, int n_scalars) {
+    if (!h || n_chains <= 0 || n_scalars < 0 || (n_scalars > 0 && !scalars) || (rhat && (!samples || n_samples < 2)))
+        return h ? fail(h, RMHMC_E_INVALID, "rmhmc_stats_gather: bad arguments") : RMHMC_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int D = h->dim;
+    // one exchange: [ess sums D | Rhat moments 3 D | chain count 1 | caller scalars]
+    const size_t n = (size_t)4 * D + 1 + n_scalars;
+    double* buf = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&buf, n * 8));
+    CUDA_TRY(h, cudaMemsetAsync(buf, 0, n * 8, h->stream));
+    if (ess && ess_sum) k_ess_colsum<<<D, kEssThreads, 0, h->stream>>>(ess, (long long)n_chains, D, buf);
+    if (rhat) k_rhat<<<D, kEssThreads, 0, h->stream>>>(samples, (size_t)chain_stride, (size_t)row_stride, (int)n_chains, (int)n_samples, nullptr, buf + D);
+    k_fill<<<1, 32, 0, h->stream>>>(buf + 4 * D, 1, (double)n_chains);
+    if (n_scalars) cudaMemcpyAsync(buf + 4 * D + 1, scalars, (size_t)n_scalars * 8, cudaMemcpyDeviceToDevice, h->stream);
+    int rc = RMHMC_OK;
+    if (h->stats_comm) {
+        ncclResult_t r = nccl_api().AllReduce(buf, buf, n, ncclDouble, ncclSum, h->stats_comm, h->stream);
+        if (r != ncclSuccess) rc = fail(h, RMHMC_E_CUDA, std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r));
+    }
+    if (!rc) {
+        double c_total = 0.0;
+        cudaMemcpyAsync(&c_total, buf + 4 * D, 8, cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        if (ess && ess_sum) cudaMemcpyAsync(ess_sum, buf, (size_t)D * 8, cudaMemcpyDeviceToDevice, h->stream);
+        if (rhat) k_rhat_finish<<<blocks_for(D, 128), 128, 0, h->stream>>>(buf + D, D, c_total, (int)n_samples, rhat);
+        if (n_scalars) cudaMemcpyAsync(scalars, buf + 4 * D + 1, (size_t)n_scalars * 8, cudaMemcpyDeviceToDevice, h->stream);
+        h->launches += 3;
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { h->err = std::string("rmhmc_stats_gather: ") + cudaGetErrorString(e); rc = RMHMC_E_CUDA; }
+    }
+    cudaFree(buf);
+    return rc;
+}
+
+int blr_device_peaks(int device, void* cuda_stream, double* fp64_dmma_tflops, double* int8_tcgen05_tops) {
+    if (cudaSetDevice(device) != cudaSuccess) return RMHMC_E_CUDA;
+    return measure_device_peaks(reinterpret_cast<cudaStream_t>(cuda_stream), fp64_dmma_tflops, int8_tcgen05_tops) == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
 }
 
 int rmhmc_set_stream(rmhmc_handle* h, void* cuda_stream) {
@@ -1610,6 +1674,31 @@ int rmhmc_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop) {
     return rmhmc_rounds(h, n_rounds);
 }
 
+// free-running rounds of the other samplers: HMC round = one leapfrog step of every chain (hmc.py:51-62), mMALA round =
+// one iteration of every chain
+int hmc_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop) {
+    if (!h || n_rounds < 0) return h ? fail(h, RMHMC_E_INVALID, "hmc_advance: bad arguments") : RMHMC_E_INVALID;
+    if (h->n_chains <= 0 || !h->is_hmc) return fail(h, RMHMC_E_STATE, "hmc_advance: call hmc_chains_init first");
+    if (!h->configured || !h->rng_set) return fail(h, RMHMC_E_STATE, "hmc_advance: configure and set a tape / philox seed first");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->P.rng_mode == 0 && it_stop > h->tape_base + h->tape_window) it_stop = h->tape_base + h->tape_window;
+    h->P.it_stop = it_stop;
+    for (int64_t r = 0; r < n_rounds; ++r) {
+        int rc = hmc_round(h);
+        if (rc) return rc;
+    }
+    return RMHMC_OK;
+}
+int mmala_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop) {
+    if (!h || n_rounds < 0) return h ? fail(h, RMHMC_E_INVALID, "mmala_advance: bad arguments") : RMHMC_E_INVALID;
+    if (h->n_chains <= 0 || !h->is_mmala) return fail(h, RMHMC_E_STATE, "mmala_advance: call mmala_chains_init first");
+    if (!h->rng_set) return fail(h, RMHMC_E_STATE, "mmala_advance: set a tape / philox seed first");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->P.rng_mode == 0 && it_stop > h->tape_base + h->tape_window) it_stop = h->tape_base + h->tape_window;
+    h->P.it_stop = it_stop;
+    return mmala_rounds(h, n_rounds);
+}
+
 int rmhmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done) {
     if (!h) return RMHMC_E_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -1736,7 +1825,7 @@ int rmhmc_profile_enable(rmhmc_handle* h, int enable) {
     return RMHMC_OK;
 }
 int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches) {
-    if (!h || kind < 0 || kind > 7) return RMHMC_E_INVALID;
+    if (!h || kind < 0 || kind > 9) return RMHMC_E_INVALID;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     drain_profile(h);
     if (ms) *ms = h->prof[kind].ms;

@@ -121,8 +121,11 @@ __global__ void k_acf_lag0(double* acf, int n_lag, int n_series) {
 // Gelman-Rubin potential scale reduction per parameter over C chains of S samples (not part of the reference;
 // SURVEY.md 8c specifies the classic estimator: W = mean_c var_c (ddof = 1), B/S = var_c(mean_c) (ddof = 1),
 // Rhat = sqrt(((S-1)/S W + B/S) / W)).  One CTA per parameter; thread i takes chains i, i + 128, ...; sums in fixed order.
+// moments_out (optional, [3][D]): sum_c mean_c, sum_c mean_c^2, sum_c var_c -- the sufficient statistics that ranks
+// holding different chains add up (rmhmc_stats_gather) before k_rhat_finish.
 __global__ void __launch_bounds__(kEssThreads) k_rhat(const double* __restrict__ samples, size_t chain_stride, size_t row_stride,
-                                                       int C, int S, double* __restrict__ rhat_out) {
+                                                       int C, int S, double* __restrict__ rhat_out,
+                                                       double* __restrict__ moments_out = nullptr) {
     __shared__ double sm[3][kEssThreads];
     const int d = blockIdx.x, tid = threadIdx.x;
     double s_mean = 0.0, s_mean2 = 0.0, s_var = 0.0;
@@ -141,10 +144,29 @@ __global__ void __launch_bounds__(kEssThreads) k_rhat(const double* __restrict__
     if (tid == 0) {
         double a = 0.0, b = 0.0, w = 0.0;
         for (int i = 0; i < kEssThreads; ++i) { a += sm[0][i]; b += sm[1][i]; w += sm[2][i]; }
+        if (moments_out) { moments_out[d] = a; moments_out[gridDim.x + d] = b; moments_out[2 * gridDim.x + d] = w; }
         w /= C;
         const double b_over_s = (b - a * a / C) / (C - 1);
-        rhat_out[d] = sqrt(((double)(S - 1) / S * w + b_over_s) / w);
+        if (rhat_out) rhat_out[d] = sqrt(((double)(S - 1) / S * w + b_over_s) / w);
     }
+}
+// Rhat from moments summed over all ranks: moments [3][D], c_total chains of S samples each
+__global__ void k_rhat_finish(const double* __restrict__ moments, int D, double c_total, int S, double* __restrict__ rhat_out) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const double a = moments[d], b = moments[D + d], w = moments[2 * D + d] / c_total;
+    const double b_over_s = (b - a * a / c_total) / (c_total - 1.0);
+    rhat_out[d] = sqrt(((double)(S - 1) / S * w + b_over_s) / w);
+}
+// out[d] = sum_c ess[c][d] with NaN (a chain frozen over the whole window: 0/0 in tools.py:27) counted as 0; fixed order
+__global__ void __launch_bounds__(kEssThreads) k_ess_colsum(const double* __restrict__ ess, long long C, int D, double* __restrict__ out) {
+    __shared__ double sm[kEssThreads];
+    const int d = blockIdx.x, tid = threadIdx.x;
+    double s = 0.0;
+    for (long long c = tid; c < C; c += kEssThreads) { const double v = ess[(size_t)c * D + d]; s += (v == v) ? v : 0.0; }
+    sm[tid] = s;
+    __syncthreads();
+    if (tid == 0) { double a = 0.0; for (int i = 0; i < kEssThreads; ++i) a += sm[i]; out[d] = a; }
 }
 #endif
 

@@ -378,6 +378,179 @@ __global__ void __launch_bounds__(kI8VmWarps * 32, 2) k_i8_vslice_mma(I8VsArgs a
     }
 }
 
+// Closing variant on the FP64 tensor path: as above for 16 chains per CTA (two m-tiles, so that the gradient accumulators fit
+// the register file), plus X^T (t - p) as a second DMMA contraction (R's accumulator fragment -> A fragment by four
+// shuffles, as in pass_kernel.cuh), the log-likelihood and c_n.  Every warp sweeps its own rows; the warps' partial
+// gradients / log-likelihoods are added in warp order at the end (fixed order: bit-reproducible).
+constexpr int kI8VcWarps = 6;      // 2 CTAs x 6 warps per SM at <= 168 registers (gradient accumulators + Theta fragments)
+template <int S, int KS>
+__global__ void __launch_bounds__(kI8VcWarps * 32, 2) k_i8_vslice_mma_closing(I8VsArgs a) {
+    constexpr int MT = 2, DT = (KS + 1) / 2;             // m-tiles of 8 chains; parameter tiles of 8
+    constexpr unsigned kFull = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* exp_tab = reinterpret_cast<double*>(smem_raw);                                   // [256]
+    double* log_tab = exp_tab + 256;                                                         // [128][2]
+    double* red = log_tab + 256;                                                             // [warps][16][DT * 8 + 1]
+    unsigned char* out_all = reinterpret_cast<unsigned char*>(red + kI8VcWarps * 16 * (DT * 8 + 1));   // [warps][S][16][16]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int chain0 = blockIdx.x * (MT * 8);
+    const int xs = a.xs, tcol = xs - 1;
+    for (int i = tid; i < 256; i += kI8VcWarps * 32) exp_tab[i] = exp_table_entry(i);
+    if (tid < 128) log_table_entry(tid, log_tab[2 * tid], log_tab[2 * tid + 1]);
+    __syncthreads();
+    unsigned char* out_w = out_all + (size_t)warp * S * 16 * 16;
+
+    double th[MT][KS];
+    double* crow[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const int c = chain0 + m * 8 + g;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int d = ks * 4 + q;
+            th[m][ks] = (c < a.n_chains && d < a.dim) ? a.theta[(size_t)c * a.dim + d] : 0.0;
+        }
+        crow[m] = nullptr;
+        if (c < a.n_chains) {
+            const size_t slot = a.cw_cur ? (size_t)(a.cw_cur[c] ^ a.cw_flip) * a.cw_slot : 0;
+            crow[m] = a.cbuf + slot + (size_t)c * a.n_rows_pad;
+        }
+    }
+    double gacc[MT][DT][2], ll[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        ll[m] = 0.0;
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) gacc[m][dt][0] = gacc[m][dt][1] = 0.0;
+    }
+    const int src0 = g * 4 + (q >> 1), src1 = src0 + 2;      // shuffle sources of the C -> A fragment conversion
+    const bool odd = q & 1;
+    const int units = a.n_rows_pad / 16;
+    auto load_b = [&](int row0, double (&b)[KS]) {
+        const double* xr = a.x + (size_t)(row0 + g) * xs + q;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) b[ks] = ks * 4 < xs ? __ldg(xr + ks * 4) : 0.0;
+    };
+    double bnext[KS];
+    int u = warp;
+    if (u < units) load_b(u * 16, bnext);
+    for (; u < units; u += kI8VcWarps) {
+        const int row0 = u * 16;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int rt = row0 + nt * 8;                  // first row of this 8-row tile
+            double b[KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) b[ks] = bnext[ks];
+            if (nt == 0) load_b(row0 + 8, bnext);
+            else if (u + kI8VcWarps < units) load_b((u + kI8VcWarps) * 16, bnext);
+            // labels of this lane's two rows and the gradient contraction's X fragments: X[rt + 4 kk + q][8 dt + g]
+            const double t0 = __ldg(a.x + (size_t)(rt + 2 * q) * xs + tcol), t1 = __ldg(a.x + (size_t)(rt + 2 * q + 1) * xs + tcol);
+            double xg[2][DT];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                for (int dt = 0; dt < DT; ++dt) {
+                    const int dcol = dt * 8 + g;
+                    xg[kk][dt] = dcol < a.dim ? __ldg(a.x + (size_t)(rt + kk * 4 + q) * xs + dcol) : 0.0;
+                }
+            double f[MT][2];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) f[m][0] = f[m][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int m = 0; m < MT; ++m) dmma884(f[m][0], f[m][1], th[m][ks], b[ks]);
+            double ev[4], qq[4], eq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ev[i] = fast_exp_nonpos(-fabs(f[i >> 1][i & 1]), exp_tab);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qq[i] = fast_rcp_1to2(1.0 + ev[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) eq[i] = ev[i] * qq[i];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                double vv[2], rr[2], cc[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int i = 2 * m + j;
+                    const double fv = f[m][j];
+                    const bool pos = fv >= 0.0;
+                    const double p = pos ? qq[i] : eq[i];
+                    const double om = pos ? eq[i] : qq[i];       // 1 - p
+                    vv[j] = eq[i] * qq[i];                       // p (1 - p)
+                    const double t = j ? t1 : t0;
+                    const bool ovf = fv > 709.782712893384;      // the reference's exp(f) overflows: NaN gradient, -inf log-likelihood
+                    rr[j] = ovf ? __longlong_as_double(0x7ff8000000000000LL) : t - p;
+                    cc[j] = vv[j] * (om - p);
+                    if (rt + 2 * q + j < a.n_rows) {
+                        const double l1pe = ovf ? __longlong_as_double(0x7ff0000000000000LL) : fmax(fv, 0.0) + fast_log1p_01(ev[i], log_tab);
+                        ll[m] += t * fv - l1pe;
+                    }
+                }
+                if (crow[m]) *reinterpret_cast<double2*>(crow[m] + rt + 2 * q) = make_double2(cc[0], cc[1]);
+                unsigned lo0, hi0, lo1, hi1;
+                i8_digits<S>(vv[0], lo0, hi0);
+                i8_digits<S>(vv[1], lo1, hi1);
+                unsigned char* dst = out_w + (size_t)(m * 8 + g) * 16 + nt * 8 + 2 * q;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    const int byte = S - 1 - s;
+                    const unsigned bsel = byte & 3;
+                    const unsigned pr = __byte_perm(byte < 4 ? lo0 : hi0, byte < 4 ? lo1 : hi1, bsel | ((4 + bsel) << 4));
+                    *reinterpret_cast<unsigned short*>(dst + (size_t)s * 16 * 16) = (unsigned short)((pr & 0xFFFFu) ^ 0x8080u);
+                }
+                // X^T (t - p): R (chain g; rows 2q, 2q+1) -> A fragments (chain g; row q) of the tile's two 4-row k-steps
+                const double e0 = __shfl_sync(kFull, rr[0], src0), o0 = __shfl_sync(kFull, rr[1], src0);
+                const double e1 = __shfl_sync(kFull, rr[0], src1), o1 = __shfl_sync(kFull, rr[1], src1);
+                const double ar0 = odd ? o0 : e0, ar1 = odd ? o1 : e1;
+#pragma unroll
+                for (int dt = 0; dt < DT; ++dt) {
+                    dmma884(gacc[m][dt][0], gacc[m][dt][1], ar0, xg[0][dt]);
+                    dmma884(gacc[m][dt][0], gacc[m][dt][1], ar1, xg[1][dt]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < MT * 8) {
+            const int c = chain0 + lane;
+            if (c < a.n_chains) {
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    *reinterpret_cast<uint4*>(a.a8 + (size_t)s * a.plane_stride + (size_t)c * a.kp + row0) =
+                        *reinterpret_cast<const uint4*>(out_w + ((size_t)s * 16 + lane) * 16);
+            }
+        }
+        __syncwarp();
+    }
+    // ---- the warps' partial gradients (accumulator layout: chain 8 m + g, parameters 8 dt + 2q, +1) and log-likelihoods
+    constexpr int RS = DT * 8 + 1;
+    double* my = red + (size_t)warp * 16 * RS;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) {
+            my[(m * 8 + g) * RS + dt * 8 + 2 * q] = gacc[m][dt][0];
+            my[(m * 8 + g) * RS + dt * 8 + 2 * q + 1] = gacc[m][dt][1];
+        }
+        double v = ll[m];
+        v += __shfl_xor_sync(kFull, v, 1);
+        v += __shfl_xor_sync(kFull, v, 2);
+        if (q == 0) my[(m * 8 + g) * RS + DT * 8] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < 16 * RS; i += kI8VcWarps * 32) {
+        const int ci = i / RS, d = i - ci * RS, c = chain0 + ci;
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kI8VcWarps; ++w) sum += red[(size_t)w * 16 * RS + i];
+        if (c < a.n_chains) {
+            if (d < a.dim) a.grad_out[(size_t)c * a.dim + d] = sum;
+            else if (d == DT * 8) a.loglik_out[c] = sum;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the GEMM
 template <int S>
 __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_constant__ CUtensorMap map_a,
@@ -547,6 +720,20 @@ inline cudaError_t i8_launch_vslice_mma(const I8VsArgs& a, cudaStream_t stream) 
     else if (ks <= 4) k_i8_vslice_mma<S, 4><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
     else if (ks <= 7) k_i8_vslice_mma<S, 7><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
     else k_i8_vslice_mma<S, 8><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+template <int KS> inline size_t i8_vslice_mma_closing_smem(int s) {
+    return (size_t)(256 + 256 + kI8VcWarps * 16 * ((KS + 1) / 2 * 8 + 1)) * 8 + (size_t)kI8VcWarps * s * 16 * 16;
+}
+// closing builds: DMMA variant, 16 chains per CTA
+template <int S>
+inline cudaError_t i8_launch_vslice_mma_closing(const I8VsArgs& a, cudaStream_t stream) {
+    const unsigned gx = (unsigned)((a.n_chains + 15) / 16);
+    const int ks = (a.dim + 3) / 4;
+    if (ks <= 2) k_i8_vslice_mma_closing<S, 2><<<gx, kI8VcWarps * 32, i8_vslice_mma_closing_smem<2>(S), stream>>>(a);
+    else if (ks <= 4) k_i8_vslice_mma_closing<S, 4><<<gx, kI8VcWarps * 32, i8_vslice_mma_closing_smem<4>(S), stream>>>(a);
+    else if (ks <= 7) k_i8_vslice_mma_closing<S, 7><<<gx, kI8VcWarps * 32, i8_vslice_mma_closing_smem<7>(S), stream>>>(a);
+    else k_i8_vslice_mma_closing<S, 8><<<gx, kI8VcWarps * 32, i8_vslice_mma_closing_smem<8>(S), stream>>>(a);
     return cudaGetLastError();
 }
 template <int S, bool CLOSING>

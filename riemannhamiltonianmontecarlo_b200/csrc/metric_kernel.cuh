@@ -104,6 +104,7 @@ __device__ __forceinline__ double fast_exp_nonpos(double x, const double* __rest
     const double kHi = 0.00270760617331689;              // ln2/256, upper 32 bits (n * kHi is exact)
     const double kLo = 7.453964567463233e-13;            // ln2/256 - kHi
     const double kMagic = 6755399441055744.0;            // 1.5 * 2^52
+    x = x < -746.0 ? -746.0 : x;                          // e^-746 = 0 in FP64; keeps n inside int32 for any finite x (NaN passes)
     double t = fma(x, kInv, kMagic);
     int n = __double2loint(t);
     double nf = t - kMagic;

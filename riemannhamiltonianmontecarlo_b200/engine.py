@@ -31,6 +31,29 @@ def shard_rows(n_rows: int, rank: int, world: int):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def shard_chains(n_chains: int, rank: int, world: int):
+    """Contiguous chain range [begin, end) of rank ``rank`` when ``n_chains`` chains are partitioned over ``world``
+    GPUs (BASELINE.json configs[3]); ``begin`` is also the rank's Philox ``chain_offset``."""
+    return shard_rows(n_chains, rank, world)
+
+
+PROFILE_KINDS = ["metric_fp", "metric_closing", "partials", "chain_turn", "chain_solve", "quad_pass", "leverage_gemm",
+                 "trace_pass", "i8_vslice", "i8_gemm"]
+
+
+def device_peaks(device=0):
+    """(FP64 DMMA TFLOP/s, INT8 tcgen05 TOP/s) issue peaks measured live on ``device`` (blr_device_peaks)."""
+    torch = _capi.require_cuda()
+    lib = _capi.load()
+    dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+    a, b = ctypes.c_double(0), ctypes.c_double(0)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rc = lib.blr_device_peaks(dev.index or 0, c_void_p(stream), ctypes.byref(a), ctypes.byref(b))
+    if rc != 0:
+        raise _capi.RmhmcError(f"blr_device_peaks failed (code {rc})")
+    return a.value, b.value
+
+
 class LogisticData:
     """``(XX, t)`` of the Bayesian logistic regression, resident on one GPU.
 
@@ -111,6 +134,42 @@ class LogisticData:
         if world > 1:
             dist.broadcast_object_list(box, src=0)
         _capi.check(self._lib.rmhmc_comm_init(self.handle, int(world), int(rank), box[0]), self.handle, "rmhmc_comm_init")
+
+    def init_stats_comm(self, rank: int, world: int):
+        """NCCL communicator for the end-of-run statistics of a chain-sharded run (``stats_gather``); the unique id
+        travels over ``torch.distributed`` (plumbing)."""
+        import torch.distributed as dist
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            rc = self._lib.rmhmc_comm_unique_id(buf)
+            if rc != 0:
+                raise _capi.RmhmcError(f"rmhmc_comm_unique_id failed (code {rc})")
+        box = [buf.raw]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        _capi.check(self._lib.rmhmc_stats_comm_init(self.handle, int(world), int(rank), box[0]), self.handle,
+                    "rmhmc_stats_comm_init")
+
+    def stats_gather(self, ess=None, samples=None, scalars=None):
+        """Sum of the per-chain ESS (C, D) over all chains of all ranks, Gelman-Rubin Rhat of the sample window
+        (C, S, D) over all chains of all ranks, and the element-wise sum of ``scalars`` -- one NCCL all-reduce inside the
+        library (rmhmc_stats_gather).  Returns (ess_sum (D,), rhat (D,), scalars) as device tensors (None where no input)."""
+        t = self.torch
+        n_chains = ess.shape[0] if ess is not None else samples.shape[0]
+        ess_sum = t.zeros(self.dim, dtype=t.float64, device=self.device) if ess is not None else None
+        rhat = t.zeros(self.dim, dtype=t.float64, device=self.device) if samples is not None else None
+        if ess is not None:
+            ess = ess.contiguous()
+        n_samples = cs = rs = 0
+        if samples is not None:
+            assert samples.dim() == 3 and samples.stride(2) == 1
+            n_samples, cs, rs = samples.shape[1], samples.stride(0), samples.stride(1)
+        if scalars is not None:
+            scalars = scalars.to(t.float64).contiguous()
+        _capi.check(self._lib.rmhmc_stats_gather(self.handle, _ptr(ess), int(n_chains), _ptr(samples), int(n_samples), int(cs),
+                                                 int(rs), _ptr(ess_sum), _ptr(rhat), _ptr(scalars),
+                                                 0 if scalars is None else scalars.numel()), self.handle, "rmhmc_stats_gather")
+        return ess_sum, rhat, scalars
 
     def update(self, xx_dev, t_dev):
         """Re-upload the design matrix / labels from device tensors of the bound shape."""
@@ -255,6 +314,24 @@ class _SamplerBase:
     def launch_count(self) -> int:
         return int(self._lib.rmhmc_launch_count(self.h))
 
+    _advance_fn = "rmhmc_advance"
+
+    def advance(self, n_rounds: int, it_stop: int = HUGE_ITERS):
+        """Enqueue ``n_rounds`` rounds without synchronising (free-running chains)."""
+        _capi.check(getattr(self._lib, self._advance_fn)(self.h, int(n_rounds), int(it_stop)), self.h, self._advance_fn)
+
+    def profile(self, enable: bool):
+        _capi.check(self._lib.rmhmc_profile_enable(self.h, 1 if enable else 0), self.h, "profile_enable")
+
+    def profile_read(self):
+        """{kind: (milliseconds, launches)} per kernel class."""
+        out = {}
+        for k, nm in enumerate(PROFILE_KINDS):
+            ms, n = ctypes.c_double(0), c_int64(0)
+            _capi.check(self._lib.rmhmc_profile_read(self.h, k, ctypes.byref(ms), ctypes.byref(n)), self.h, "profile_read")
+            out[nm] = (ms.value, n.value)
+        return out
+
 
 class RMHMCSampler(_SamplerBase):
     """C independent RMHMC chains; every ``round`` advances each chain by one generalized leapfrog step."""
@@ -284,29 +361,12 @@ class RMHMCSampler(_SamplerBase):
         _capi.check(self._lib.rmhmc_run(self.h, int(it_stop), ctypes.byref(rounds)), self.h, "rmhmc_run")
         return rounds.value
 
-    def advance(self, n_rounds: int, it_stop: int = HUGE_ITERS):
-        """Enqueue ``n_rounds`` rounds without synchronising (free-running chains)."""
-        _capi.check(self._lib.rmhmc_advance(self.h, int(n_rounds), int(it_stop)), self.h, "rmhmc_advance")
-
-    def profile(self, enable: bool):
-        _capi.check(self._lib.rmhmc_profile_enable(self.h, 1 if enable else 0), self.h, "profile_enable")
-
-    def profile_read(self):
-        """{kind: (milliseconds, launches)} per kernel class."""
-        names = ["metric_fp", "metric_closing", "partials", "chain_turn", "chain_solve", "quad_pass", "leverage_gemm",
-                 "trace_pass"]
-        out = {}
-        for k, nm in enumerate(names):
-            ms, n = ctypes.c_double(0), c_int64(0)
-            _capi.check(self._lib.rmhmc_profile_read(self.h, k, ctypes.byref(ms), ctypes.byref(n)), self.h, "profile_read")
-            out[nm] = (ms.value, n.value)
-        return out
-
 
 class HMCSampler(_SamplerBase):
     """C independent Euclidean-HMC chains (identity mass)."""
 
     _is_hmc = True
+    _advance_fn = "hmc_advance"
 
     def __init__(self, data: LogisticData, n_chains: int, n_leapfrog: int = 100, step_size: float = 0.14, theta0=None):
         super().__init__(data, n_chains, theta0)
@@ -334,6 +394,8 @@ class MMALASampler(_SamplerBase):
 
     MATLAB-only in the reference (BLR_mMALA.m / BLR_mMALA_Simp.m); see include/rmhmc_b200.h.
     """
+
+    _advance_fn = "mmala_advance"
 
     def __init__(self, data: LogisticData, n_chains: int, step_size: float = 1.0, simplified: bool = False, theta0=None):
         lib, h, c = data._lib, data.handle, int(n_chains)

@@ -1,4 +1,4 @@
-"""Row-sharded RMHMC/HMC across ranks (NCCL all-reduce of every build) == the unsharded run.
+"""Row-sharded RMHMC/HMC across ranks (NCCL all-reduce of every build) == the unsharded run == the oracle.
 
 Launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
             --master-port 29533 tests/multi_gpu_row_shard.py
@@ -53,17 +53,25 @@ def main():
         dist.broadcast(ref, src=0)
         same = bool((ref.cpu().numpy() == sharded).all())
         if rank == 0:
+            # the oracle (CPU restatement of rmhmc.py / hmc.py) on the UNSHARDED data, same tape
+            o_ref, o_infos = bo.rmhmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=4, step_size=0.4, n_fixed=4)
+            h_ref, _ = bo.hmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=15, step_size=0.05)
             full, _, info = r.rmhmc_batched(xx, t, c, n_iter, burn, 4, 0.4, 4, draws=st, device=f"cuda:{local}")
             hfull, _, _ = r.hmc_batched(xx, t, c, n_iter, burn, 15, 0.05, draws=st, device=f"cuda:{local}")
             err = float(np.abs(sharded[:, 1:] - full[:, 1:]).max() / np.abs(full[:, 1:]).max())
             herr = float(np.abs(hmc_sharded[:, 1:] - hfull[:, 1:]).max() / np.abs(hfull[:, 1:]).max())
-            out[tag] = {"rel_err_rmhmc": err, "rel_err_hmc": herr, "accept_equal": bool(np.array_equal(acc, info["accepted"]))}
+            oerr = float(np.abs(sharded[:, 1:] - o_ref[:, 1:]).max() / np.abs(o_ref[:, 1:]).max())
+            oherr = float(np.abs(hmc_sharded[:, 1:] - h_ref[:, 1:]).max() / np.abs(h_ref[:, 1:]).max())
+            out[tag] = {"rel_err_rmhmc": err, "rel_err_hmc": herr, "accept_equal": bool(np.array_equal(acc, info["accepted"])),
+                        "rel_err_rmhmc_vs_oracle": oerr, "rel_err_hmc_vs_oracle": oherr,
+                        "accept_equal_oracle": bool(np.array_equal(acc, [i["accepted"].sum() for i in o_infos]))}
         flags = torch.tensor([1.0 if same else 0.0], device="cuda")
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if rank == 0:
             out[tag]["ranks_bit_identical"] = bool(flags.item() == 1.0)
     if rank == 0:
         ok = all(v["rel_err_rmhmc"] < 1e-10 and v["rel_err_hmc"] < 1e-10 and v["accept_equal"] and v["ranks_bit_identical"]
+                 and v["rel_err_rmhmc_vs_oracle"] < 1e-9 and v["rel_err_hmc_vs_oracle"] < 1e-9 and v["accept_equal_oracle"]
                  for v in out.values())
         print(json.dumps({"world": world, "ok": ok, **out}))
     dist.destroy_process_group()

@@ -184,12 +184,15 @@ static int test_end_to_end(int n_rows, int dim, int n_chains, double theta_sd, b
 
     int bad = 0;
     const int n_check = n_chains < 24 ? n_chains : 24;
-    for (int closing = 0; closing < 3; ++closing) {       // 0 scalar iterate kernel, 1 closing kernel, 2 DMMA iterate kernel
+    for (int variant = 0; variant < 4; ++variant) {       // 0 scalar iterate kernel, 1 scalar closing kernel, 2 DMMA iterate kernel, 3 DMMA closing kernel
+        const int closing = variant == 3 ? 1 : variant;
+        if (variant == 3) { CK(cudaMemset(dgrad, 0xff, (size_t)n_chains * dim * 8)); CK(cudaMemset(dll, 0xff, (size_t)n_chains * 8)); CK(cudaMemset(dcb, 0xff, (size_t)a_rows * P.n_rows_pad * 8)); }
         CK(cudaMemset(dg, 0xff, (size_t)n_chains * P.p2p * 8));
         CK(cudaMemset(da, 0x55, (size_t)S * a_rows * kp));
-        if (closing == 1) CK((i8_launch_vslice<S, true>(v, 0)));
-        else if (closing == 0) CK((i8_launch_vslice<S, false>(v, 0)));
-        else CK((i8_launch_vslice_mma<S>(v, 0)));
+        if (variant == 1) CK((i8_launch_vslice<S, true>(v, 0)));
+        else if (variant == 0) CK((i8_launch_vslice<S, false>(v, 0)));
+        else if (variant == 2) CK((i8_launch_vslice_mma<S>(v, 0)));
+        else CK((i8_launch_vslice_mma_closing<S>(v, 0)));
         CK(i8_launch_gemm<S>(ma, mb, g, 0));
         CK(cudaDeviceSynchronize());
         std::vector<double> hg((size_t)n_chains * P.p2p), hgrad((size_t)n_chains * dim), hll(n_chains), hcb;
@@ -234,7 +237,7 @@ static int test_end_to_end(int n_rows, int dim, int n_chains, double theta_sd, b
         }
         const double tol_g = S == 5 ? 2e-11 : 1e-12;
         std::printf("end-to-end S=%d N=%d D=%d C=%d theta_sd=%.2f %s: max rel err G %.3g (tol %.1g)", S, n_rows, dim, n_chains, theta_sd,
-                    closing == 1 ? "closing" : (closing == 0 ? "iterate" : "iterate(dmma)"), eg, tol_g);
+                    variant == 1 ? "closing" : (variant == 0 ? "iterate" : (variant == 2 ? "iterate(dmma)" : "closing(dmma)")), eg, tol_g);
         if (closing == 1) std::printf(", grad %.3g, loglik %.3g, c_n %.3g", egr, ell, ecb);
         std::printf("\n");
         if (!(eg < tol_g)) ++bad;
@@ -260,6 +263,7 @@ static int test_end_to_end(int n_rows, int dim, int n_chains, double theta_sd, b
         timeit("vslice", [&]() { CK((i8_launch_vslice<S, false>(v, 0))); }, el * 2.0 * (dim + 20));
         timeit("vslice_mma", [&]() { CK((i8_launch_vslice_mma<S>(v, 0))); }, el * 2.0 * (dim + 20));
         timeit("vslice_closing", [&]() { CK((i8_launch_vslice<S, true>(v, 0))); }, el * 2.0 * (2 * dim + 32));
+        timeit("vslice_mma_closing", [&]() { CK((i8_launch_vslice_mma_closing<S>(v, 0))); }, el * 2.0 * (2 * dim + 32));
         timeit("gemm", [&]() { CK(i8_launch_gemm<S>(ma, mb, g, 0)); }, 2.0 * (S * (S + 1) / 2) * (double)a_rows * kp * b_rows);
         timeit("vslice_mma+gemm", [&]() { CK((i8_launch_vslice_mma<S>(v, 0))); CK(i8_launch_gemm<S>(ma, mb, g, 0)); }, 2.0 * (double)n_chains * P.n_rows * (P.p2 + dim));
     }

@@ -422,6 +422,37 @@ def test_row_sharded_matches_unsharded_on_two_gpus(pkg):
 
 
 @pytest.mark.parametrize("metric", METRIC)
+@pytest.mark.parametrize("dim,n_rows", [(15, 690), (40, 500)])
+def test_row_sharded_code_path_on_one_rank_matches_oracle(pkg, dim, n_rows, metric):
+    """BASELINE.json configs[4] mechanism on ONE GPU: rmhmc_comm_init(world = 1) switches the engine to the row-sharded
+    schedule (an NCCL all-reduce after every metric build and every pass, unfused momentum iterates); with one rank the
+    sums are the data set's, so the chains must follow the oracle (the 2-GPU test compares real shards as well)."""
+    if dim > 32 and metric == "i8":
+        pytest.skip("the INT8 build covers dim <= 32")
+    xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 5100 + dim)
+    n_iter, burn, c = 5, 1, 4
+    tapes = [bo.make_tape(n_iter, dim, 9350 + i) for i in range(c)]
+    st = bo.stack_tapes(tapes)
+    ref, infos = bo.rmhmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=4, step_size=0.3, n_fixed=4)
+    href, hinfos = bo.hmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=12, step_size=0.03)
+    data = pkg.LogisticData(xx, t, row_shard=(0, 1), metric=metric)
+    s = pkg.RMHMCSampler(data, c, 4, 0.3, 4)
+    s.set_tape(st["z"], st["u_step"], st["z_dir"], st["u_acc"])
+    s.set_samples(n_iter - burn, burn)
+    s.run(n_iter)
+    out, acc = s.samples.cpu().numpy(), s.state()["accepted"]
+    hs = pkg.HMCSampler(data, c, 12, 0.03)
+    hs.set_tape(st["z"], st["u_step"], st["u_acc"])
+    hs.set_samples(n_iter - burn, burn)
+    hs.run(n_iter)
+    hout = hs.samples.cpu().numpy()
+    data.close()
+    assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
+    assert np.array_equal(acc, [i["accepted"].sum() for i in infos])
+    assert rel_err(hout[:, 1:], href[:, 1:]) < RTOL
+
+
+@pytest.mark.parametrize("metric", METRIC)
 @pytest.mark.parametrize("shape", ["australian", "german"])
 def test_leapfrog_seam_matches_oracle(pkg, shape, metric):
     """rmhmc_leapfrog: deterministic generalized leapfrog from given (theta, p), both directions."""
