@@ -187,7 +187,8 @@ int64_t rmhmc_launch_count(const rmhmc_handle* h);
  * 1 metric build (closing), 2 partials build (tensor mode), 3 per-chain turn (end of one leapfrog step +
  * start of the next; matrix-free: also the momentum iterates), 4 per-chain position solve / factorisation,
  * 5 quadratic-form pass, 6 leverage GEMM, 7 trace pass (matrix-free mode), 8 / 9 the two kernels of the INT8 metric
- * build (v digits, tcgen05 GEMM; their sum is also counted under 0 / 1).  Returns accumulated
+ * build (v digits, tcgen05 GEMM; their sum is also counted under 0 / 1), 10 the NCCL all-reduces of the row-sharded
+ * mode.  Returns accumulated
  * milliseconds and launch count since the last reset; synchronises. */
 int rmhmc_profile_enable(rmhmc_handle* h, int enable);
 int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches);
@@ -213,9 +214,18 @@ int hmc_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop);
  * rmhmc_set_samples (row it - burn_in for it >= burn_in, as in the MATLAB loop), rmhmc_set_trace (theta_end = the
  * proposal, h_current = log q(new|old), h_proposed = Ratio, flags bit0 accepted / bit1 uniform consumed) and
  * rmhmc_read_state apply.  dim <= 32.  The full drift runs on the MATRIX_FREE partials (the handle is switched). */
+/* simplified == 2 selects the IWLS proposal of code/iwls.py:13-89 (Gamerman's iterated weighted least squares): the same
+ * Metropolis-Hastings loop with proposal N(w + G^-1 grad, G^-1) -- algebraically cov . X^T W z of iwls.py:31-35 -- and the
+ * density's log-determinant taken from chol(cov + 1e-6 I) as in iwls.py:64,68; step_size is ignored.  Pinned: the
+ * unmodified iwls.py runs under a tape with np.random.multivariate_normal replaced by mean + chol(cov) z
+ * (tests/golden/iwls_*.npz). */
 int mmala_chains_init(rmhmc_handle* h, int64_t n_chains, const double* theta0, int simplified, double step_size);
 int mmala_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const double* z, const double* u_acc);
 int mmala_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
+/* Current proposal distribution N(mean, L L^T) of every chain: mean (n_chains x dim), L lower (n_chains x dim x dim);
+ * either may be NULL.  Lets a host that owns the random stream (the single-chain iwls() drop-in) draw the proposal itself
+ * and pass the engine z = L^-1 (w' - mean).  Synchronises. */
+int mmala_read_proposal(rmhmc_handle* h, double* mean, double* chol_lower);
 int mmala_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop);     /* one round = one iteration of every chain */
 
 /* ---- tools.py:32-74 batched ------------------------------------------------------------------ */

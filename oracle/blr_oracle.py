@@ -523,6 +523,68 @@ def mmala_chain(xx, t, tape: DrawTape, n_iter=10000, burn_in=5000, step_size=1.0
     return samples, info
 
 
+# --------------------------------------------------------------------------- IWLS (code/iwls.py)
+def iwls_chain(xx, t, tape: DrawTape, n_iter=10000, burn_in=5000, alpha=ALPHA, record=False, w0=None):
+    """One iterated-weighted-least-squares Metropolis chain under a draw tape; restates ``code/iwls.py:13-89``.
+
+    The reference draws its proposal with ``np.random.multivariate_normal(current_mean, current_cov)`` (iwls.py:45),
+    whose SVD factor depends on LAPACK sign conventions; under a tape that call is replaced by
+    ``current_mean + cholesky(current_cov) @ z[it]`` (the same distribution) -- in the live reference run by patching
+    that one NumPy attribute (oracle/ref_live.py: run_iwls), here directly.  ``u_acc[it]`` feeds
+    ``np.random.uniform()`` (iwls.py:76), consumed only when ``ratio > 0`` is false.  Samples: row ``i - burn_in`` for
+    ``i >= burn_in`` (iwls.py:84-85).  Everything else keeps the reference's NumPy operation order (bit-identical).
+    """
+    n_samples, dim = xx.shape
+    beta = np.zeros(dim) if w0 is None else np.array(w0, dtype=float).reshape(dim)                # iwls.py:18
+    beta_saved = np.zeros((n_iter - burn_in, dim))
+
+    def joint(b):                                                                                 # iwls.py:22-25, :48-51
+        log_prior = log_norm_pdf(np.zeros((1, dim)), b[:, np.newaxis], alpha)
+        f = np.dot(xx, b)
+        return np.dot(f.T, t) - np.sum(np.log(1 + np.exp(f))) + log_prior
+
+    def moments(b):                                                                               # iwls.py:28-35, :54-61
+        p = 1 / (1 + np.exp(-np.sum(b * xx, axis=1)))
+        w = p * (np.ones(n_samples) - p)
+        cov = np.linalg.inv(np.eye(dim) / alpha + (xx.T * np.tile(w[:, np.newaxis].T, (dim, 1))).dot(xx))
+        # inv_W.dot(t - p) with inv_W = eye / W: a diagonal matrix product, i.e. (1 / W_i) (t - p)_i exactly
+        z = xx.dot(b)[:, np.newaxis] + (1.0 / w)[:, np.newaxis] * (t - p[:, np.newaxis])
+        mean = cov.dot(xx.T.dot(w[:, np.newaxis] * z))[:, 0]                                      # np.diag(W).dot(z)
+        return cov, mean
+
+    current_ljl = joint(beta)
+    current_cov, current_mean = moments(beta)
+    accepted = np.zeros(n_iter, dtype=bool)
+    records = []
+    for i in range(n_iter):
+        beta_new = current_mean + np.linalg.cholesky(current_cov).dot(tape.z[i])                  # iwls.py:45 (see above)
+        proposed_ljl = joint(beta_new)
+        new_cov, new_mean = moments(beta_new)
+        p_new_old = -np.sum(np.diag(np.log(np.linalg.cholesky(current_cov + np.eye(dim) * 1e-6))))   # iwls.py:64-66
+        p_new_old -= 0.5 * (beta_new - current_mean).T.dot(np.linalg.inv(current_cov)).dot(beta_new - current_mean)
+        p_old_new = -np.sum(np.diag(np.log(np.linalg.cholesky(new_cov + np.eye(dim) * 1e-6))))       # iwls.py:68-70
+        p_old_new -= 0.5 * (beta - new_mean).T.dot(np.linalg.inv(new_cov)).dot(beta - new_mean)
+        ratio = proposed_ljl + p_old_new - current_ljl - p_new_old                                # iwls.py:76
+        used_uniform = False
+        take = bool(ratio > 0)
+        if not take:
+            used_uniform = True
+            take = bool(ratio > np.log(tape.u_acc[i]))
+        if record:
+            records.append({"theta": beta_new.copy(), "ratio": _scalar(ratio), "accepted": take, "used_uniform": used_uniform})
+        if take:                                                                                  # iwls.py:76-81
+            accepted[i] = True
+            beta, current_cov, current_mean, current_ljl = beta_new, new_cov, new_mean, proposed_ljl
+        if i >= burn_in:
+            beta_saved[i - burn_in] = beta                                                        # iwls.py:84-85
+    return beta_saved, {"w": beta.copy(), "log_joint": _scalar(current_ljl), "accepted": accepted, "records": records}
+
+
+def iwls_chains(xx, t, tapes: list[DrawTape], **kw):
+    out = [iwls_chain(xx, t, tp, **kw) for tp in tapes]
+    return np.stack([o[0] for o in out]), [o[1] for o in out]
+
+
 def mmala_chains(xx, t, tapes: list[DrawTape], **kw):
     out = [mmala_chain(xx, t, tp, **kw) for tp in tapes]
     return np.stack([o[0] for o in out]), [o[1] for o in out]

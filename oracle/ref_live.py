@@ -151,3 +151,36 @@ def run_hmc(xx, t, tape, n_iter, burn_in, n_leapfrog, step_size):
             dict(NumOfIterations=n_iter, BurnIn=burn_in, NumOfLeapFrogSteps=n_leapfrog,
                  StepSize=step_size))
     return w_saved, {"uniform_used": np.array(feeder.uniform_used, dtype=bool), "iters": events}
+
+
+def run_iwls(xx, t, tape, max_iter, burn_in, alpha=100):
+    """Reference ``iwls.iwls`` (code/iwls.py) under ``tape``.
+
+    ``np.random.multivariate_normal`` (iwls.py:45) is replaced for the call by ``mean + cholesky(cov) @ z[it]`` and
+    ``np.random.uniform`` (iwls.py:76) by ``u_acc[it]``: every other line of the unmodified reference runs as is.
+    Returns ``(beta_saved, info)`` with the per-iteration proposal and ratio (line 76).
+    """
+    if REFERENCE_CODE not in sys.path:
+        sys.path.insert(0, REFERENCE_CODE)
+    load_reference()
+    ref = importlib.import_module("iwls")
+    assert os.path.dirname(os.path.abspath(ref.__file__)) == REFERENCE_CODE
+    state = {"it": -1, "used": []}
+
+    def mvn(mean, cov):
+        state["it"] += 1
+        state["used"].append(False)
+        return mean + np.linalg.cholesky(cov).dot(tape.z[state["it"]])
+
+    def uniform():
+        state["used"][state["it"]] = True
+        return float(tape.u_acc[state["it"]])
+
+    saved = (np.random.multivariate_normal, np.random.uniform)
+    np.random.multivariate_normal, np.random.uniform = mvn, uniform
+    try:
+        (beta_saved, _), events = _run_traced(ref.iwls, {76: ("i", "beta_new", "ratio")}, (xx, t),
+                                              dict(alpha=alpha, max_iter=max_iter, burn_in=burn_in))
+    finally:
+        np.random.multivariate_normal, np.random.uniform = saved
+    return beta_saved, {"uniform_used": np.array(state["used"], dtype=bool), "iters": events}

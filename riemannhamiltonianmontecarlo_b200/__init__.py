@@ -10,9 +10,10 @@ from . import datasets  # noqa: F401
 from ._capi import RmhmcError  # noqa: F401
 from .engine import HMCSampler, LogisticData, MMALASampler, RMHMCSampler, autocorr_batched, ess_batched, rhat_batched  # noqa: F401
 from .hmc import HMC, hmc_batched  # noqa: F401
+from .iwls import iwls, iwls_batched  # noqa: F401
 from .mmala import mMALA, mmala_batched  # noqa: F401
 from .rmhmc import RMHMC, rmhmc_batched  # noqa: F401
 from .tools import CalculateESS, LogNormPDF, ac, nextpow2  # noqa: F401
 
 __all__ = ["RMHMC", "HMC", "mMALA", "LogNormPDF", "nextpow2", "ac", "CalculateESS", "RMHMCSampler", "HMCSampler",
-           "MMALASampler", "LogisticData", "rmhmc_batched", "hmc_batched", "mmala_batched", "ess_batched", "rhat_batched", "datasets", "RmhmcError"]
+           "MMALASampler", "LogisticData", "rmhmc_batched", "hmc_batched", "mmala_batched", "iwls", "iwls_batched", "ess_batched", "rhat_batched", "datasets", "RmhmcError"]

@@ -59,6 +59,7 @@ SIGNATURES = {
     "mmala_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "mmala_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     "mmala_advance": (c_int, [c_void_p, c_int64, c_int64]),
+    "mmala_read_proposal": (c_int, [c_void_p, c_void_p, c_void_p]),
     "blr_ess_batched": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p]),
     "blr_autocorr": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "blr_rhat": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p]),

@@ -106,7 +106,7 @@ struct rmhmc_handle {
     double* t_tmp = nullptr;        // [C][P3p] contiguous partials of the last build (sharded mode)
     double* split_buf = nullptr;    // partial outputs of row-split metric builds / passes
     size_t split_cap = 0;
-    ProfSlot prof[10];
+    ProfSlot prof[11];
     ncclComm_t stats_comm = nullptr;   // chain-sharded runs: end-of-run statistics only (rmhmc_stats_comm_init)
     int stats_world = 1;
     // INT8-slice metric build on tcgen05 (i8_metric.cuh): digit planes of KR2(X)^T per data set, of V per chain set
@@ -328,6 +328,18 @@ __global__ void k_copy_theta(const double* theta, const int* cur, size_t slot_st
     if (i >= C * D) return;
     int64_t c = i / D;
     dst[i] = theta[(size_t)cur[c] * slot_stride + i];
+}
+
+// manifold-MALA / IWLS: mean and lower Cholesky factor of the current proposal distribution of every chain
+__global__ void k_copy_proposal(const double* theta, const double* drift, const double* rfac, const int* cur, size_t slot_theta,
+                                size_t slot_mat, double* mean, double* chol, int64_t C, int D) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= C * D * D) return;
+    const int64_t c = i / (D * D);
+    const int r = (int)(i - c * D * D), a = r / D, b = r - a * D;
+    const int sl = cur[c];
+    if (chol) chol[i] = rfac[(size_t)sl * slot_mat + (size_t)c * D * D + (size_t)b * D + a];      // L[a][b] = R[b][a]
+    if (mean && b == 0) mean[c * D + a] = theta[(size_t)sl * slot_theta + c * D + a] + drift[(size_t)sl * slot_theta + c * D + a];
 }
 
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -729,6 +741,7 @@ int launch_seam_factor(rmhmc_handle* h, const EngineParams& P, int64_t C, const 
 
 int allreduce_sum(rmhmc_handle* h, double* buf, size_t count) {
     if (!h->comm) return RMHMC_OK;
+    Bracket b(h, 10);
     ncclResult_t r = nccl_api().AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->stream);
     if (r != ncclSuccess) return fail(h, RMHMC_E_CUDA, std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r));
     return RMHMC_OK;
@@ -1720,7 +1733,7 @@ int mmala_chains_init(rmhmc_handle* h, int64_t C, const double* theta0, int simp
     int rc = alloc_chains(h, C, false);
     if (rc) { h->matrix_free = saved_mf; return rc; }
     h->is_mmala = true;
-    h->mmala_simplified = simplified ? 1 : 0;
+    h->mmala_simplified = simplified < 0 || simplified > 2 ? 1 : simplified;       // 0 full mMALA, 1 simplified, 2 IWLS proposal
     h->P.step_size = step_size; h->P.n_leapfrog = 1; h->P.n_fixed = 0;       // the cached drift / proposal factor depend on eps
     h->configured = true;
     ChainArrays& S = h->S;
@@ -1744,6 +1757,17 @@ int mmala_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const dou
     h->P.tape_z_dir = nullptr; h->P.tape_u_acc = u_acc;
     h->tape_base = it_base; h->tape_window = n_window;
     h->rng_set = true;
+    return RMHMC_OK;
+}
+int mmala_read_proposal(rmhmc_handle* h, double* mean, double* chol_lower) {
+    if (!h) return RMHMC_E_INVALID;
+    if (h->n_chains <= 0 || !h->is_mmala) return fail(h, RMHMC_E_STATE, "mmala_read_proposal: call mmala_chains_init first");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int64_t C = h->n_chains;
+    k_copy_proposal<<<blocks_for(C * h->dim * h->dim, 256), 256, 0, h->stream>>>(h->S.theta, h->S.grad, h->S.invg, h->S.cur, h->P.slot_theta,
+                                                                                h->P.slot_invg, mean, chol_lower, C, h->dim);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return RMHMC_OK;
 }
 int mmala_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done) {
@@ -1825,7 +1849,7 @@ int rmhmc_profile_enable(rmhmc_handle* h, int enable) {
     return RMHMC_OK;
 }
 int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches) {
-    if (!h || kind < 0 || kind > 9) return RMHMC_E_INVALID;
+    if (!h || kind < 0 || kind > 10) return RMHMC_E_INVALID;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     drain_profile(h);
     if (ms) *ms = h->prof[kind].ms;

@@ -40,6 +40,10 @@ __global__ void __launch_bounds__(32) k_mmala_turn(EngineParams P, ChainArrays S
     const bool live = lane < D;
     const size_t cd = (size_t)c * D + lane;
     const double eps = P.step_size;
+    // variant 2 = the IWLS proposal of code/iwls.py:28-45: N(w + G^-1 grad, G^-1) -- the simplified-mMALA proposal with
+    // drift coefficient 1 and covariance G^-1 (cov . X^T W z = w + G^-1 (X^T (t - p) - w / alpha))
+    const bool iwls = simplified == 2;
+    const double drift_c = iwls ? 1.0 : eps / 2, cov_c = iwls ? 1.0 : eps;
     int cur = S.cur[c];
 
     if (do_back) {
@@ -50,10 +54,10 @@ __global__ void __launch_bounds__(32) k_mmala_turn(EngineParams P, ChainArrays S
         if (live) {
             th = S.theta_w[cd];
             dr = S.grad_tmp[cd] - th / P.alpha;                                                   // M:258 (gradient)
-            if (!simplified) dr -= S.trace_tmp[cd];                                               // grad - tr
+            if (simplified == 0) dr -= S.trace_tmp[cd];                                           // grad - tr
         }
         // drift = eps/2 G^-1 (grad - tr)                                                          M:258,:273-277
-        const double drift = (eps / 2) * mf_matvec<32>(invg_out, dr, xs, D, lane);
+        const double drift = drift_c * mf_matvec<32>(invg_out, dr, xs, D, lane);
         // log prior, summed in parameter order (LogNormPDF.m)
         __syncwarp();
         xs[lane] = th;
@@ -66,9 +70,20 @@ __global__ void __launch_bounds__(32) k_mmala_turn(EngineParams P, ChainArrays S
         double row[N], dinv;
 #pragma unroll
         for (int j = 0; j < N; ++j)
-            row[j] = (j < D && lane >= j && live) ? eps * invg_out[(size_t)lane * D + j] : (j == lane ? 1.0 : 0.0);
+            row[j] = (j < D && lane >= j && live) ? cov_c * invg_out[(size_t)lane * D + j] : (j == lane ? 1.0 : 0.0);
         __syncwarp();
-        const double ldp = chol_fixed<N>(row, colbuf, lane, dinv);
+        double ldp;
+        if (iwls) {
+            // iwls.py:64,68: the density's log-determinant term is sum log diag chol(cov + 1e-6 I), the draw uses cov itself
+            double row2[N], dinv2;
+#pragma unroll
+            for (int j = 0; j < N; ++j) row2[j] = row[j] + ((j == lane && live) ? 1e-6 : 0.0);
+            ldp = chol_fixed<N>(row2, colbuf, lane, dinv2);
+            __syncwarp();
+            chol_fixed<N>(row, colbuf, lane, dinv);
+        } else {
+            ldp = chol_fixed<N>(row, colbuf, lane, dinv);
+        }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < N; ++j)
@@ -87,7 +102,7 @@ __global__ void __launch_bounds__(32) k_mmala_turn(EngineParams P, ChainArrays S
         const double w_cur = live ? S.theta[cur * P.slot_theta + cd] : 0.0;
         const double diff = live ? (th + drift) - w_cur : 0.0;
         const double y = mf_matvec<32>(lg_out, diff, xs, D, lane);
-        const double p_old_new = -ldp - 0.5 * mf_sum<32>(live ? y * y : 0.0, red, D, lane) / eps;
+        const double p_old_new = -ldp - 0.5 * mf_sum<32>(live ? y * y : 0.0, red, D, lane) / cov_c;
         const double ratio = ljl + p_old_new - S.logjoint[cur * P.slot_scalar + c] - S.hcur[c];   // M:282
         bool take = ratio > 0.0, used_u = false;
         if (!take) {                                    // the uniform is consumed only when Ratio > 0 is false (M:285)
@@ -134,7 +149,7 @@ __global__ void __launch_bounds__(32) k_mmala_turn(EngineParams P, ChainArrays S
         S.theta_w[cd] = w_new;
     }
     const double y = mf_matvec<32>(lg_cur, diff, xs, D, lane);
-    const double p_new_old = -S.logdet[cur * P.slot_scalar + c] - 0.5 * mf_sum<32>(live ? y * y : 0.0, red, D, lane) / eps;
+    const double p_new_old = -S.logdet[cur * P.slot_scalar + c] - 0.5 * mf_sum<32>(live ? y * y : 0.0, red, D, lane) / cov_c;
     if (lane == 0) {
         S.hcur[c] = p_new_old;
         S.nsteps[c] = 1;                                // k_chain_factor treats the chain as active

@@ -38,7 +38,7 @@ def shard_chains(n_chains: int, rank: int, world: int):
 
 
 PROFILE_KINDS = ["metric_fp", "metric_closing", "partials", "chain_turn", "chain_solve", "quad_pass", "leverage_gemm",
-                 "trace_pass", "i8_vslice", "i8_gemm"]
+                 "trace_pass", "i8_vslice", "i8_gemm", "allreduce"]
 
 
 def device_peaks(device=0):
@@ -397,11 +397,21 @@ class MMALASampler(_SamplerBase):
 
     _advance_fn = "mmala_advance"
 
-    def __init__(self, data: LogisticData, n_chains: int, step_size: float = 1.0, simplified: bool = False, theta0=None):
+    def __init__(self, data: LogisticData, n_chains: int, step_size: float = 1.0, simplified: bool = False, theta0=None,
+                 iwls: bool = False):
         lib, h, c = data._lib, data.handle, int(n_chains)
+        variant = 2 if iwls else (1 if simplified else 0)        # 2: the IWLS proposal of code/iwls.py
         super().__init__(data, n_chains, theta0,
-                         _init=lambda th0: lib.mmala_chains_init(h, c, _ptr(th0), 1 if simplified else 0, float(step_size)))
-        self.step_size, self.simplified = float(step_size), bool(simplified)
+                         _init=lambda th0: lib.mmala_chains_init(h, c, _ptr(th0), variant, float(step_size)))
+        self.step_size, self.simplified, self.iwls = float(step_size), bool(simplified), bool(iwls)
+
+    def proposal_moments(self):
+        """(mean (C, D), L (C, D, D)) of every chain's current proposal N(mean, L L^T) as numpy arrays; one chain: (D,), (D, D)."""
+        t, dev, c, d = self.torch, self.data.device, self.n_chains, self.dim
+        mean, chol = t.empty(c, d, dtype=t.float64, device=dev), t.empty(c, d, d, dtype=t.float64, device=dev)
+        _capi.check(self._lib.mmala_read_proposal(self.h, _ptr(mean), _ptr(chol)), self.h, "mmala_read_proposal")
+        mean, chol = mean.cpu().numpy(), chol.cpu().numpy()
+        return (mean[0], chol[0]) if c == 1 else (mean, chol)
 
     def set_tape(self, z, u_acc, it_base: int = 0):
         d = self.data

@@ -44,9 +44,15 @@ if world > 1:
     flag = torch.tensor([1.0 if same else 0.0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN); same = bool(flag.item() == 1.0)
 if rank == 0:
     P2 = D * (D + 1) // 2
+    P2p, F = (P2 + 7) // 8 * 8, 6
+    ar_ms, ar_n = prof.get("allreduce", (0.0, 0))
     out = {"rows_total": N_PER * world, "rows_per_rank": N_PER, "dim": D, "chains": C, "ranks": world, "partials": data.partials_mode,
            "ms_per_round": dt / R * 1e3, "ranks_bit_identical": same,
-           "kernels": {k: {"ms_avg": ms / max(n, 1), "launches": n} for k, (ms, n) in prof.items() if n},
+           "allreduce": {"launches_per_round": ar_n / R, "ms_per_round": ar_ms / R, "share_of_round": ar_ms / (dt * 1e3),
+                         "message_bytes": {"metric_iterate (G)": C * P2p * 8, "metric_closing (G | X^T(t-p) | loglik)": C * (P2p + D + 1) * 8,
+                                           "quad pass": C * D * 8, "pair pass (quad | trace)": 2 * C * D * 8},
+                         "per_leapfrog_step": f"{F - 1} x G + 1 x closing + {F} x quad + 1 x pair"},
+           "kernels": {k: {"ms_avg": ms / max(n, 1), "launches": n, "ms_per_round": ms / R} for k, (ms, n) in prof.items() if n},
            "metric_tflops_per_rank": 2.0 * C * N_PER * P2 / (prof["metric_fp"][0] / max(prof["metric_fp"][1], 1) * 1e-3) / 1e12}
     print(json.dumps(out))
 data.close()

@@ -116,6 +116,34 @@ def hmc_fixture(name, xx, t, seeds, n_iter, burn_in, n_leapfrog, step_size):
     print(f"{name}: accept {accepted.mean():.2f}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def iwls_fixture(name, xx, t, seeds, n_iter, burn_in):
+    d = xx.shape[1]
+    tapes = [bo.make_tape(n_iter, d, s) for s in seeds]
+    samples = np.zeros((len(seeds), n_iter - burn_in, d))
+    ratio = np.zeros((len(seeds), n_iter))
+    proposals = np.zeros((len(seeds), n_iter, d))
+    accepted = np.zeros((len(seeds), n_iter), dtype=bool)
+    used_u = np.zeros((len(seeds), n_iter), dtype=bool)
+    for c, tape in enumerate(tapes):
+        w_ref, info = ref_live.run_iwls(xx, t, tape, n_iter, burn_in)
+        w_orc, oinfo = bo.iwls_chain(xx, t, tape, n_iter, burn_in, record=True)
+        assert np.array_equal(w_ref, w_orc), f"IWLS oracle != reference on chain {c}"
+        samples[c] = w_ref
+        for it, e in enumerate(info["iters"]):
+            ratio[c, it] = _flat(e["ratio"])[0]
+            proposals[c, it] = _flat(e["beta_new"])
+            assert oinfo["records"][it]["ratio"] == ratio[c, it]
+        accepted[c] = oinfo["accepted"]
+        used_u[c] = info["uniform_used"]
+        assert np.array_equal(used_u[c], [r["used_uniform"] for r in oinfo["records"]])
+    stacked = bo.stack_tapes(tapes)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, xx=xx, t=t, seeds=np.array(seeds), n_iter=n_iter, burn_in=burn_in, z=stacked["z"],
+                        u_acc=stacked["u_acc"], samples=samples, ratio=ratio, proposals=proposals, accepted=accepted,
+                        used_uniform=used_u)
+    print(f"{name}: accept {accepted.mean():.2f}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def tools_fixture():
     tools = ref_live.load_reference()["tools"]
     rng = np.random.default_rng(2024)
@@ -155,11 +183,17 @@ def posterior_fixture(name, xx, t, seed, n_iter=6000, burn_in=1000, n_fixed=6):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--long", action="store_true")
+    ap.add_argument("--only-iwls", action="store_true", help="regenerate only the IWLS fixtures")
     args = ap.parse_args()
     assert ref_live.available(), "needs /root/reference"
 
     xa, ta = datasets.shaped("australian")
     xg, tg = datasets.shaped("german")
+    if args.only_iwls:
+        xp, tp = datasets.load_csv(os.path.join(ref_live.REFERENCE_CODE, "data", "pima.csv"))
+        iwls_fixture("iwls_australian_shaped", xa, ta, seeds=[701, 702, 703], n_iter=30, burn_in=6)
+        iwls_fixture("iwls_pima_real", xp, tp, seeds=[801, 802], n_iter=30, burn_in=6)
+        return
     rmhmc_fixture("rmhmc_australian_shaped", xa, ta, seeds=[101, 102, 103, 104, 105, 106],
                   n_iter=24, burn_in=4, n_leapfrog=6, step_size=0.5, n_fixed=6)
     rmhmc_fixture("rmhmc_german_shaped", xg, tg, seeds=[201, 202, 203],
@@ -174,6 +208,8 @@ def main():
                 n_leapfrog=100, step_size=0.1)
     hmc_fixture("hmc_pima_real", xp, tp, seeds=[601, 602], n_iter=40, burn_in=8,
                 n_leapfrog=100, step_size=0.1)
+    iwls_fixture("iwls_australian_shaped", xa, ta, seeds=[701, 702, 703], n_iter=30, burn_in=6)
+    iwls_fixture("iwls_pima_real", xp, tp, seeds=[801, 802], n_iter=30, burn_in=6)
     tools_fixture()
     if args.long:
         posterior_fixture("posterior_australian_shaped", xa, ta, seed=7001)

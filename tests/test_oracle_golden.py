@@ -55,6 +55,29 @@ def test_hmc_oracle_reproduces_reference_fixture(golden, name):
     assert np.all(s[0] == 0.0)                                        # hmc.py:28,83
 
 
+@pytest.mark.parametrize("name", ["iwls_australian_shaped", "iwls_pima_real"])
+def test_iwls_oracle_reproduces_reference_fixture(golden, name):
+    fx = golden(name)
+    n = fx["z"].shape[0]
+    tape = bo.DrawTape(z=fx["z"][:, 0], u_step=np.zeros(n), z_dir=np.zeros(n), u_acc=fx["u_acc"][:, 0])
+    s, info = bo.iwls_chain(fx["xx"], fx["t"], tape, int(fx["n_iter"]), int(fx["burn_in"]), record=True)
+    assert np.array_equal(s, fx["samples"][0])                        # bit-exact
+    assert np.array_equal(info["accepted"], fx["accepted"][0])
+    assert [r["used_uniform"] for r in info["records"]] == list(fx["used_uniform"][0])
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_live.available(), reason="/root/reference not mounted")
+def test_iwls_oracle_matches_live_reference_on_a_fresh_tape():
+    from riemannhamiltonianmontecarlo_b200 import datasets
+    xx, t = datasets.shaped("australian")
+    tape = bo.make_tape(12, xx.shape[1], 4242)
+    w_ref, info = ref_live.run_iwls(xx, t, tape, 12, 3)
+    w_orc, oinfo = bo.iwls_chain(xx, t, tape, 12, 3, record=True)
+    assert np.array_equal(w_ref, w_orc)
+    assert np.array_equal(info["uniform_used"], [r["used_uniform"] for r in oinfo["records"]])
+
+
 def test_tools_oracle_reproduces_reference_fixture(golden):
     fx = golden("tools_ess")
     x = fx["x"]

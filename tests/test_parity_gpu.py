@@ -710,3 +710,39 @@ def test_mmala_and_hmc_sample_the_same_posterior(pkg):
         assert np.all(np.abs(s.mean(axis=0) - r.mean(axis=0)) < 0.05 * r.std(axis=0))
         assert np.all(np.abs(s.var(axis=0) / r.var(axis=0) - 1) < 0.06)
         assert 0.4 < info["accepted"].sum() / info["iters"].sum() < 0.8
+
+
+# ---- IWLS (code/iwls.py): pinned -- the fixtures come from the unmodified iwls.py run under a tape
+@pytest.mark.parametrize("name", ["iwls_australian_shaped", "iwls_pima_real"])
+def test_iwls_matches_reference(pkg, golden, name):
+    fx = golden(name)
+    n_iter, burn_in, c = int(fx["n_iter"]), int(fx["burn_in"]), fx["z"].shape[1]
+    out, _, info = pkg.iwls_batched(fx["xx"], fx["t"], c, n_iter, burn_in, draws={"z": fx["z"], "u_acc": fx["u_acc"]}, trace=True)
+    assert np.array_equal(info["accepted_flags"], fx["accepted"])
+    assert np.array_equal(info["used_uniform"], fx["used_uniform"])
+    assert rel_err(info["proposals"], fx["proposals"]) < RTOL
+    assert np.abs(info["ratio"] - fx["ratio"]).max() < 1e-7 * max(1.0, np.abs(fx["ratio"]).max())
+    assert rel_err(out, fx["samples"]) < RTOL
+
+
+def test_dropin_iwls_follows_global_numpy_rng(pkg, golden):
+    """iwls(XX, t, ...) consumes np.random like the reference (multivariate_normal, then uniform iff ratio <= 0): with
+    multivariate_normal patched exactly as in the fixture generator (mean + chol(cov) z) it replays a golden chain."""
+    fx = golden("iwls_pima_real")
+    n_iter, burn_in = int(fx["n_iter"]), int(fx["burn_in"])
+    state = {"i": -1}
+    real = (np.random.multivariate_normal, np.random.uniform, np.random.get_state, np.random.set_state)
+
+    def mvn(mean, cov):                          # the first draw of an iteration
+        state["i"] += 1
+        return mean + np.linalg.cholesky(cov).dot(fx["z"][state["i"], 0])
+
+    np.random.multivariate_normal = mvn
+    np.random.uniform = lambda: float(fx["u_acc"][state["i"], 0])
+    np.random.get_state, np.random.set_state = (lambda: None), (lambda s_: None)      # the patched draws are index-based
+    try:
+        w, secs = pkg.iwls(fx["xx"], fx["t"], 100, n_iter, burn_in, verbose=False)
+    finally:
+        np.random.multivariate_normal, np.random.uniform, np.random.get_state, np.random.set_state = real
+    assert state["i"] == n_iter - 1 and w.shape == (n_iter - burn_in, fx["xx"].shape[1]) and secs > 0
+    assert rel_err(w, fx["samples"][0]) < RTOL
