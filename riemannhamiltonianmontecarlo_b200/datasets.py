@@ -54,6 +54,35 @@ def shaped(name: str):
     return synthetic_logistic(n, d, seed)
 
 
+# The five data sets of the reference (code/data/*.csv) as the MATLAB drivers prepare them
+# (authors_code/Bayes_Log_Reg/MCMC/BLR_RMHMC.m:9-178): name -> (relabel {1,2} -> {0,1}, polynomial order of the basis).
+# main.py itself only wires 'heart' and 'australian' (main.py:20-32); Ripley uses the cubic basis [1, X, X^2, X^3]
+# (BLR_RMHMC.m:152-175, D = 7).
+DATASETS = {"australian": (False, 1), "german": (True, 1), "heart": (True, 1), "pima": (False, 1), "ripley": (False, 3)}
+
+
+def polynomial_basis(x: np.ndarray, order: int) -> np.ndarray:
+    """``XX = [1, X, X.^2, ..., X.^order]`` of the column-standardised covariates (ddof = 0 as in main.py:34-37; the
+    MATLAB original standardises with ddof = 1, BLR_RMHMC.m:23) -- BLR_RMHMC.m:26-31, :167-172."""
+    x = (x - x.mean(axis=0)) / x.std(axis=0)
+    cols = [np.ones((x.shape[0], 1))] + [x ** i for i in range(1, order + 1)]
+    return np.ascontiguousarray(np.hstack(cols))
+
+
+def load_dataset(name: str, data_dir: str):
+    """``(XX, t)`` of one of the reference's data sets by name (case-insensitive), read from ``data_dir/<name>.csv``."""
+    import os
+    key = name.lower()
+    if key not in DATASETS:
+        raise ValueError(f"Error! Dataset must be one of {sorted(DATASETS)}.")          # main.py:31-32
+    relabel, order = DATASETS[key]
+    raw = np.loadtxt(os.path.join(data_dir, key + ".csv"), delimiter=",")
+    t = raw[:, -1].reshape(-1, 1).copy()
+    if relabel:
+        t = t - 1.0
+    return polynomial_basis(raw[:, :-1], order), np.ascontiguousarray(t, dtype=np.float64)
+
+
 def load_csv(path: str, relabel_12: bool = False):
     """Reference preprocessing of a ``code/data/*.csv`` file (main.py:23-41).
 

@@ -37,6 +37,22 @@ def shard_chains(n_chains: int, rank: int, world: int):
     return shard_rows(n_chains, rank, world)
 
 
+def chain_moments(samples):
+    """Host mirror of the sufficient statistics rmhmc_stats_gather exchanges for Gelman-Rubin: for a (C, S, D) array the
+    (3, D) sums over chains of the chain means, squared chain means and chain variances (ddof = 1)."""
+    s = np.asarray(samples, dtype=np.float64)
+    m, v = s.mean(axis=1), s.var(axis=1, ddof=1)
+    return np.stack([m.sum(axis=0), (m * m).sum(axis=0), v.sum(axis=0)])
+
+
+def rhat_from_moments(moments, c_total: int, n_samples: int):
+    """Rhat per parameter from moments summed over ALL ranks (csrc/ess_kernel.cuh: k_rhat_finish)."""
+    a, b, w = np.asarray(moments, dtype=np.float64)
+    w = w / c_total
+    b_over_s = (b - a * a / c_total) / (c_total - 1.0)
+    return np.sqrt(((n_samples - 1.0) / n_samples * w + b_over_s) / w)
+
+
 PROFILE_KINDS = ["metric_fp", "metric_closing", "partials", "chain_turn", "chain_solve", "quad_pass", "leverage_gemm",
                  "trace_pass", "i8_vslice", "i8_gemm", "allreduce"]
 

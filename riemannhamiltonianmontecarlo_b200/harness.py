@@ -8,6 +8,11 @@ the population std, prepends the intercept (main.py:20-41), runs one sampler 10 
 debugger/plots are dropped, and the same summary is returned and printed.
 
     python -m riemannhamiltonianmontecarlo_b200.harness data.csv --sampler rmhmc [--relabel-12]
+    python -m riemannhamiltonianmontecarlo_b200.harness german --data-dir /path/to/code/data --sampler hmc
+
+A data-set NAME (australian, german, heart, pima, ripley) instead of a CSV path applies the per-data-set preparation of
+the MATLAB drivers (relabelling, Ripley's cubic basis: datasets.load_dataset) and, for HMC, their per-data-set step size
+(BLR_hmc.m:36,72,108,138,168) unless --step-size is given.
 """
 from __future__ import annotations
 
@@ -17,6 +22,7 @@ import numpy as np
 
 from . import datasets
 from .hmc import hmc_batched
+from .iwls import iwls_batched
 from .mmala import mmala_batched
 from .rmhmc import rmhmc_batched
 from .tools import CalculateESS
@@ -38,9 +44,13 @@ def run_experiments(XX, t, sampler="rmhmc", n_experiments=10, NumOfIterations=60
     elif sampler in ("mmala", "mmala_simp"):                 # the MATLAB originals' samplers (BLR_mMALA.m, BLR_mMALA_Simp.m)
         samples, seconds, info = mmala_batched(XX, t, n_experiments, NumOfIterations, BurnIn, Simplified=sampler == "mmala_simp",
                                                seed=seed, device=device, **sampler_kwargs)
+    elif sampler == "iwls":                                  # code/iwls.py (main.py:51)
+        sampler_kwargs.pop("StepSize", None)
+        samples, seconds, info = iwls_batched(XX, t, n_experiments, NumOfIterations, BurnIn, seed=seed, device=device,
+                                              **sampler_kwargs)
     else:
-        raise ValueError("sampler must be 'rmhmc', 'hmc', 'mmala' or 'mmala_simp'")
-    first = 0 if sampler.startswith("mmala") else 1          # RMHMC / HMC never write row 0 (rmhmc.py:190, hmc.py:83)
+        raise ValueError("sampler must be 'rmhmc', 'hmc', 'mmala', 'mmala_simp' or 'iwls'")
+    first = 0 if sampler.startswith("mmala") or sampler == "iwls" else 1     # RMHMC / HMC never write row 0 (rmhmc.py:190, hmc.py:83)
     results_beta = samples                                   # (n_experiments, NumOfIterations-BurnIn, D), main.py:46
     avg_beta_posterior = results_beta.mean(axis=0)           # main.py:54
     ess = CalculateESS(avg_beta_posterior, avg_beta_posterior.shape[0] - 1)      # main.py:71
@@ -65,20 +75,26 @@ def run_experiments(XX, t, sampler="rmhmc", n_experiments=10, NumOfIterations=60
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
-    ap.add_argument("csv")
+    ap.add_argument("csv", help="path of a CSV file (label = last column) or the name of one of the reference's data sets")
+    ap.add_argument("--data-dir", default="data", help="directory holding <name>.csv when a data-set name is given (main.py: data/)")
     ap.add_argument("--relabel-12", action="store_true", help="labels {1,2} -> {0,1} (heart, german)")
-    ap.add_argument("--sampler", default="rmhmc", choices=["rmhmc", "hmc", "mmala", "mmala_simp"])
+    ap.add_argument("--sampler", default="rmhmc", choices=["rmhmc", "hmc", "mmala", "mmala_simp", "iwls"])
     ap.add_argument("--experiments", type=int, default=10)
     ap.add_argument("--iterations", type=int, default=6000)
     ap.add_argument("--burn-in", type=int, default=1000)
     ap.add_argument("--step-size", type=float, default=None)
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args(argv)
-    XX, t = datasets.load_csv(args.csv, relabel_12=args.relabel_12)
     kw = {}
+    if args.csv.lower() in datasets.DATASETS:
+        XX, t = datasets.load_dataset(args.csv, args.data_dir)
+        if args.sampler == "hmc":
+            kw["StepSize"] = HMC_STEP_SIZES[args.csv.lower()]
+    else:
+        XX, t = datasets.load_csv(args.csv, relabel_12=args.relabel_12)
     if args.step_size is not None:
         kw["StepSize"] = args.step_size
-    run_experiments(XX, t, args.sampler, args.experiments, args.iterations, args.burn_in, args.seed, **kw)
+    return run_experiments(XX, t, args.sampler, args.experiments, args.iterations, args.burn_in, args.seed, **kw)
 
 
 if __name__ == "__main__":

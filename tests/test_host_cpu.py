@@ -114,47 +114,83 @@ def test_row_shards_partition_the_rows():
 
 
 def _gloo_worker(rank, world, port, q):
+    """One rank of a chain-sharded run on CPU: the repo's partition (engine.shard_chains), its Gelman-Rubin sufficient
+    statistics (engine.chain_moments, the host mirror of what rmhmc_stats_gather exchanges) and the finishing formula
+    (engine.rhat_from_moments = k_rhat_finish), with gloo standing in for the library's NCCL all-reduce."""
     import ctypes
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    # the row-sharded mode ships rank 0's NCCL unique id (128 bytes from the C ABI) to every rank
     from riemannhamiltonianmontecarlo_b200 import _capi
+    from riemannhamiltonianmontecarlo_b200.engine import chain_moments, rhat_from_moments, shard_chains
+    from oracle import blr_oracle as bo
+    # the communicators are bootstrapped with rank 0's NCCL unique id (128 bytes from the C ABI) sent over torch.distributed
     buf = ctypes.create_string_buffer(128)
     if rank == 0:
         assert _capi.load().rmhmc_comm_unique_id(buf) == 0
     box = [buf.raw]
     dist.broadcast_object_list(box, src=0)
     assert len(box[0]) == 128 and any(box[0])
-    # chain sharding: contiguous blocks, Philox streams keyed by the global chain id
-    c_local = 6
-    offset = rank * c_local
-    ids = torch.arange(offset, offset + c_local, dtype=torch.float64)
-    ess_local = torch.stack([ids + 1.0, 2.0 * ids + 1.0], dim=1)          # stand-in per-chain ESS (C, D)
-    ess_sum = ess_local.sum(dim=0)
+    # every rank builds the same global (C, S, D) array and keeps only ITS chains
+    c_total, n_s, d = 13, 200, 3
+    rng = np.random.default_rng(77)
+    full = rng.normal(0, 1, (c_total, n_s, d)).cumsum(axis=1) * 0.05 + rng.normal(0, 1, (c_total, 1, d)) * np.array([0.0, 0.3, 1.0])
+    c0, c1 = shard_chains(c_total, rank, world)
+    mine = full[c0:c1]
+    ess_sum = torch.from_numpy(np.sum([bo.ess(mine[i], n_s - 1)[:, 0] for i in range(c1 - c0)], axis=0))
+    buf_t = torch.from_numpy(np.concatenate([chain_moments(mine).ravel(), [float(c1 - c0)]]))
     dist.all_reduce(ess_sum, op=dist.ReduceOp.SUM)
+    dist.all_reduce(buf_t, op=dist.ReduceOp.SUM)
     tmax = torch.tensor([1.0 + rank], dtype=torch.float64)
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    gathered = [torch.zeros_like(ess_local) for _ in range(world)]
-    dist.all_gather(gathered, ess_local)
-    q.put((rank, ess_sum.tolist(), float(tmax.item()), torch.cat(gathered).shape[0]))
+    rhat = rhat_from_moments(buf_t[:-1].numpy().reshape(3, d), int(buf_t[-1].item()), n_s)
+    q.put((rank, (c0, c1), ess_sum.tolist(), rhat.tolist(), float(tmax.item())))
     dist.destroy_process_group()
 
 
-def test_two_rank_statistics_gather_over_gloo():
-    """The N>1 reduction the bench does over NCCL (sum of per-chain ESS, max of time), on gloo."""
+def test_two_rank_chain_sharded_statistics_over_gloo():
+    """N > 1 host logic of BASELINE.json configs[3] on CPU (world_size 2, gloo): the partition covers every chain once
+    and the combined statistics equal the single-process oracle on all chains."""
     import torch.multiprocessing as mp
+    from oracle import blr_oracle as bo
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in procs)
+    res = sorted(q.get(timeout=180) for _ in procs)
     for p in procs:
         p.join(timeout=60)
-    ids = np.arange(12.0)
-    for rank, ess_sum, tmax, n in res:
-        assert ess_sum == [float((ids + 1).sum()), float((2 * ids + 1).sum())]
-        assert tmax == 2.0 and n == 12
+    c_total, n_s, d = 13, 200, 3
+    rng = np.random.default_rng(77)
+    full = rng.normal(0, 1, (c_total, n_s, d)).cumsum(axis=1) * 0.05 + rng.normal(0, 1, (c_total, 1, d)) * np.array([0.0, 0.3, 1.0])
+    ess_ref = np.sum([bo.ess(full[i], n_s - 1)[:, 0] for i in range(c_total)], axis=0)
+    rhat_ref = bo.rhat(full)
+    assert [r[1] for r in res] == [(0, 7), (7, 13)]
+    for rank, span, ess_sum, rhat, tmax in res:
+        assert np.allclose(ess_sum, ess_ref, rtol=1e-12) and np.allclose(rhat, rhat_ref, rtol=1e-12) and tmax == 2.0
+
+
+def test_dataset_dispatch_and_ripley_cubic_basis(tmp_path):
+    """datasets.load_dataset: the MATLAB drivers' per-data-set preparation (BLR_RMHMC.m:9-178) -- relabelling for german /
+    heart, the cubic basis [1, X, X^2, X^3] for ripley (D = 7), population-std standardisation as in main.py:34-37."""
+    from riemannhamiltonianmontecarlo_b200 import datasets
+    rng = np.random.default_rng(11)
+    x = rng.normal(1.0, 2.0, (50, 2))
+    lab01 = (rng.random(50) < 0.5).astype(float)
+    np.savetxt(tmp_path / "ripley.csv", np.hstack([x, lab01[:, None]]), delimiter=",")
+    np.savetxt(tmp_path / "german.csv", np.hstack([x, lab01[:, None] + 1.0]), delimiter=",")
+    xx, t = datasets.load_dataset("Ripley", str(tmp_path))
+    xs = (x - x.mean(0)) / x.std(0)
+    assert xx.shape == (50, 7) and np.array_equal(t[:, 0], lab01)
+    assert np.array_equal(xx[:, 0], np.ones(50))
+    assert np.allclose(xx[:, 1:3], xs) and np.allclose(xx[:, 3:5], xs ** 2) and np.allclose(xx[:, 5:7], xs ** 3)
+    xg, tg = datasets.load_dataset("german", str(tmp_path))
+    assert xg.shape == (50, 3) and np.array_equal(tg[:, 0], lab01)          # {1, 2} -> {0, 1}
+    assert np.array_equal(xg, datasets.load_csv(str(tmp_path / "german.csv"), relabel_12=True)[0])
+    with pytest.raises(ValueError):
+        datasets.load_dataset("mnist", str(tmp_path))
+    from riemannhamiltonianmontecarlo_b200 import harness
+    assert set(harness.HMC_STEP_SIZES) == set(datasets.DATASETS)

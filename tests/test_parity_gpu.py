@@ -339,6 +339,45 @@ def test_dropin_rmhmc_follows_global_numpy_rng(pkg, golden):
     assert rel_err(w[1:], fx["samples"][0, 1:]) < RTOL
 
 
+def test_dropin_hmc_follows_global_numpy_rng(pkg, golden):
+    """HMC(XX, t, ...) consumes np.random like the reference (randn(1,D) -> rand() -> [rand() iff Ratio <= 0],
+    hmc.py:41,48,77): replay chain 0 of a golden fixture through it."""
+    fx = golden("hmc_pima_real")
+    n_iter, burn_in, d = int(fx["n_iter"]), int(fx["burn_in"]), fx["xx"].shape[1]
+    used = ~(fx["ratio"][0] > 0)                       # the uniform is drawn only when Ratio > 0 is false
+    calls = []
+    for it in range(n_iter):
+        calls += [("randn2", fx["z"][it, 0]), ("rand", fx["u_step"][it, 0])]
+        if used[it]:
+            calls.append(("rand", fx["u_acc"][it, 0]))
+    state = {"i": 0}
+    real = (np.random.randn, np.random.rand, np.random.get_state, np.random.set_state)
+
+    def randn(*shape):
+        kind, val = calls[state["i"]]
+        state["i"] += 1
+        assert kind == "randn2" and len(shape) == 2, (kind, shape)
+        return val.reshape(shape).copy()
+
+    def rand(*shape):
+        if state["i"] >= len(calls) or calls[state["i"]][0] != "rand":
+            return 0.5                      # speculative draw that will be rolled back
+        kind, val = calls[state["i"]]
+        state["i"] += 1
+        return float(val)
+
+    np.random.randn, np.random.rand = randn, rand
+    np.random.get_state = lambda: ("fake", state["i"])
+    np.random.set_state = lambda s_: state.update(i=s_[1])
+    try:
+        w, secs = pkg.HMC(fx["xx"], fx["t"], n_iter, burn_in, int(fx["n_leapfrog"]), float(fx["step_size"]), verbose=False)
+    finally:
+        np.random.randn, np.random.rand, np.random.get_state, np.random.set_state = real
+    assert w.shape == (n_iter - burn_in, d) and secs > 0 and state["i"] == len(calls)
+    assert rel_err(w[1:], fx["samples"][0, 1:]) < RTOL
+    assert np.all(w[0] == 0.0)                          # hmc.py:28,83: row 0 stays zero
+
+
 def test_philox_chains_reach_the_reference_posterior(pkg, golden):
     """Long-run agreement: pooled posterior mean/variance of many short Philox chains vs a
     6000-iteration reference chain, within Monte-Carlo error."""
@@ -559,6 +598,27 @@ def test_rhat_matches_oracle(pkg):
     import torch
     t = torch.from_numpy(np.concatenate([chains, chains], axis=1)).cuda()[:, 5:45]
     assert rel_err(pkg.rhat_batched(t).cpu().numpy(), bo.rhat(view)) < 1e-12
+
+
+def test_stats_gather_matches_oracle(pkg):
+    """rmhmc_stats_gather (the library-side combination bench.py uses; one NCCL rank here): ESS sums with frozen chains
+    counted as zero, Rhat of a strided sample window, scalar sums."""
+    import torch
+    rng = np.random.default_rng(21)
+    chains = rng.normal(0, 1, (70, 120, 5)).cumsum(axis=1) * 0.1 + rng.normal(0, 0.5, (70, 1, 5))
+    xx, t = pkg.datasets.synthetic_logistic(64, 5, 3)
+    data = pkg.LogisticData(xx, t)
+    data.init_stats_comm(0, 1)
+    samp = torch.from_numpy(np.concatenate([chains, chains], axis=1)).cuda()[:, 7:111]        # strided window
+    ess = pkg.ess_batched(samp.contiguous())
+    ess[3, 2] = float("nan")
+    ess_sum, rhat, scal = data.stats_gather(ess=ess, samples=samp, scalars=torch.tensor([1.5, 2.0], device="cuda"))
+    data.close()
+    ref_ess = np.stack([bo.ess(chains[c, 7:111], 103)[:, 0] for c in range(70)])
+    ref_ess[3, 2] = 0.0
+    assert rel_err(ess_sum.cpu().numpy(), ref_ess.sum(axis=0)) < 1e-10
+    assert rel_err(rhat.cpu().numpy(), bo.rhat(chains[:, 7:111])) < 1e-12
+    assert scal.cpu().tolist() == [1.5, 2.0]
 
 
 def test_update_data_rebinds_every_derived_array(pkg):
