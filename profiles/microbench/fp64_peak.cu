@@ -105,13 +105,22 @@ static int run(const char* name, K kern, int threads, int blocks_per_sm, double 
     int nsm = 148;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int w = 0; w < 3; ++w) kern<<<nsm * blocks_per_sm, threads>>>(d, 1.0000001, 1e-9);
-    CK(cudaDeviceSynchronize());
+    {
+        // a launch that does not fit (e.g. 1024 threads of a >64-register kernel) must not be printed as a result
+        cudaError_t le = cudaGetLastError();
+        if (le == cudaSuccess) le = cudaDeviceSynchronize();
+        if (le != cudaSuccess) {
+            printf("%-28s threads=%4d blk/SM=%d  launch failed (%s): skipped\n", name, threads, blocks_per_sm, cudaGetErrorString(le));
+            return 0;
+        }
+    }
     float best = 1e30f;
     for (int r = 0; r < 5; ++r) {
         cudaEventRecord(e0);
         kern<<<nsm * blocks_per_sm, threads>>>(d, 1.0000001, 1e-9);
         cudaEventRecord(e1);
         CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (ms < best) best = ms;
     }

@@ -120,6 +120,16 @@ struct rmhmc_handle {
     CUtensorMap map_b;
     signed char* a8 = nullptr;      // [S][c_pad][kp] (with the chains)
     CUtensorMap map_a;
+    // leverage GEMM h = q . KR2(X)^T on the same kernel: digits of KR2(X) by data row (per data set), of q (per chain set)
+    bool i8_leverage = true;        // RMHMC_I8_LEVERAGE=0: keep the FP64 DMMA GEMM
+    signed char* bl8 = nullptr;     // [S][bl_rows][kpl]
+    double2* colinfo_l = nullptr;   // [bl_rows]
+    double* rowmax_l = nullptr;     // [Np]
+    int i8_kpl = 0, i8_bl_rows = 0;
+    CUtensorMap map_bl;
+    signed char* aq8 = nullptr;     // [S][c_pad][kpl] (with the chains)
+    double* qscale = nullptr;       // [c_pad]
+    CUtensorMap map_aq;
     // kernel-variant selection that depends on the chain count (few chains: SM-filling variants); tests pin it
     int launch_regime = RMHMC_REGIME_AUTO;
     int64_t tape_base = 0, tape_window = 0;      // iterations covered by the host tape (rng_mode 0)
@@ -504,7 +514,30 @@ int launch_tbuild(rmhmc_handle* h, int64_t C, const double* cbuf, double* tpack,
 
 // leverages of the newest metric, hbuf[c][n] = x_n^T G_c^-1 x_n = sum_pairs q_c[pair] KR2(X)[n][pair]: the same
 // TMA-fed DMMA GEMM as the partials build with (A, B, K, columns) = (qpack, KR2(X)^T, P2k, Np)
+template <int S>
+int i8_leverage_s(rmhmc_handle* h) {
+    const int64_t C = h->n_chains;
+    {
+        Bracket b(h, 8);
+        k_i8_qdigits<S><<<blocks_for(C, 8), 256, 0, h->stream>>>(h->S.qpack, h->p2, h->p2k, h->aq8, (size_t)h->c_pad * h->i8_kpl,
+                                                                  h->i8_kpl, h->qscale, (int)C);
+    }
+    I8GemmArgs g{};
+    g.g_out = h->S.hbuf; g.colinfo = h->colinfo_l; g.alpha_inv = 0.0; g.rowscale = h->qscale;
+    g.n_chains = (int)C; g.p2 = h->n_rows_pad; g.p2p = h->n_rows_pad; g.k_blocks = h->i8_kpl / kI8BlockK;
+    g.a_rows = (int)h->c_pad; g.b_rows = h->i8_bl_rows; g.debug_class = -1;
+    cudaError_t e;
+    {
+        Bracket b(h, 6);
+        e = i8_launch_gemm<S>(h->map_aq, h->map_bl, g, h->stream);
+    }
+    if (e != cudaSuccess) return fail(h, RMHMC_E_CUDA, std::string("k_i8_gemm (leverage): ") + cudaGetErrorString(e));
+    h->launches += 2;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
 int launch_leverage(rmhmc_handle* h) {
+    if (h->aq8 && use_i8(h)) return h->i8_slices == 6 ? i8_leverage_s<6>(h) : i8_leverage_s<5>(h);
     TBuildArgs a{};
     a.kr3 = h->kr2t; a.cbuf = h->S.qpack; a.tpack = h->S.hbuf; a.cur = h->S.cur; a.flip = 0; a.slot_stride = 0;
     a.n_chains = (int)h->n_chains; a.n_rows_pad = h->p2k; a.p3 = h->n_rows_pad; a.p3p = h->n_rows_pad;
@@ -535,7 +568,7 @@ void free_chains(rmhmc_handle* h) {
     h->chain_allocs.clear();
     h->S = ChainArrays{};
     h->t_tmp = nullptr;
-    h->a8 = nullptr;
+    h->a8 = nullptr; h->aq8 = nullptr; h->qscale = nullptr;
     h->n_chains = 0;
 }
 
@@ -598,6 +631,15 @@ int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
         if (!rc && !make_tensor_map_u8_k64(&h->map_a, h->a8, (uint64_t)h->i8_slices * h->c_pad, (uint64_t)h->i8_kp, kI8TileM)) {
             free_chains(h);
             return fail(h, RMHMC_E_CUDA, "cuTensorMapEncodeTiled failed for the V digit planes");
+        }
+    }
+    h->aq8 = nullptr; h->qscale = nullptr;
+    if (!hmc && use_i8(h) && h->bl8 && h->matrix_free) {
+        rc |= dev_alloc(h, &h->aq8, (size_t)h->i8_slices * h->c_pad * h->i8_kpl, tr);
+        rc |= dev_alloc(h, &h->qscale, (size_t)h->c_pad, tr);
+        if (!rc && !make_tensor_map_u8_k64(&h->map_aq, h->aq8, (uint64_t)h->i8_slices * h->c_pad, (uint64_t)h->i8_kpl, kI8TileM)) {
+            free_chains(h);
+            return fail(h, RMHMC_E_CUDA, "cuTensorMapEncodeTiled failed for the q digit planes");
         }
     }
     rc |= dev_alloc(h, &S.mom, c * D, tr);
@@ -915,7 +957,21 @@ int i8_form_b_planes(rmhmc_handle* h, cudaStream_t st) {
     CUDA_TRY(h, cudaGetLastError());
     return RMHMC_OK;
 }
-int i8_form_b(rmhmc_handle* h, cudaStream_t st) { return h->i8_slices == 6 ? i8_form_b_planes<6>(h, st) : i8_form_b_planes<5>(h, st); }
+template <int S>
+int i8_form_bl_planes(rmhmc_handle* h, cudaStream_t st) {
+    k_i8_rowmax<<<blocks_for(h->n_rows_pad, 8), 256, 0, st>>>(h->x_pad, h->pair_tab, h->rowmax_l, h->n_rows_pad, h->xs, h->p2);
+    const long long n = (long long)h->i8_bl_rows * h->i8_kpl;
+    k_i8_form_bl<S><<<blocks_for(n, 256), 256, 0, st>>>(h->x_pad, h->pair_tab, h->rowmax_l, h->bl8, h->colinfo_l, h->n_rows_pad,
+                                                        h->xs, h->p2, h->i8_bl_rows, h->i8_kpl);
+    h->launches += 2;
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+int i8_form_b(rmhmc_handle* h, cudaStream_t st) {
+    int rc = h->i8_slices == 6 ? i8_form_b_planes<6>(h, st) : i8_form_b_planes<5>(h, st);
+    if (!rc && h->bl8) rc = h->i8_slices == 6 ? i8_form_bl_planes<6>(h, st) : i8_form_bl_planes<5>(h, st);
+    return rc;
+}
 
 // digit planes of KR2(X)^T + their tensor map; leaves i8_ok false when the shape is outside the kernel's range
 int i8_setup(rmhmc_handle* h) {
@@ -926,10 +982,20 @@ int i8_setup(rmhmc_handle* h) {
     CUDA_TRY(h, cudaMalloc((void**)&h->b8, (size_t)S * h->i8_b_rows * h->i8_kp));
     CUDA_TRY(h, cudaMalloc((void**)&h->colinfo, (size_t)h->i8_b_rows * sizeof(double2)));
     CUDA_TRY(h, cudaMalloc((void**)&h->colmax, (size_t)h->p2p * 8));
+    if (const char* e = std::getenv("RMHMC_I8_LEVERAGE")) h->i8_leverage = std::atoi(e) != 0;
+    if (h->i8_leverage && h->kr2t) {
+        h->i8_kpl = pad_up(h->p2, kI8BlockK);
+        h->i8_bl_rows = (h->n_rows_pad + nc - 1) / nc * nc;
+        CUDA_TRY(h, cudaMalloc((void**)&h->bl8, (size_t)S * h->i8_bl_rows * h->i8_kpl));
+        CUDA_TRY(h, cudaMalloc((void**)&h->colinfo_l, (size_t)h->i8_bl_rows * sizeof(double2)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->rowmax_l, (size_t)h->n_rows_pad * 8));
+    }
     int rc = i8_form_b(h, h->stream);
     if (rc) return rc;
     if (!make_tensor_map_u8_k64(&h->map_b, h->b8, (uint64_t)S * h->i8_b_rows, (uint64_t)h->i8_kp, (uint32_t)nc))
         return fail(h, RMHMC_E_CUDA, "cuTensorMapEncodeTiled failed for the KR2(X) digit planes");
+    if (h->bl8 && !make_tensor_map_u8_k64(&h->map_bl, h->bl8, (uint64_t)S * h->i8_bl_rows, (uint64_t)h->i8_kpl, (uint32_t)nc))
+        return fail(h, RMHMC_E_CUDA, "cuTensorMapEncodeTiled failed for the leverage digit planes");
     h->i8_ok = true;
     return RMHMC_OK;
 }
@@ -1332,7 +1398,7 @@ void rmhmc_destroy(rmhmc_handle* h) {
     free_chains(h);
     if (h->comm) nccl_api().CommDestroy(h->comm);
     if (h->stats_comm) nccl_api().CommDestroy(h->stats_comm);
-    cudaFree(h->b8); cudaFree(h->colinfo); cudaFree(h->colmax); cudaFree(h->split_buf); cudaFree(h->kr2n); cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->kr2t); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
+    cudaFree(h->b8); cudaFree(h->colinfo); cudaFree(h->colmax); cudaFree(h->bl8); cudaFree(h->colinfo_l); cudaFree(h->rowmax_l); cudaFree(h->split_buf); cudaFree(h->kr2n); cudaFree(h->x_pad); cudaFree(h->kr3); cudaFree(h->kr2t); cudaFree(h->pair_tab); cudaFree(h->tri_tab); cudaFree(h->tidx); cudaFree(h->tidx32);
     cudaFree(h->pair_a); cudaFree(h->pair_b); cudaFree(h->d_remaining);
     delete h;
 }

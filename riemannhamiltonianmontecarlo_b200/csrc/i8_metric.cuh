@@ -58,7 +58,8 @@ struct I8GemmArgs {
     double* g_out;              // [C][P2p] packed metric
     const double2* colinfo;     // [columns] {sA sB[col] 2^(8(S-1) - 2 BITS), 1 if diagonal pair else 0}; {0, 0} for padding
     double alpha_inv;
-    int n_chains, p2, p2p, k_blocks;
+    const double* rowscale;     // [C] per-chain scale of the A operand, or null (1): the leverage GEMM's q digits
+    int n_chains, p2, p2p, k_blocks;      // p2 valid output columns, p2p = row stride of g_out (columns < p2p are stored)
     int a_rows, b_rows;         // rows per digit plane in the A / B tensor maps
     int debug_class;            // >= 0: write accumulator `class` alone (self-test)
 };
@@ -124,6 +125,88 @@ __global__ void k_i8_form_b(const double* __restrict__ x, const uchar2* __restri
 #pragma unroll
     for (int s = 0; s < S; ++s)      // digit s has weight 256^(S-1-s)
         b8[((size_t)s * b_rows + col) * kp + n] = (signed char)(((u >> (8 * (S - 1 - s))) & 0xFF) ^ 0x80);
+}
+
+// ------------------------------------------------------------------------------------------------ leverage GEMM operands
+// h[c][n] = x_n^T G_c^-1 x_n = sum_pairs q_c[pair] KR2(X)[n][pair]  (rmhmc.py:76-77 via the matrix-free identity): the same
+// digit GEMM with (A, B, K, columns) = (q digits, KR2(X) digits by data row, packed pairs, data rows).
+// max over the packed pairs of |x_na x_nb| per data row (one warp per row)
+__global__ void k_i8_rowmax(const double* __restrict__ x, const uchar2* __restrict__ pair_tab, double* __restrict__ rowmax,
+                            int n_rows_pad, int xs, int p2) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= n_rows_pad) return;
+    double m = 0.0;
+    for (int k = lane; k < p2; k += 32) { const uchar2 ab = pair_tab[k]; m = fmax(m, fabs(x[(size_t)n * xs + ab.x] * x[(size_t)n * xs + ab.y])); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) rowmax[n] = m;
+}
+// bl8[s][n][k]: digits of KR2(X)[n][k] / sBL[n] (zero for n >= n_rows_pad, k >= p2); colinfo_l[n] = {sBL[n] 2^(8(S-1) - 2 BITS), 0}
+template <int S>
+__global__ void k_i8_form_bl(const double* __restrict__ x, const uchar2* __restrict__ pair_tab, const double* __restrict__ rowmax,
+                             signed char* __restrict__ bl8, double2* __restrict__ colinfo_l, int n_rows_pad, int xs, int p2,
+                             int bl_rows, int kpl) {
+    constexpr int BITS = I8Shape<S>::BITS;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)bl_rows * kpl) return;
+    const int n = (int)(i / kpl), k = (int)(i - (long long)n * kpl);
+    long long I = 0;
+    if (n < n_rows_pad) {
+        const double m = rowmax[n], sb = m > 0.0 ? m / 0.99 : 1.0;
+        if (k < p2) {
+            const uchar2 ab = pair_tab[k];
+            I = __double2ll_rn(x[(size_t)n * xs + ab.x] * x[(size_t)n * xs + ab.y] / sb * exp2((double)BITS));
+        }
+        if (k == 0) colinfo_l[n] = make_double2(sb * exp2((double)(8 * (S - 1) - 2 * BITS)), 0.0);
+    } else if (k == 0) {
+        colinfo_l[n] = make_double2(0.0, 0.0);
+    }
+    long long bias = 0;
+#pragma unroll
+    for (int j = 0; j < S; ++j) bias = bias * 256 + 128;
+    const unsigned long long u = (unsigned long long)(I + bias);
+#pragma unroll
+    for (int s = 0; s < S; ++s) bl8[((size_t)s * bl_rows + n) * kpl + k] = (signed char)(((u >> (8 * (S - 1 - s))) & 0xFF) ^ 0x80);
+}
+// digits of the packed inverse metric q_c (chain_kernels.cuh: qpack, off-diagonal pairs doubled) scaled by the chain's
+// max |q| / 0.99 -> aq8[s][c][k], qscale[c].  One warp per chain; lane l < kpl / 16 converts 16 consecutive entries.
+template <int S>
+__global__ void k_i8_qdigits(const double* __restrict__ qpack, int p2, int p2k, signed char* __restrict__ aq8, size_t plane_stride,
+                             int kpl, double* __restrict__ qscale, int n_chains) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= n_chains) return;
+    const double* q = qpack + (size_t)c * p2k;
+    double m = 0.0;
+    for (int k = lane; k < p2; k += 32) m = fmax(m, fabs(q[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const double sa = m > 0.0 && m < 1e300 ? m / 0.99 : 1.0;     // NaN / inf metric (diverged chain): digits are meaningless, h becomes NaN via qscale
+    if (lane == 0) qscale[c] = (m == m && m < 1e300) ? sa : __longlong_as_double(0x7ff8000000000000LL);
+    const double factor = (1.0 / sa) * (double)(1ull << 31) * (double)(1ull << (I8Shape<S>::BITS - 31));
+    for (int k0 = lane * 16; k0 < kpl; k0 += 32 * 16) {
+        unsigned lo[16], hi[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const double v = k0 + j < p2 ? q[k0 + j] : 0.0;
+            const double vc = v == v ? fmin(fmax(v, -sa), sa) : 0.0;
+            const double t = fma(vc, factor, i8_magic(S));
+            lo[j] = (unsigned)__double2loint(t);
+            hi[j] = (unsigned)__double2hiint(t);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int byte = S - 1 - s;
+            const unsigned b = byte & 3;
+            unsigned w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned v0 = byte < 4 ? lo[4 * j] : hi[4 * j], v1 = byte < 4 ? lo[4 * j + 1] : hi[4 * j + 1];
+                const unsigned v2 = byte < 4 ? lo[4 * j + 2] : hi[4 * j + 2], v3 = byte < 4 ? lo[4 * j + 3] : hi[4 * j + 3];
+                w[j] = __byte_perm(__byte_perm(v0, v1, b | ((4 + b) << 4)), __byte_perm(v2, v3, b | ((4 + b) << 4)), 0x5410) ^ 0x80808080u;
+            }
+            *reinterpret_cast<uint4*>(aq8 + (size_t)s * plane_stride + (size_t)c * kpl + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ A planes
@@ -642,6 +725,8 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
         mbar_wait_or_trap(acc_full, 0);          // all MMAs done: accumulators final, the operand ring is free
         tcgen05_fence_after();
         double* out_s = reinterpret_cast<double*>(base) + (size_t)ew * 32 * OS;
+        const int c_lane = m0 + quarter * 32 + lane;
+        const double rs = (a.rowscale && c_lane < a.n_chains) ? a.rowscale[c_lane] : 1.0;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
         for (int cg = cg_begin; cg < cg_end; ++cg) {
@@ -666,7 +751,7 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
                     for (int w = 0; w < S; ++w) if (w == a.debug_class) t = x[w];
                 }
                 const double2 ci = ci_s[cg * 16 + j];
-                out_s[lane * OS + (cg - cg_begin) * 16 + j] = n0 + cg * 16 + j < a.p2 ? fma(t, ci.x, ci.y * a.alpha_inv) : 0.0;
+                out_s[lane * OS + (cg - cg_begin) * 16 + j] = n0 + cg * 16 + j < a.p2 ? fma(t * rs, ci.x, ci.y * a.alpha_inv) : 0.0;
             }
         }
         __syncwarp();
