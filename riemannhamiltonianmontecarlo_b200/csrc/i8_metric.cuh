@@ -31,7 +31,7 @@ namespace rmhmc {
 constexpr double kI8ScaleA = 0.26;        // v / sA <= 0.962: inside the balanced-digit range (|y| < 0.996)
 constexpr int kI8TileM = 128;             // chains per GEMM CTA (= TMEM lanes)
 constexpr int kI8BlockK = 64;             // bytes of K per pipeline stage (one SWIZZLE_64B row)
-constexpr int kI8GemmThreads = 320;       // warp 0: TMA producer, warp 1: TMEM allocation + MMA issue, warps 2-9: epilogue
+constexpr int kI8GemmThreads = 448;       // warp 0: TMA producer, warp 1: TMEM allocation + MMA issue, warps 2-13: epilogue
 constexpr int kI8MaxRows = 16384;         // S * K * 2^14 < 2^31
 constexpr int kI8VsThreads = 128;         // chains per k_i8_vslice CTA
 constexpr int kI8VsRows = 32;             // rows per staged X block
@@ -652,12 +652,25 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
     const int n0 = blockIdx.x * NC;                 // first packed column
     const int m0 = blockIdx.y * kI8TileM;           // first chain
 
+    // one stage of operands: S digit tiles of V (128 chains x 64 bytes of K) and S of KR2(X) (NC columns x 64 bytes)
+    auto issue_stage = [&](int kb) {
+        const int st = kb % ST;
+        unsigned char* sa = base + (size_t)st * Sh::STAGE_BYTES;
+        unsigned char* sb = sa + S * Sh::A_SLICE;
+        mbar_expect_tx(&full[st], Sh::STAGE_BYTES);
+#pragma unroll
+        for (int s = 0; s < S; ++s) tma_load_2d(sa + s * Sh::A_SLICE, &map_a, kb * kI8BlockK, s * a.a_rows + m0, &full[st]);
+#pragma unroll
+        for (int s = 0; s < S; ++s) tma_load_2d(sb + s * Sh::B_SLICE, &map_b, kb * kI8BlockK, s * a.b_rows + n0, &full[st]);
+    };
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         mbar_fence_init();
+        // the first stages need neither TMEM nor the other warps: their latency overlaps the allocation and the CTA barrier
+        for (int kb = 0; kb < ST && kb < a.k_blocks; ++kb) issue_stage(kb);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tcgen05_fence_before();
@@ -667,16 +680,9 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < a.k_blocks; ++kb) {
-                const int st = kb % ST;
-                if (kb >= ST) mbar_wait_or_trap(&empty[st], (uint32_t)(((kb / ST) - 1) & 1));
-                unsigned char* sa = base + (size_t)st * Sh::STAGE_BYTES;
-                unsigned char* sb = sa + S * Sh::A_SLICE;
-                mbar_expect_tx(&full[st], Sh::STAGE_BYTES);
-#pragma unroll
-                for (int s = 0; s < S; ++s) tma_load_2d(sa + s * Sh::A_SLICE, &map_a, kb * kI8BlockK, s * a.a_rows + m0, &full[st]);
-#pragma unroll
-                for (int s = 0; s < S; ++s) tma_load_2d(sb + s * Sh::B_SLICE, &map_b, kb * kI8BlockK, s * a.b_rows + n0, &full[st]);
+            for (int kb = ST; kb < a.k_blocks; ++kb) {
+                mbar_wait_or_trap(&empty[kb % ST], (uint32_t)(((kb / ST) - 1) & 1));
+                issue_stage(kb);
             }
         }
     } else if (warp == 1) {
@@ -710,13 +716,13 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
             umma_commit(acc_full);
         }
     } else {
-        // ---- epilogue (8 warps): warp w reads TMEM lanes 32 (w % 4) .. + 31 = chains m0 + 32 (w % 4) + lane, the two
+        // ---- epilogue (12 warps): warp w reads TMEM lanes 32 (w % 4) .. + 31 = chains m0 + 32 (w % 4) + lane, the three
         // warps of a lane quarter split the column groups.  int32 classes -> FP64 exactly (magic-number conversion on
         // the integer pipe + one DADD), classes recombined with exact FMAs and ONE rounding, scaled, staged through the
         // (now idle) operand ring so that the global stores are contiguous 256-byte row segments.
-        const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
-        constexpr int G0 = 3;                                   // column groups of the first warp of a quarter
-        const int cg_begin = half ? G0 : 0, cg_end = half ? NC / 16 : G0;
+        const int ew = warp - 2, quarter = warp & 3, third = ew >> 2;
+        constexpr int G0 = 2;                                   // column groups (of 16) per warp: three warps per lane quarter
+        const int cg_begin = third * G0, cg_end = cg_begin + G0 < NC / 16 ? cg_begin + G0 : NC / 16;
         const int ncols = (cg_end - cg_begin) * 16;
         constexpr int OS = G0 * 16 + 1;                         // staging row stride (doubles): odd -> conflict-free
         double2* ci_s = reinterpret_cast<double2*>(bars + 16);              // [NC] column scales of this CTA
@@ -764,8 +770,8 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
                 if (c < a.n_chains && col0 + col < a.p2p) a.g_out[(size_t)c * a.p2p + col0 + col] = out_s[row * OS + col];
             }
         };
-        if (ncols == 48) copy_out(std::integral_constant<int, 48>{});
-        else copy_out(std::integral_constant<int, 32>{});
+        if (ncols == 32) copy_out(std::integral_constant<int, 32>{});
+        else if (ncols == 16) copy_out(std::integral_constant<int, 16>{});
         tcgen05_fence_before();
     }
     __syncthreads();
