@@ -423,12 +423,14 @@ def gpu_main(args):
         work["metric_closing"] = (4.0 * C * N * D, "fp64")          # k_metric<MODE 2>: f = X theta and X^T (t - p)
     if metric_mode == "i8" and args.sampler != "hmc":        # kinds 0 / 1 are the sums of the two i8 kernels there
         work.pop("metric_fp"); work.pop("metric_closing")
+        if args.partials == "matrix_free" and os.environ.get("RMHMC_I8_LEVERAGE", "1") != "0":
+            work["leverage_gemm"] = (2.0 * n_digit_products * C * N * P2, "i8")     # the same digit GEMM, K = packed pairs
     names = {
         "metric_fp": "k_metric<MODE 0> (f = X theta, G = V . KR2(X), FP64 DMMA.8x8x4)",
         "metric_closing": "k_metric<MODE 1|2> (closing build / HMC gradient, FP64 DMMA.8x8x4)",
         "partials": "k_tbuild_pre (partials build T = Cw . KR3(X), FP64 DMMA.8x8x4)",
         "quad_pass": "k_pass<MOMFP> (implicit momentum fixed point: F quadratic-form passes, FP64 DMMA.8x8x4)",
-        "leverage_gemm": "k_tbuild_pre (leverage GEMM h = q . KR2(X)^T, FP64 DMMA.8x8x4)",
+        "leverage_gemm": "leverage GEMM h = q . KR2(X)^T (k_i8_gemm in INT8 metric mode, else k_tbuild_pre on FP64 DMMA.8x8x4)",
         "trace_pass": "k_pass<PAIR|TRACE> (tr(G^-1 dG_d) and u^T dG_d u passes, FP64 DMMA.8x8x4)",
         "i8_gemm": "k_i8_gemm (G = V . KR2(X) as 15 exact INT8 digit GEMMs: tcgen05.mma.kind::i8, TMEM, tensor-map TMA)",
         "i8_vslice": "k_i8_vslice_mma / k_i8_vslice (f = X theta, logistic terms, base-256 digits of v; FP64)",
@@ -459,8 +461,10 @@ def gpu_main(args):
     NCU_TRAFFIC = {
         ("german", 65536, "metric_fp"): (13.44e6 + 117.75e6, "profiles/r01/ncu_v3_metric_fp_raw.csv"),
         ("german", 65536, "partials"): (539.19e6 + 1487.65e6, "profiles/r01/ncu_v2_tbuild_raw.csv"),
-        ("german", 65536, "i8_gemm"): (337.59e6 + 144.84e6, "profiles/r02/ncu_i8_gemm_v2_raw.csv"),
-        ("german", 65536, "quad_pass"): (5235.48e6 + 37.63e6, "profiles/r01/ncu_v3_mom_fixed_point_raw.csv"),
+        ("german", 65536, "i8_gemm"): (337.59e6 + 144.97e6, "profiles/r02/ncu_r02_i8_gemm_metric_raw.csv"),
+        ("german", 65536, "quad_pass"): (5233.21e6 + 38.79e6, "profiles/r02/ncu_r02_mom_fixed_point_raw.csv"),
+        ("german", 65536, "i8_vslice"): (25.08e6 + 286.99e6, "profiles/r02/ncu_r02_i8_vslice_iterate_raw.csv"),
+        ("german", 65536, "chain_solve"): (212.91e6 + 11.90e6, "profiles/r02/ncu_r02_chain_solve_raw.csv"),
     }
     traffic, traffic_src = NCU_TRAFFIC.get((args.workload, C, top), (None, None))
     roof = None
