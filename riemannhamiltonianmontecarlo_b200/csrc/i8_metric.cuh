@@ -31,15 +31,29 @@ namespace rmhmc {
 constexpr double kI8ScaleA = 0.26;        // v / sA <= 0.962: inside the balanced-digit range (|y| < 0.996)
 constexpr int kI8TileM = 128;             // chains per GEMM CTA (= TMEM lanes)
 constexpr int kI8BlockK = 64;             // bytes of K per pipeline stage (one SWIZZLE_64B row)
-constexpr int kI8GemmThreads = 448;       // warp 0: TMA producer, warp 1: TMEM allocation + MMA issue, warps 2-13: epilogue
+// GEMM tile shape.  WIDE (default): one CTA per SM, 128 chains x 96 columns, five accumulators fill 480 of the 512 TMEM
+// columns, 12 epilogue warps.  NARROW (-DRMHMC_I8_NARROW=1): 128 x 48 tiles, 240 TMEM columns, 2-stage ring -> TWO CTAs per
+// SM whose prologue / epilogue overlap the other's MMAs, N = 240 MMAs (all five KR2(X) digits of a K step in one
+// instruction), 336 instead of 384 padded columns -- but 7 instead of 4 reads of the V digits from L2.  Measured
+// (profiles/r02/i8_selftest_v7_n{0,1}.log, German-shaped): WIDE 0.292 / 0.146 / 0.083 / 0.043 ms at 65536 / 32768 / 16384 /
+// 8192 chains, NARROW 0.316 / 0.165 / 0.091 / 0.051 ms (L2 -> SM operand traffic 3.2 GB instead of 2.35 GB per launch);
+// NARROW only wins when WIDE cannot fill the SMs (Australian-shaped 4096 chains: 0.0159 vs 0.0186 ms).
+#ifndef RMHMC_I8_NARROW
+#define RMHMC_I8_NARROW 0
+#endif
 constexpr int kI8MaxRows = 16384;         // S * K * 2^14 < 2^31
 constexpr int kI8VsThreads = 128;         // chains per k_i8_vslice CTA
 constexpr int kI8VsRows = 32;             // rows per staged X block
 
 template <int S> struct I8Shape {
     static_assert(S == 5 || S == 6, "5 or 6 digits");
-    static constexpr int NC = S == 5 ? 96 : 80;            // packed columns per CTA: S * NC <= 512 TMEM columns
-    static constexpr int STAGES = S == 5 ? 3 : 2;
+    static constexpr bool NARROW = RMHMC_I8_NARROW != 0;
+    static constexpr int NC = NARROW ? (S == 5 ? 48 : 32) : (S == 5 ? 96 : 80);      // packed columns per CTA: S * NC <= TMEM columns
+    static constexpr int STAGES = NARROW ? 2 : (S == 5 ? 3 : 2);
+    static constexpr int TMEM_COLS = NARROW ? 256 : 512;
+    static constexpr int EPI_WARPS = NARROW ? 4 : 12;      // warp 0: TMA producer, warp 1: TMEM allocation + MMA issue, then the epilogue
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int CTAS_PER_SM = NARROW ? 2 : 1;
     static constexpr int BITS = 8 * S - 1;                 // operand = rint(y * 2^BITS), |y| < 1
     static constexpr uint32_t A_SLICE = kI8TileM * kI8BlockK, B_SLICE = NC * kI8BlockK;
     static constexpr uint32_t STAGE_BYTES = S * (A_SLICE + B_SLICE);
@@ -636,7 +650,7 @@ __global__ void __launch_bounds__(kI8VcWarps * 32, 2) k_i8_vslice_mma_closing(I8
 
 // ------------------------------------------------------------------------------------------------ the GEMM
 template <int S>
-__global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) k_i8_gemm(const __grid_constant__ CUtensorMap map_a,
                                                                const __grid_constant__ CUtensorMap map_b, I8GemmArgs a) {
     using Sh = I8Shape<S>;
     constexpr int NC = Sh::NC, ST = Sh::STAGES;
@@ -672,7 +686,7 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
         // the first stages need neither TMEM nor the other warps: their latency overlaps the allocation and the CTA barrier
         for (int kb = 0; kb < ST && kb < a.k_blocks; ++kb) issue_stage(kb);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tmem_alloc(tmem_slot, Sh::TMEM_COLS);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -721,13 +735,14 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
         // the integer pipe + one DADD), classes recombined with exact FMAs and ONE rounding, scaled, staged through the
         // (now idle) operand ring so that the global stores are contiguous 256-byte row segments.
         const int ew = warp - 2, quarter = warp & 3, third = ew >> 2;
-        constexpr int G0 = 2;                                   // column groups (of 16) per warp: three warps per lane quarter
+        constexpr int WPQ = Sh::EPI_WARPS / 4;                  // warps per TMEM lane quarter
+        constexpr int G0 = (NC / 16 + WPQ - 1) / WPQ;           // column groups (of 16) per warp
         const int cg_begin = third * G0, cg_end = cg_begin + G0 < NC / 16 ? cg_begin + G0 : NC / 16;
         const int ncols = (cg_end - cg_begin) * 16;
         constexpr int OS = G0 * 16 + 1;                         // staging row stride (doubles): odd -> conflict-free
         double2* ci_s = reinterpret_cast<double2*>(bars + 16);              // [NC] column scales of this CTA
-        for (int i = threadIdx.x - 64; i < NC; i += kI8GemmThreads - 64) ci_s[i] = a.colinfo[n0 + i];
-        asm volatile("bar.sync 1, %0;" ::"n"(kI8GemmThreads - 64) : "memory");
+        for (int i = threadIdx.x - 64; i < NC; i += Sh::THREADS - 64) ci_s[i] = a.colinfo[n0 + i];
+        asm volatile("bar.sync 1, %0;" ::"n"(Sh::THREADS - 64) : "memory");
         mbar_wait_or_trap(acc_full, 0);          // all MMAs done: accumulators final, the operand ring is free
         tcgen05_fence_after();
         double* out_s = reinterpret_cast<double*>(base) + (size_t)ew * 32 * OS;
@@ -770,7 +785,8 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
                 if (c < a.n_chains && col0 + col < a.p2p) a.g_out[(size_t)c * a.p2p + col0 + col] = out_s[row * OS + col];
             }
         };
-        if (ncols == 32) copy_out(std::integral_constant<int, 32>{});
+        if (ncols == 48) copy_out(std::integral_constant<int, 48>{});
+        else if (ncols == 32) copy_out(std::integral_constant<int, 32>{});
         else if (ncols == 16) copy_out(std::integral_constant<int, 16>{});
         tcgen05_fence_before();
     }
@@ -778,7 +794,7 @@ __global__ void __launch_bounds__(kI8GemmThreads, 1) k_i8_gemm(const __grid_cons
     if (warp == 1) {
         __syncwarp();
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, Sh::TMEM_COLS);
     }
 }
 #endif  // __CUDACC__
@@ -855,7 +871,7 @@ inline cudaError_t i8_launch_gemm(const CUtensorMap& map_a, const CUtensorMap& m
         attr_set = true;
     }
     const dim3 grid((unsigned)i8_chunks<S>(a.p2), (unsigned)((a.n_chains + kI8TileM - 1) / kI8TileM));
-    k_i8_gemm<S><<<grid, kI8GemmThreads, I8Shape<S>::SMEM, stream>>>(map_a, map_b, a);
+    k_i8_gemm<S><<<grid, I8Shape<S>::THREADS, I8Shape<S>::SMEM, stream>>>(map_a, map_b, a);
     return cudaGetLastError();
 }
 #endif

@@ -28,7 +28,7 @@ using namespace rmhmc;
 template <int S>
 static int test_raw_gemm() {
     constexpr int NC = I8Shape<S>::NC;
-    const int kp = 6 * kI8BlockK, n_chains = 200, a_rows = 256, p2 = NC + 54, p2p = pad_up(p2, 8), b_rows = 2 * NC;
+    const int kp = 6 * kI8BlockK, n_chains = 200, a_rows = 256, p2 = NC + NC / 2 + 6, p2p = pad_up(p2, 8), b_rows = 2 * NC;
     std::mt19937 rng(123);
     std::uniform_int_distribution<int> dig(-128, 127);
     std::vector<signed char> ha((size_t)S * a_rows * kp), hb((size_t)S * b_rows * kp);
@@ -292,6 +292,9 @@ int main(int argc, char** argv) {
         bad += test_end_to_end<5>(1000, 25, 65536, 0.3, true);
         bad += test_end_to_end<6>(1000, 25, 65536, 0.3, true);
         bad += test_end_to_end<5>(690, 15, 4096, 0.3, true);
+        bad += test_end_to_end<5>(1000, 25, 8192, 0.3, true);
+        bad += test_end_to_end<5>(1000, 25, 16384, 0.3, true);
+        bad += test_end_to_end<5>(1000, 25, 32768, 0.3, true);
     }
     std::printf(bad ? "I8 SELFTEST FAILED (%d)\n" : "I8 SELFTEST OK\n", bad);
     return bad ? 1 : 0;
