@@ -179,6 +179,10 @@ int rmhmc_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
 int rmhmc_read_state(rmhmc_handle* h, double* theta, int64_t* iters, int64_t* accepted,
                      int64_t* leapfrogs, int32_t* renorm_mom, int32_t* renorm_pos);
 
+/* A handle owns ONE chain set: every *_chains_init, rmhmc_leapfrog, rmhmc_set_partials_mode and rmhmc_set_metric_mode
+ * replaces (or frees) it.  The generation counter changes whenever that happens, so that a caller holding a sampler
+ * object can detect that its chains are gone (the Python samplers check it and raise). */
+int64_t rmhmc_chain_generation(const rmhmc_handle* h);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t rmhmc_launch_count(const rmhmc_handle* h);
 
@@ -231,7 +235,8 @@ int mmala_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop);     /* on
 /* ---- tools.py:32-74 batched ------------------------------------------------------------------ */
 /* ESS of every (chain, parameter) series: samples (n_chains x n_samples x dim) with the given
  * strides in doubles; ess (n_chains x dim).  Exactly tools.CalculateESS(series, max_lag) incl. the
- * nFFT = nextpow2(n)+1 circular aliasing.  n_samples <= 24000.  Does not need a handle. */
+ * nFFT = nextpow2(n)+1 circular aliasing; max_lag <= nFFT - 1 as in the reference.  Series of more than 24000 samples
+ * use a global scratch copy instead of shared memory (and synchronise).  Does not need a handle. */
 int blr_ess_batched(int device, void* cuda_stream, const double* samples, int64_t n_chains,
                     int64_t n_samples, int dim, int64_t chain_stride, int64_t row_stride,
                     int64_t max_lag, double* ess);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "rmhmc_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     "rmhmc_read_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rmhmc_launch_count": (c_int64, [c_void_p]),
+    "rmhmc_chain_generation": (c_int64, [c_void_p]),
     "rmhmc_profile_enable": (c_int, [c_void_p, c_int]),
     "rmhmc_profile_read": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),
     "hmc_chains_init": (c_int, [c_void_p, c_int64, c_void_p]),

@@ -132,6 +132,8 @@ struct rmhmc_handle {
     CUtensorMap map_aq;
     // kernel-variant selection that depends on the chain count (few chains: SM-filling variants); tests pin it
     int launch_regime = RMHMC_REGIME_AUTO;
+    int64_t chain_gen = 0;          // bumped whenever the handle's chain set is (re)allocated or freed (rmhmc_chain_generation)
+    bool matrix_free_user = false;  // the caller's partials mode; mmala_chains_init overrides matrix_free for its own chain set only
     int64_t tape_base = 0, tape_window = 0;      // iterations covered by the host tape (rng_mode 0)
     mutable std::string err;
 };
@@ -367,13 +369,18 @@ struct Bracket {
             cudaEventRecord(e0, h->stream);
         }
     }
-    ~Bracket() {
-        if (on) {
-            cudaEventRecord(e1, h->stream);
-            h->prof[kind].ev.emplace_back(e0, e1);
-        }
-    }
+    ~Bracket();
 };
+
+void drain_profile(rmhmc_handle* h);
+Bracket::~Bracket() {
+    if (on) {
+        cudaEventRecord(e1, h->stream);
+        h->prof[kind].ev.emplace_back(e0, e1);
+        // bound the number of live events while profiling stays enabled (draining waits for the recorded launches)
+        if (h->prof[kind].ev.size() >= 16384) drain_profile(h);
+    }
+}
 
 void drain_profile(rmhmc_handle* h) {
     for (auto& slot : h->prof) {
@@ -564,6 +571,7 @@ int dev_alloc(rmhmc_handle* h, T** p, size_t count, std::vector<void*>* track) {
 }
 
 void free_chains(rmhmc_handle* h) {
+    h->chain_gen += 1;
     for (void* p : h->chain_allocs) cudaFree(p);
     h->chain_allocs.clear();
     h->S = ChainArrays{};
@@ -1357,7 +1365,7 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
             long long n = (long long)h->n_rows_pad * h->p2k;
             k_form_kr2t<<<blocks_for(n, 256), 256>>>(h->x_pad, h->pair_tab, h->kr2t, h->n_rows_pad, h->xs, h->p2, h->p2k);
             CREATE_TRY(cudaGetLastError());
-            h->matrix_free = true;
+            h->matrix_free = h->matrix_free_user = true;
         }
         // 32 < D: KR2(X) itself (rows x pairs) for the plain-GEMM metric build
         size_t bytes_n = (size_t)h->n_rows_pad * h->p2p * 8;
@@ -1438,7 +1446,7 @@ int rmhmc_set_partials_mode(rmhmc_handle* h, int mode) {
     if (mode == RMHMC_PARTIALS_MATRIX_FREE && !h->kr2t)
         return fail(h, RMHMC_E_UNSUPPORTED, "rmhmc_set_partials_mode: KR2(X)^T does not fit on this device");
     if (h->n_chains > 0) free_chains(h);
-    h->matrix_free = mode == RMHMC_PARTIALS_MATRIX_FREE;
+    h->matrix_free = h->matrix_free_user = mode == RMHMC_PARTIALS_MATRIX_FREE;
     return RMHMC_OK;
 }
 int rmhmc_get_partials_mode(const rmhmc_handle* h) {
@@ -1639,6 +1647,7 @@ static int chains_init_common(rmhmc_handle* h, int64_t C, const double* theta0, 
     if (!h || C <= 0) return h ? fail(h, RMHMC_E_INVALID, "chains_init: bad arguments") : RMHMC_E_INVALID;
     if (C > 0x7fffffff / 64) return fail(h, RMHMC_E_INVALID, "chains_init: too many chains");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    h->matrix_free = h->matrix_free_user;         // a previous mMALA chain set may have forced the matrix-free partials
     int rc = alloc_chains(h, C, hmc);
     if (rc) return rc;
     ChainArrays& S = h->S;
@@ -1794,8 +1803,8 @@ int mmala_chains_init(rmhmc_handle* h, int64_t C, const double* theta0, int simp
     if (h->dim > kMaxDimWarp) return fail(h, RMHMC_E_UNSUPPORTED, "mmala: dim > 32 is not supported");
     if (!simplified && !h->kr2t) return fail(h, RMHMC_E_UNSUPPORTED, "mmala: the full drift needs the matrix-free partials (KR2(X)^T resident)");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    const bool saved_mf = h->matrix_free;
-    if (!simplified) h->matrix_free = true;
+    const bool saved_mf = h->matrix_free_user;
+    h->matrix_free = simplified ? saved_mf : true;       // restored by the next rmhmc / hmc chains_init (matrix_free_user)
     int rc = alloc_chains(h, C, false);
     if (rc) { h->matrix_free = saved_mf; return rc; }
     h->is_mmala = true;
@@ -1906,6 +1915,7 @@ int rmhmc_read_state(rmhmc_handle* h, double* theta, int64_t* iters, int64_t* ac
 }
 
 int64_t rmhmc_launch_count(const rmhmc_handle* h) { return h ? h->launches : 0; }
+int64_t rmhmc_chain_generation(const rmhmc_handle* h) { return h ? h->chain_gen : -1; }
 
 int rmhmc_profile_enable(rmhmc_handle* h, int enable) {
     if (!h) return RMHMC_E_INVALID;
@@ -1925,19 +1935,32 @@ int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches)
 
 int blr_ess_batched(int device, void* cuda_stream, const double* samples, int64_t n_chains, int64_t n_samples,
                     int dim, int64_t chain_stride, int64_t row_stride, int64_t max_lag, double* ess) {
-    if (!samples || !ess || n_chains <= 0 || n_samples < 2 || dim <= 0 || max_lag < 1 || max_lag > n_samples - 1)
+    if (!samples || !ess || n_chains <= 0 || n_samples < 2 || dim <= 0 || max_lag < 1 || n_samples > 0x7fffffff / 2)
         return RMHMC_E_INVALID;
-    if (n_samples > 24000 || dim > 65535) return RMHMC_E_UNSUPPORTED;
+    if (dim > 65535) return RMHMC_E_UNSUPPORTED;
     if (cudaSetDevice(device) != cudaSuccess) return RMHMC_E_CUDA;
     int n_fft = 1;
     while (n_fft < n_samples) n_fft *= 2;           // tools.py:16-19
     n_fft += 1;                                     // tools.py:23
-    size_t smem = (size_t)n_samples * 8;
-    if (cudaFuncSetAttribute(k_ess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return RMHMC_E_CUDA;
+    if (max_lag > n_fft - 1) return RMHMC_E_INVALID;         // tools.py:26: the reference slices the nFFT-point circular ACF
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     dim3 grid((unsigned)n_chains, (unsigned)dim);
-    k_ess<<<grid, kEssThreads, smem, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
-        samples, (size_t)chain_stride, (size_t)row_stride, (int)n_samples, (int)max_lag, n_fft, ess, dim, nullptr, nullptr);
-    return cudaGetLastError() == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
+    if (n_samples <= 24000) {
+        size_t smem = (size_t)n_samples * 8;
+        if (cudaFuncSetAttribute(k_ess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return RMHMC_E_CUDA;
+        k_ess<<<grid, kEssThreads, smem, st>>>(samples, (size_t)chain_stride, (size_t)row_stride, (int)n_samples, (int)max_lag, n_fft,
+                                               ess, dim, nullptr, nullptr, nullptr);
+        return cudaGetLastError() == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
+    }
+    // longer series: the centred copy goes to a global scratch row per (chain, parameter)
+    double* scratch = nullptr;
+    if (cudaMalloc((void**)&scratch, (size_t)n_chains * dim * n_samples * 8) != cudaSuccess) return RMHMC_E_CUDA;
+    k_ess<<<grid, kEssThreads, 0, st>>>(samples, (size_t)chain_stride, (size_t)row_stride, (int)n_samples, (int)max_lag, n_fft, ess,
+                                        dim, nullptr, nullptr, scratch);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    return e == cudaSuccess ? RMHMC_OK : RMHMC_E_CUDA;
 }
 
 int blr_autocorr(int device, void* cuda_stream, const double* series, int64_t n_series, int64_t n_samples,

@@ -35,9 +35,11 @@ __global__ void __launch_bounds__(kEssThreads) k_ess(const double* __restrict__ 
                                                       size_t row_stride, int S, int max_lag, int n_fft,
                                                       double* __restrict__ ess_out, int D,
                                                       const long long* __restrict__ starts,
-                                                      const long long* __restrict__ counts) {
+                                                      const long long* __restrict__ counts,
+                                                      double* __restrict__ gscratch = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* y = reinterpret_cast<double*>(smem_raw);
+    // the centred series lives in shared memory (<= 24000 samples) or, for longer series, in a global scratch row
+    double* y = gscratch ? gscratch + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * (size_t)S : reinterpret_cast<double*>(smem_raw);
     __shared__ double scratch[4];
     const int c = blockIdx.x, d = blockIdx.y;
     const double* src = samples + (size_t)c * chain_stride + d;

@@ -270,9 +270,16 @@ class _SamplerBase:
         th0 = None if theta0 is None else data._dev(np.asarray(theta0, dtype=np.float64).reshape(self.n_chains, self.dim))
         if _init is not None:
             _capi.check(_init(th0), self.h, "chains_init")
-            return
-        fn = self._lib.hmc_chains_init if self._is_hmc else self._lib.rmhmc_chains_init
-        _capi.check(fn(self.h, self.n_chains, _ptr(th0)), self.h, "chains_init")
+        else:
+            fn = self._lib.hmc_chains_init if self._is_hmc else self._lib.rmhmc_chains_init
+            _capi.check(fn(self.h, self.n_chains, _ptr(th0)), self.h, "chains_init")
+        self._gen = self._lib.rmhmc_chain_generation(self.h)
+
+    def _check_alive(self):
+        """A handle owns one chain set: a later sampler / seam call on the same LogisticData replaced this one's chains."""
+        if self._lib.rmhmc_chain_generation(self.h) != self._gen:
+            raise _capi.RmhmcError("this sampler's chains were replaced by a later chains_init / seam call on the same "
+                                   "LogisticData handle (one chain set per handle)")
 
     # ---------------------------------------------------------------- randomness
     def set_philox(self, seed: int, chain_offset: int = 0):
@@ -315,6 +322,7 @@ class _SamplerBase:
         return out
 
     def state(self):
+        self._check_alive()
         t, dev, c = self.torch, self.data.device, self.n_chains
         theta = t.empty(c, self.dim, dtype=t.float64, device=dev)
         iters = t.empty(c, dtype=t.int64, device=dev)
@@ -334,6 +342,7 @@ class _SamplerBase:
 
     def advance(self, n_rounds: int, it_stop: int = HUGE_ITERS):
         """Enqueue ``n_rounds`` rounds without synchronising (free-running chains)."""
+        self._check_alive()
         _capi.check(getattr(self._lib, self._advance_fn)(self.h, int(n_rounds), int(it_stop)), self.h, self._advance_fn)
 
     def profile(self, enable: bool):
@@ -373,6 +382,7 @@ class RMHMCSampler(_SamplerBase):
 
     def run(self, it_stop: int) -> int:
         """Run rounds until every chain has completed ``it_stop`` iterations; returns the round count."""
+        self._check_alive()
         rounds = c_int64(0)
         _capi.check(self._lib.rmhmc_run(self.h, int(it_stop), ctypes.byref(rounds)), self.h, "rmhmc_run")
         return rounds.value
@@ -400,6 +410,7 @@ class HMCSampler(_SamplerBase):
         super().set_trace(n_iters, 1)
 
     def run(self, it_stop: int) -> int:
+        self._check_alive()
         rounds = c_int64(0)
         _capi.check(self._lib.hmc_run(self.h, int(it_stop), ctypes.byref(rounds)), self.h, "hmc_run")
         return rounds.value
@@ -441,6 +452,7 @@ class MMALASampler(_SamplerBase):
         super().set_trace(n_iters, 1)
 
     def run(self, it_stop: int) -> int:
+        self._check_alive()
         rounds = c_int64(0)
         _capi.check(self._lib.mmala_run(self.h, int(it_stop), ctypes.byref(rounds)), self.h, "mmala_run")
         return rounds.value

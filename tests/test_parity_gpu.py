@@ -806,3 +806,39 @@ def test_dropin_iwls_follows_global_numpy_rng(pkg, golden):
         np.random.multivariate_normal, np.random.uniform, np.random.get_state, np.random.set_state = real
     assert state["i"] == n_iter - 1 and w.shape == (n_iter - burn_in, fx["xx"].shape[1]) and secs > 0
     assert rel_err(w, fx["samples"][0]) < RTOL
+
+
+def test_one_chain_set_per_handle_is_enforced(pkg, golden):
+    """A second sampler (or a seam that needs chains) on the same LogisticData replaces the first one's chains: the
+    first sampler must fail loudly instead of silently reading the new chains; the partials mode survives an mMALA
+    chain set."""
+    fx = golden("rmhmc_pima_real")
+    data = pkg.LogisticData(fx["xx"], fx["t"], partials="tensor")
+    s1 = pkg.RMHMCSampler(data, 2, 6, 0.5, 4)
+    s1.set_philox(1)
+    s1.set_samples(4, 0)
+    s1.run(2)
+    s2 = pkg.MMALASampler(data, 3, 1.0)            # forces the matrix-free partials for ITS chain set
+    with pytest.raises(pkg.RmhmcError):
+        s1.run(3)
+    with pytest.raises(pkg.RmhmcError):
+        s1.state()
+    s3 = pkg.RMHMCSampler(data, 2, 6, 0.5, 4)
+    assert data.partials_mode == "tensor"           # restored for the next RMHMC chain set
+    with pytest.raises(pkg.RmhmcError):
+        s2.state()
+    s3.set_philox(1)
+    s3.set_samples(4, 0)
+    s3.run(2)
+    data.close()
+
+
+def test_ess_accepts_long_series_and_lags_up_to_nfft(pkg):
+    """tools.CalculateESS limits of the reference: MaxLag up to nFFT - 1 (tools.py:23-26) and series longer than the
+    shared-memory capacity of the ESS kernel (global-scratch path)."""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((700, 2)).cumsum(axis=0) * 0.05 + rng.standard_normal((700, 2))
+    assert rel_err(pkg.CalculateESS(x, 900), bo.ess(x, 900)) < 1e-9            # nFFT = 1025
+    long = rng.standard_normal((30000, 1))
+    long[1:, 0] += 0.6 * long[:-1, 0]
+    assert rel_err(pkg.CalculateESS(long, 29999), bo.ess(long, 29999)) < 1e-9
