@@ -150,6 +150,17 @@ int rmhmc_configure(rmhmc_handle* h, int n_leapfrog, double step_size, int n_fix
 int rmhmc_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const double* z,
                    const double* u_step, const double* z_dir, const double* u_acc);
 int rmhmc_set_philox(rmhmc_handle* h, uint64_t seed, int64_t chain_offset);
+/* Kinetic energy of the RMHMC engine.  GAUSSIAN: rmhmc.py (K = p' G^-1 p / 2).  STUDENT_T: the MATLAB original
+ * authors_code/Bayes_Log_Reg/MCMC/BLR_RMHMC_StudentT.m:205-414 -- K = (1+D)/2 log(1 + p' G^-1 p), momentum drawn as
+ * mvtrnd(G, 1)' = diag(G)^-1/2 L z / sqrt(chi2_1) (:265), LastTerm scaled by (1+D)/2 / (1 + p' G^-1 p) (:296,:370),
+ * position update weights (1+D) / (1 + p' G^-1 p) (:311-326), no renormalisation hacks, samples stored from iteration
+ * BurnIn on (:403-405).  Needs the MATRIX_FREE partials, dim <= 32, unsharded data; the implicit momentum iterates then run
+ * as one pass + one per-chain kernel each.  MATLAB only: parity is against a port (oracle/blr_oracle.py), unpinned.
+ * Under a host tape the chi-square draw is z_chi^2 with z_chi (n_window x n_chains) set by rmhmc_set_tape_chi after
+ * rmhmc_set_tape. */
+enum { RMHMC_MOMENTUM_GAUSSIAN = 0, RMHMC_MOMENTUM_STUDENT_T = 1 };
+int rmhmc_set_momentum_family(rmhmc_handle* h, int family);
+int rmhmc_set_tape_chi(rmhmc_handle* h, const double* z_chi);
 
 /* Sample store (rmhmc.py:190-191): samples (n_chains x capacity x dim); the state after
  * iteration `it` goes to row it - burn_in for it > burn_in (row 0 is never written, as in the

@@ -523,6 +523,93 @@ def mmala_chain(xx, t, tape: DrawTape, n_iter=10000, burn_in=5000, step_size=1.0
     return samples, info
 
 
+# --------------------------------------------------------------------------- Student-t RMHMC (MATLAB original only)
+def studentt_rmhmc_chain(xx, t, tape: DrawTape, z_chi, n_iter=6000, burn_in=1000, n_leapfrog=6, step_size=0.5, n_fixed=4,
+                         alpha=ALPHA, record=False):
+    """RMHMC with a multivariate Student-t (one degree of freedom) kinetic energy; restates the MATLAB original
+    ``code/authors_code/Bayes_Log_Reg/MCMC/BLR_RMHMC_StudentT.m:205-414`` (cited as T:line).
+
+    PARITY UNPINNED: MATLAB only, no Python original in the reference and no MATLAB / Octave here.  Differences from
+    ``BLR_RMHMC.m`` / ``rmhmc.py``: the momentum draw ``mvtrnd(G, 1)'`` (T:265), the LastTerm scaling
+    ``(1+D)/2 (.) / (1 + p' G^-1 p)`` (T:296, :370), the position update weights (T:311-326) and the kinetic term
+    ``(1+D)/2 log(1 + p' G^-1 p)`` (T:386, :392); no renormalisation hacks (those are rmhmc.py's).
+    Conventions of this port: 0-based iterations (MATLAB IterationNum = it + 1), sample of iteration ``it`` in row
+    ``it - burn_in`` for ``it >= burn_in`` (T:403-405).  ``mvtrnd(C, 1)`` rescales C to a correlation matrix, draws
+    ``randn(1, D) * chol(corr)`` and divides by ``sqrt(chi2rnd(1))``: the tape supplies ``z[it]`` for the normals and
+    ``z_chi[it]`` with ``chi2 = z_chi^2``.  Direction ``randn > 0.5`` (T:272) from ``z_dir``, ``RandomSteps =
+    ceil(rand * L)`` (T:274) from ``u_step``, the Metropolis uniform (T:398) from ``u_acc`` (consumed only if Ratio <= 0).
+    """
+    n, d = xx.shape
+    nu = 1.0 + d
+    w = np.ones((d, 1)) * 1e-3                                                   # T:207
+    samples = np.zeros((n_iter - burn_in, d))
+    cur_ljl = log_joint(xx, t, w, alpha)                                         # T:217-220
+    accepted = np.zeros(n_iter, dtype=bool)
+    steps_taken = np.zeros(n_iter, dtype=np.int64)
+    records = []
+    for it in range(n_iter):
+        w_new = w.copy()
+        _, p, v, g = fisher_metric(xx, w_new, alpha)                             # T:236-240
+        inv_g = np.linalg.inv(g)
+        orig_chol, orig_inv_g = np.linalg.cholesky(g), inv_g.copy()
+        inv_g_dg, tr = metric_partials(xx, p, v, inv_g)                          # T:248-262
+        sd = np.sqrt(np.diag(g))
+        corr_l = np.linalg.cholesky(g / np.outer(sd, sd))                        # mvtrnd: chol of the correlation matrix
+        mom = (corr_l.dot(tape.z[it].reshape(d, 1))) / np.sqrt(z_chi[it] ** 2)   # T:265: (z chol(corr))' / sqrt(chi2 / 1)
+        mom0 = mom.copy()
+        sgn = 1 if tape.z_dir[it] > 0.5 else -1                                  # T:272
+        n_steps = int(np.ceil(tape.u_step[it] * n_leapfrog))                     # T:274
+        steps_taken[it] = n_steps
+        rec = {"theta_steps": [], "mom0": mom0[:, 0].copy(), "n_steps": n_steps, "direction": sgn}
+        for _ in range(n_steps):
+            grad = likelihood_gradient(xx, t, w_new, alpha)                      # T:285
+            pm = mom.copy()
+            for _f in range(n_fixed):                                            # T:289-300
+                u = inv_g.dot(pm)
+                den = 1.0 + _scalar(pm.T.dot(u))
+                last = np.array([[(nu / 2) * _scalar(pm.T.dot(inv_g_dg[k]).dot(u)) / den] for k in range(d)])
+                pm = mom + sgn * (step_size / 2) * (grad - 0.5 * tr + last)
+            mom = pm
+            u0 = np.linalg.solve(g, mom)                                         # T:309-310
+            den0 = 1.0 + _scalar(mom.T.dot(u0))
+            pw = w_new.copy()
+            for _f in range(n_fixed):                                            # T:313-327
+                _, p, v, g = fisher_metric(xx, pw, alpha)
+                u = np.linalg.solve(g, mom)
+                pw = w_new + (sgn * (step_size / 2) * nu) * u0 / den0 + (sgn * (step_size / 2) * nu) * u / (1.0 + _scalar(mom.T.dot(u)))
+            w_new = pw
+            _, p, v, g = fisher_metric(xx, w_new, alpha)                         # T:331-340
+            inv_g = np.linalg.inv(g)
+            inv_g_dg, tr = metric_partials(xx, p, v, inv_g)                      # T:345-356
+            grad = likelihood_gradient(xx, t, w_new, alpha)                      # T:363-364
+            u = inv_g.dot(mom)                                                   # T:368-373
+            den = 1.0 + _scalar(mom.T.dot(u))
+            last = np.array([[(nu / 2) * _scalar(mom.T.dot(inv_g_dg[k]).dot(u)) / den] for k in range(d)])
+            mom = mom + sgn * (step_size / 2) * (grad - 0.5 * tr + last)
+            rec["theta_steps"].append(w_new[:, 0].copy())
+        prop_ljl = log_joint(xx, t, w_new, alpha)                                # T:379-383
+        prop_logdet = np.sum(np.log(np.diag(np.linalg.cholesky(g))))             # T:385
+        prop_h = -prop_ljl + prop_logdet + (nu / 2) * np.log(1.0 + _scalar(mom.T.dot(inv_g).dot(mom)))   # T:386
+        cur_logdet = np.sum(np.log(np.diag(orig_chol)))                          # T:390
+        cur_h = -cur_ljl + cur_logdet + (nu / 2) * np.log(1.0 + _scalar(mom0.T.dot(orig_inv_g).dot(mom0)))  # T:392
+        ratio = _scalar(-prop_h + cur_h)                                         # T:395
+        used_uniform = False
+        take = bool(ratio > 0)
+        if not take:
+            used_uniform = True
+            take = bool(ratio > np.log(tape.u_acc[it]))                          # T:398
+        if take:
+            cur_ljl, w = prop_ljl, w_new
+            accepted[it] = True
+        if record:
+            rec.update({"mom_end": mom[:, 0].copy(), "theta_end": w_new[:, 0].copy(), "h_current": _scalar(cur_h),
+                        "h_proposed": _scalar(prop_h), "ratio": ratio, "accepted": take, "used_uniform": used_uniform})
+            records.append(rec)
+        if it >= burn_in:
+            samples[it - burn_in, :] = w.T                                       # T:403-405
+    return samples, {"w": w[:, 0].copy(), "accepted": accepted, "steps": steps_taken, "records": records}
+
+
 # --------------------------------------------------------------------------- IWLS (code/iwls.py)
 def iwls_chain(xx, t, tape: DrawTape, n_iter=10000, burn_in=5000, alpha=ALPHA, record=False, w0=None):
     """One iterated-weighted-least-squares Metropolis chain under a draw tape; restates ``code/iwls.py:13-89``.

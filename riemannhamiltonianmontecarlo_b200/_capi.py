@@ -42,6 +42,8 @@ SIGNATURES = {
     "rmhmc_configure": (c_int, [c_void_p, c_int, c_double, c_int]),
     "rmhmc_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rmhmc_set_philox": (c_int, [c_void_p, c_uint64, c_int64]),
+    "rmhmc_set_momentum_family": (c_int, [c_void_p, c_int]),
+    "rmhmc_set_tape_chi": (c_int, [c_void_p, c_void_p]),
     "rmhmc_set_samples": (c_int, [c_void_p, c_void_p, c_int64, c_int64]),
     "rmhmc_set_trace": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rmhmc_advance": (c_int, [c_void_p, c_int64, c_int64]),

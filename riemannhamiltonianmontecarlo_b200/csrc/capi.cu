@@ -653,6 +653,7 @@ int alloc_chains(rmhmc_handle* h, int64_t C, bool hmc) {
     rc |= dev_alloc(h, &S.mom, c * D, tr);
     rc |= dev_alloc(h, &S.theta_w, c * D, tr);
     rc |= dev_alloc(h, &S.hcur, c, tr);
+    rc |= dev_alloc(h, &S.pudot, c, tr);
     rc |= dev_alloc(h, &S.cur, c, tr);
     rc |= dev_alloc(h, &S.step, c, tr);
     rc |= dev_alloc(h, &S.nsteps, c, tr);
@@ -860,7 +861,7 @@ int mf_momentum_fixed_point(rmhmc_handle* h) {
     // all F iterates in one launch (needs no exchange between iterates).  Two formulations: one warp per 8 chains
     // (pass_kernel.cuh; 2.58 vs 3.02 ms at 65 536 German-shaped chains) or 12 cooperating warps per 32 chains
     // (momfp_kernel.cuh; shorter dependent chains, 0.08 vs 0.23 ms when 4096 chains leave most of the GPU idle)
-    const bool fusable = !is_big(h) && !h->comm && h->P.n_fixed >= 2;
+    const bool fusable = !is_big(h) && !h->comm && h->P.n_fixed >= 2 && !h->P.student_t;      // Student-t: per-iterate kernels
     const bool few = few_chains(h, (int64_t)148 * 2 * kPassWarps * 8);
     if (fusable && (h->fuse_momentum == 1 && !few)) return launch_pass<kPassMomFp>(h);
     if (fusable && (h->fuse_momentum == 2 || (h->fuse_momentum == 1 && few))) {
@@ -1198,6 +1199,8 @@ int run_until(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done, bool hmc, 
     if (h->n_chains <= 0 || h->is_hmc != hmc || h->is_mmala != mmala)
         return fail(h, RMHMC_E_STATE, "chains not initialised for this sampler");
     if (!h->configured || !h->rng_set) return fail(h, RMHMC_E_STATE, "configure and set a tape / philox seed first");
+    if (h->P.rng_mode == 0 && h->P.student_t && !hmc && !mmala && !h->P.tape_z_chi)
+        return fail(h, RMHMC_E_STATE, "Student-t momentum under a host tape needs rmhmc_set_tape_chi");
     if (h->P.rng_mode == 0) {
         // a host tape covers iterations [tape_base, tape_base + tape_window): never index outside it
         if (it_stop > h->tape_base + h->tape_window)
@@ -1446,6 +1449,7 @@ int rmhmc_set_partials_mode(rmhmc_handle* h, int mode) {
     if (mode == RMHMC_PARTIALS_MATRIX_FREE && !h->kr2t)
         return fail(h, RMHMC_E_UNSUPPORTED, "rmhmc_set_partials_mode: KR2(X)^T does not fit on this device");
     if (h->n_chains > 0) free_chains(h);
+    if (mode != RMHMC_PARTIALS_MATRIX_FREE) h->P.student_t = 0;       // the Student-t variant exists in the matrix-free kernels only
     h->matrix_free = h->matrix_free_user = mode == RMHMC_PARTIALS_MATRIX_FREE;
     return RMHMC_OK;
 }
@@ -1722,6 +1726,19 @@ int hmc_set_tape(rmhmc_handle* h, int64_t it_base, int64_t n_window, const doubl
     h->P.tape_z_dir = nullptr; h->P.tape_u_acc = u_acc;
     h->tape_base = it_base; h->tape_window = n_window;
     h->rng_set = true;
+    return RMHMC_OK;
+}
+int rmhmc_set_momentum_family(rmhmc_handle* h, int family) {
+    if (!h || (family != RMHMC_MOMENTUM_GAUSSIAN && family != RMHMC_MOMENTUM_STUDENT_T))
+        return h ? fail(h, RMHMC_E_INVALID, "rmhmc_set_momentum_family: bad arguments") : RMHMC_E_INVALID;
+    if (family == RMHMC_MOMENTUM_STUDENT_T && (!h->matrix_free || is_big(h) || h->comm))
+        return fail(h, RMHMC_E_UNSUPPORTED, "rmhmc_set_momentum_family: Student-t needs the matrix-free partials, dim <= 32 and unsharded data");
+    h->P.student_t = family == RMHMC_MOMENTUM_STUDENT_T ? 1 : 0;
+    return RMHMC_OK;
+}
+int rmhmc_set_tape_chi(rmhmc_handle* h, const double* z_chi) {
+    if (!h || !z_chi) return h ? fail(h, RMHMC_E_INVALID, "rmhmc_set_tape_chi: bad arguments") : RMHMC_E_INVALID;
+    h->P.tape_z_chi = z_chi;
     return RMHMC_OK;
 }
 int rmhmc_set_philox(rmhmc_handle* h, uint64_t seed, int64_t chain_offset) {

@@ -31,6 +31,10 @@ struct EngineParams {
     const double* tape_u_step;         // [W][C]
     const double* tape_z_dir;          // [W][C]
     const double* tape_u_acc;          // [W][C]
+    // Student-t kinetic energy (BLR_RMHMC_StudentT.m; matrix-free partials, D <= 32): K = (1+D)/2 log(1 + p' G^-1 p),
+    // momentum p = D^-1/2 L z / |z_chi| (mvtrnd(G, 1): correlation-scaled normals over sqrt(chi2_1))
+    int student_t;
+    const double* tape_z_chi;          // [W][C] normal whose square is the chi-square draw
     long long tape_base;               // iteration index of tape row 0
     unsigned long long seed;
     long long chain_offset;            // global id of local chain 0 (multi-GPU sharding)
@@ -892,8 +896,9 @@ __global__ void __launch_bounds__(32, 16) k_chain_solve(EngineParams P, ChainArr
     chol_fixed<N>(lrow, colbuf, lane, dinv);
     store_rows_fixed<N>(Lsm, lrow, lane);
     double u = chol_solve_fixed<N>(lrow, Lsm, dinv, lane, p);                        // rmhmc.py:121
+    if (P.student_t) u = (1.0 + D) * u / (1.0 + warp_sum(live ? p * u : 0.0));       // BLR_RMHMC_StudentT.m:326 (u0 is stored scaled)
     double pw = w + (S.dir[c] * P.step_size / 2) * (u0 + u);                        // rmhmc.py:122
-    if (is_last) pw = clamp_position(pw, lane, D, &S.renorm_pos[c]);
+    if (is_last && !P.student_t) pw = clamp_position(pw, lane, D, &S.renorm_pos[c]);
     if (live) S.theta_w[(size_t)c * D + lane] = pw;
 }
 

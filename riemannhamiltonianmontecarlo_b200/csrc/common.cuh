@@ -127,6 +127,7 @@ struct ChainArrays {
     double* theta_w;   // [C][D]   working position (fixed-point iterate; input of the metric builds)
     double* u0;        // [C][D]   G(theta)^-1 p of the current leapfrog step (rmhmc.py:113)
     double* hcur;      // [C]      Hamiltonian at the start of the iteration
+    double* pudot;     // [C]      PM . G^-1 PM of the momentum iterate whose u = G^-1 PM is in uvec (Student-t kinetic energy only)
     double* g_tmp;     // [C][P2p] metric at theta_w (output of a metric build)
     double* grad_tmp;  // [C][D]   X^T (t - p) at theta_w (closing build only)
     double* loglik_tmp;// [C]      log-likelihood at theta_w (closing build only)

@@ -115,8 +115,12 @@ __global__ void __launch_bounds__(NTHR) k_mf_turn(EngineParams P, ChainArrays S,
             if (init) return;
 
             // ---- R14: explicit closing momentum half-step (quad_tmp = u^T dG_d u, u = G_new^-1 p)
+            // LastTerm scaling: 1/2 (rmhmc.py:159-161), Student-t: (1+D)/2 / (1 + p' G^-1 p) with u = G_new^-1 p from the
+            // factor kernel (BLR_RMHMC_StudentT.m:368-373)
+            double qscale = 0.5;
+            if (P.student_t) qscale = 0.5 * (1.0 + D) / (1.0 + mf_sum<NTHR>(live ? p * S.uvec[cd] : 0.0, red, D, tid));
             if (live) {
-                p = p + (sgn * P.step_size / 2) * (grad - 0.5 * tr + 0.5 * S.quad_tmp[cd]);      // rmhmc.py:163
+                p = p + (sgn * P.step_size / 2) * (grad - 0.5 * tr + qscale * S.quad_tmp[cd]);   // rmhmc.py:163
                 S.mom[cd] = p;
                 if (P.tr_theta_steps && it < P.tr_iters)
                     P.tr_theta_steps[(((size_t)c * P.tr_iters + it) * P.n_leapfrog + step) * D + tid] = th;
@@ -129,7 +133,8 @@ __global__ void __launch_bounds__(NTHR) k_mf_turn(EngineParams P, ChainArrays S,
             } else {
                 // ---- R15: proposed Hamiltonian
                 const double u = mf_matvec<NTHR>(S.invg + out * P.slot_invg + (size_t)c * D * D, p, xs, D, tid);
-                hprop = -ljl + logdet + 0.5 * mf_sum<NTHR>(live ? p * u : 0.0, red, D, tid);     // rmhmc.py:172
+                const double pgp = mf_sum<NTHR>(live ? p * u : 0.0, red, D, tid);
+                hprop = -ljl + logdet + (P.student_t ? 0.5 * (1.0 + D) * log(1.0 + pgp) : 0.5 * pgp);   // rmhmc.py:172 / T:386
             }
         } else {
             // empty trajectory (RandomStep = 0): the proposal is the current state
@@ -160,7 +165,8 @@ __global__ void __launch_bounds__(NTHR) k_mf_turn(EngineParams P, ChainArrays S,
                 }
             }
             // ---- R18: store (row it - burn_in, only for it > burn_in)
-            if (P.samples && it > P.burn_in && it - P.burn_in < P.sample_cap && live)
+            // (the MATLAB loop of the Student-t variant stores iteration BurnIn as well: BLR_RMHMC_StudentT.m:403-405)
+            if (P.samples && (it > P.burn_in || (P.student_t && it == P.burn_in)) && it - P.burn_in < P.sample_cap && live)
                 P.samples[((size_t)c * P.sample_cap + (it - P.burn_in)) * D + tid] = S.theta[fin * P.slot_theta + cd];
             mf_sync<NTHR>();       // everyone has read the pre-update state
             if (tid == 0) {
@@ -189,36 +195,48 @@ __global__ void __launch_bounds__(NTHR) k_mf_turn(EngineParams P, ChainArrays S,
             nsteps = P.ext_nsteps[c];
             sgn = P.ext_dir[c];
         } else {
-            double z = 0.0, u_step, z_dir;
+            double z = 0.0, u_step, z_dir, z_chi = 1.0;
             if (P.rng_mode == 0) {
                 size_t row = (size_t)(it - P.tape_base) * P.n_chains + c;
                 if (live) z = P.tape_z[row * D + tid];
                 u_step = P.tape_u_step[row];
                 z_dir = P.tape_z_dir[row];
+                if (P.student_t) z_chi = P.tape_z_chi[row];
             } else {
                 if (live) z = philox_normal(P, c, it, (uint32_t)tid);
                 u_step = philox_pair(P, c, it, 0x100u).u0;
                 z_dir = philox_normal(P, c, it, 0x101u);
+                if (P.student_t) z_chi = philox_normal(P, c, it, 0x103u);
             }
             mf_sync<NTHR>();
             xs[tid] = live ? z : 0.0;
             mf_sync<NTHR>();
-            if (live) {
-                const double* lf = S.lfac + in_slot * P.slot_invg + (size_t)c * D * D;
-                for (int i = tid; i < D; ++i) p = fma(lf[(size_t)i * D + tid], xs[i], p);        // (z L)^T = L^T z, rmhmc.py:80
-            }
-            const double nrm = sqrt(mf_sum<NTHR>(live ? p * p : 0.0, red, D, tid));
-            if (nrm > 100.0) {                                                                    // rmhmc.py:81-85
-                p /= nrm * 25.0;
-                if (tid == 0) ++S.renorm_mom[c];
+            const double* lf = S.lfac + in_slot * P.slot_invg + (size_t)c * D * D;
+            if (P.student_t) {
+                // mvtrnd(G, 1)' (BLR_RMHMC_StudentT.m:265): normals through the Cholesky factor of the CORRELATION matrix of G,
+                // chol(corr) = diag(G)^-1/2 L, divided by sqrt(chi2_1 / 1); no renormalisation hack (that is rmhmc.py's)
+                double lz = 0.0, gii = 0.0;
+                if (live)
+                    for (int k = 0; k <= tid; ++k) { const double l = lf[(size_t)tid * D + k]; lz = fma(l, xs[k], lz); gii = fma(l, l, gii); }
+                if (live) p = lz / sqrt(gii) / fabs(z_chi);
+            } else {
+                if (live)
+                    for (int i = tid; i < D; ++i) p = fma(lf[(size_t)i * D + tid], xs[i], p);    // (z L)^T = L^T z, rmhmc.py:80
+                const double nrm = sqrt(mf_sum<NTHR>(live ? p * p : 0.0, red, D, tid));
+                if (nrm > 100.0) {                                                                // rmhmc.py:81-85
+                    p /= nrm * 25.0;
+                    if (tid == 0) ++S.renorm_mom[c];
+                }
             }
             nsteps = (int)ceil(u_step * (double)P.n_leapfrog);                                    // rmhmc.py:89
             sgn = z_dir > 0.5 ? 1 : -1;                                                           // rmhmc.py:90-93
         }
         const double u = mf_matvec<NTHR>(invg, p, xs, D, tid);
+        const double pgp = mf_sum<NTHR>(live ? p * u : 0.0, red, D, tid);
         const double hcur = -S.logjoint[in_slot * P.slot_scalar + c] + S.logdet[in_slot * P.slot_scalar + c] +
-                            0.5 * mf_sum<NTHR>(live ? p * u : 0.0, red, D, tid);                  // rmhmc.py:175-176
+                            (P.student_t ? 0.5 * (1.0 + D) * log(1.0 + pgp) : 0.5 * pgp);         // rmhmc.py:175-176 / T:392
         if (tid == 0) {
+            if (P.student_t) S.pudot[c] = pgp;
             S.hcur[c] = hcur;
             S.nsteps[c] = nsteps;
             S.dir[c] = sgn;
@@ -235,6 +253,10 @@ __global__ void __launch_bounds__(NTHR) k_mf_turn(EngineParams P, ChainArrays S,
     } else {
         if (live) p = S.mom[cd];
         u_first = mf_matvec<NTHR>(invg, p, xs, D, tid);
+        if (P.student_t) {
+            const double pgp = mf_sum<NTHR>(live ? p * u_first : 0.0, red, D, tid);
+            if (tid == 0) S.pudot[c] = pgp;
+        }
         if (tid == 0) S.aslot[c] = in_slot;
         if (live) S.uvec[cd] = u_first;
     }
@@ -242,7 +264,7 @@ __global__ void __launch_bounds__(NTHR) k_mf_turn(EngineParams P, ChainArrays S,
         const double th = live ? S.theta[in_slot * P.slot_theta + cd] : 0.0;
         const double nrm = sqrt(mf_sum<NTHR>(th * th, red, D, tid));                              // rmhmc.py:125-130
         double div = 1.0;
-        if (nrm > 10.0) {
+        if (nrm > 10.0 && !P.student_t) {
             div = nrm * 3.0;
             if (tid == 0) ++S.renorm_pos[c];
         }
@@ -269,19 +291,25 @@ __global__ void __launch_bounds__(NTHR) k_mf_mom_iter(EngineParams P, ChainArray
     const int in_slot = S.step[c] == 0 ? cur : 1 - cur;
     const double h = S.dir[c] * P.step_size / 2;
     double pm = 0.0, th = 0.0;
+    // LastTerm scaling: 1/2, Student-t: (1+D)/2 / (1 + PM' G^-1 PM) of the iterate the quad pass used (T:293-297)
+    const double qscale = P.student_t ? 0.5 * (1.0 + D) / (1.0 + S.pudot[c]) : 0.5;
     if (live) {
         const size_t so = in_slot * P.slot_theta + cd;
-        pm = S.mom[cd] + h * (S.grad[so] - 0.5 * S.trace[so] + 0.5 * S.quad_tmp[cd]);             // rmhmc.py:108
+        pm = S.mom[cd] + h * (S.grad[so] - 0.5 * S.trace[so] + qscale * S.quad_tmp[cd]);          // rmhmc.py:108
         if (is_last) th = S.theta[so];
     }
-    const double u = mf_matvec<NTHR>(S.invg + in_slot * P.slot_invg + (size_t)c * D * D, pm, xs, D, tid);
+    double u = mf_matvec<NTHR>(S.invg + in_slot * P.slot_invg + (size_t)c * D * D, pm, xs, D, tid);
+    double pgp = 0.0;
+    if (P.student_t) pgp = mf_sum<NTHR>(live ? pm * u : 0.0, red, D, tid);
     if (!is_last) {
         if (live) S.uvec[cd] = u;
+        if (P.student_t && tid == 0) S.pudot[c] = pgp;
         return;
     }
+    if (P.student_t) u = (1.0 + D) * u / (1.0 + pgp);          // T:309-326: both terms of the position update carry this weight
     double y = th + h * (u + u);
     double div = 1.0;
-    if (P.n_fixed <= 1) {                       // this iterate is already the step's final position
+    if (P.n_fixed <= 1 && !P.student_t) {       // this iterate is already the step's final position
         const double nrm = sqrt(mf_sum<NTHR>(live ? y * y : 0.0, red, D, tid));                   // rmhmc.py:125-130
         if (nrm > 10.0) {
             div = nrm * 3.0;

@@ -362,13 +362,15 @@ class RMHMCSampler(_SamplerBase):
     """C independent RMHMC chains; every ``round`` advances each chain by one generalized leapfrog step."""
 
     def __init__(self, data: LogisticData, n_chains: int, n_leapfrog: int = 6, step_size: float = 0.5,
-                 n_fixed: int = 4, theta0=None):
+                 n_fixed: int = 4, theta0=None, student_t: bool = False):
         super().__init__(data, n_chains, theta0)
         self.n_leapfrog, self.step_size, self.n_fixed = int(n_leapfrog), float(step_size), int(n_fixed)
         _capi.check(self._lib.rmhmc_configure(self.h, self.n_leapfrog, self.step_size, self.n_fixed), self.h, "configure")
+        self.student_t = bool(student_t)      # BLR_RMHMC_StudentT.m: Student-t kinetic energy (include/rmhmc_b200.h)
+        _capi.check(self._lib.rmhmc_set_momentum_family(self.h, 1 if student_t else 0), self.h, "rmhmc_set_momentum_family")
 
-    def set_tape(self, z, u_step, z_dir, u_acc, it_base: int = 0):
-        """Host draws in the C-ABI layout: z (W,C,D), u_step/z_dir/u_acc (W,C)."""
+    def set_tape(self, z, u_step, z_dir, u_acc, it_base: int = 0, z_chi=None):
+        """Host draws in the C-ABI layout: z (W,C,D), u_step/z_dir/u_acc (W,C); Student-t: z_chi (W,C)."""
         d = self.data
         self._keep["tape"] = [d._dev(z), d._dev(u_step), d._dev(z_dir), d._dev(u_acc)]
         w = self._keep["tape"][0].shape[0]
@@ -376,6 +378,10 @@ class RMHMCSampler(_SamplerBase):
         assert zt.shape == (w, self.n_chains, self.dim) and us.shape == (w, self.n_chains)
         _capi.check(self._lib.rmhmc_set_tape(self.h, int(it_base), int(w), _ptr(zt), _ptr(us), _ptr(zd), _ptr(ua)),
                     self.h, "set_tape")
+        if z_chi is not None:
+            self._keep["tape_chi"] = d._dev(z_chi)
+            assert self._keep["tape_chi"].shape == (w, self.n_chains)
+            _capi.check(self._lib.rmhmc_set_tape_chi(self.h, _ptr(self._keep["tape_chi"])), self.h, "set_tape_chi")
 
     def set_trace(self, n_iters: int):          # noqa: D102
         super().set_trace(n_iters, self.n_leapfrog)

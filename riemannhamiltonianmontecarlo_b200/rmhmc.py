@@ -110,7 +110,7 @@ def _set_trace_base(sampler, it_base):
 
 def rmhmc_batched(XX, t, n_chains, NumOfIterations=6000, BurnIn=1000, NumOfLeapFrogSteps=6, StepSize=0.5,
                   NumOfNewtonSteps=4, *, seed=0, chain_offset=0, device="cuda:0", draws=None, return_device=False,
-                  partials=None, metric=None, regime=None):
+                  partials=None, metric=None, regime=None, student_t=False):
     """``n_chains`` independent RMHMC chains -> ``(samples (C, n-b, D), seconds, info)``.
 
     ``draws`` = dict(z, u_step, z_dir, u_acc) in the (W, C, ...) layout replays a host tape
@@ -118,16 +118,18 @@ def rmhmc_batched(XX, t, n_chains, NumOfIterations=6000, BurnIn=1000, NumOfLeapF
     Row 0 of every chain's samples is never written (zeros), as in the reference.
     ``partials``: ``"tensor"`` / ``"matrix_free"`` (see ``LogisticData.set_partials_mode``); None = library default.
     ``metric``: ``"dmma"`` / ``"i8"`` (``LogisticData.set_metric_mode``); ``regime``: kernel-variant pin (tests).
+    ``student_t=True``: the Student-t kinetic energy of the MATLAB original ``BLR_RMHMC_StudentT.m`` (``draws`` then also
+    needs ``z_chi`` (W, C); samples are stored from iteration ``BurnIn`` on, as in that script).
     """
     data = LogisticData(XX, t, alpha=ALPHA, device=device, partials=partials, metric=metric, regime=regime)
-    sampler = RMHMCSampler(data, n_chains, NumOfLeapFrogSteps, StepSize, NumOfNewtonSteps)
+    sampler = RMHMCSampler(data, n_chains, NumOfLeapFrogSteps, StepSize, NumOfNewtonSteps, student_t=student_t)
     if draws is not None:
-        sampler.set_tape(draws["z"], draws["u_step"], draws["z_dir"], draws["u_acc"])
+        sampler.set_tape(draws["z"], draws["u_step"], draws["z_dir"], draws["u_acc"], z_chi=draws.get("z_chi"))
     else:
         sampler.set_philox(seed, chain_offset)
     sampler.set_samples(NumOfIterations - BurnIn, BurnIn)
     torch = data.torch
-    sampler.run(min(BurnIn + 1, NumOfIterations))
+    sampler.run(min(BurnIn + (0 if student_t else 1), NumOfIterations))
     torch.cuda.synchronize(data.device)
     start = timeit.default_timer()
     rounds = sampler.run(NumOfIterations)

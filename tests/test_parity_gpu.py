@@ -842,3 +842,40 @@ def test_ess_accepts_long_series_and_lags_up_to_nfft(pkg):
     long = rng.standard_normal((30000, 1))
     long[1:, 0] += 0.6 * long[:-1, 0]
     assert rel_err(pkg.CalculateESS(long, 29999), bo.ess(long, 29999)) < 1e-9
+
+
+# ---- Student-t RMHMC (MATLAB only: the oracle is a port, parity unpinned)
+@pytest.mark.parametrize("metric", METRIC)
+@pytest.mark.parametrize("shape", ["australian", "german"])
+def test_studentt_rmhmc_matches_oracle_port_under_a_tape(pkg, shape, metric):
+    xx, t = pkg.datasets.shaped(shape)
+    d = xx.shape[1]
+    n_iter, burn, c = 8, 2, 4
+    tapes = [bo.make_tape(n_iter, d, 9900 + i) for i in range(c)]
+    z_chi = np.random.default_rng(123).standard_normal((n_iter, c))
+    refs = [bo.studentt_rmhmc_chain(xx, t, tapes[i], z_chi[:, i], n_iter=n_iter, burn_in=burn, n_leapfrog=6, step_size=0.5,
+                                    n_fixed=6, record=True) for i in range(c)]
+    st = bo.stack_tapes(tapes)
+    st["z_chi"] = z_chi
+    data = pkg.LogisticData(xx, t, metric=metric)
+    s = pkg.RMHMCSampler(data, c, 6, 0.5, 6, student_t=True)
+    s.set_tape(st["z"], st["u_step"], st["z_dir"], st["u_acc"], z_chi=z_chi)
+    s.set_samples(n_iter - burn, burn)
+    s.set_trace(n_iter)
+    s.run(n_iter)
+    tr, out, state = s.trace_numpy(), s.samples.cpu().numpy(), s.state()
+    data.close()
+    for ci in range(c):
+        rec = refs[ci][1]["records"]
+        assert np.array_equal(tr["accepted"][ci], [r["accepted"] for r in rec])
+        assert np.array_equal(tr["used_uniform"][ci], [r["used_uniform"] for r in rec])
+        assert np.array_equal(tr["n_steps"][ci], [r["n_steps"] for r in rec])
+        for it in range(n_iter):
+            assert rel_err(tr["mom0"][ci, it], rec[it]["mom0"]) < RTOL
+            for k in range(rec[it]["n_steps"]):
+                assert rel_err(tr["theta_steps"][ci, it, k], rec[it]["theta_steps"][k]) < 1e-8
+            assert rel_err(tr["mom_end"][ci, it], rec[it]["mom_end"]) < 1e-8
+            assert abs(tr["h_current"][ci, it] - rec[it]["h_current"]) < 1e-8 * abs(rec[it]["h_current"])
+            assert abs(tr["h_proposed"][ci, it] - rec[it]["h_proposed"]) < 1e-8 * abs(rec[it]["h_proposed"])
+        assert rel_err(out[ci], refs[ci][0]) < 1e-8
+    assert np.array_equal(state["renorm_momentum"], np.zeros(c)) and np.array_equal(state["renorm_position"], np.zeros(c))
