@@ -421,6 +421,9 @@ def gpu_main(args):
     }
     if args.sampler == "hmc":
         work["metric_closing"] = (4.0 * C * N * D, "fp64")          # k_metric<MODE 2>: f = X theta and X^T (t - p)
+        if os.environ.get("RMHMC_HMC_FUSED", "1") != "0" and D <= 32:
+            # k_hmc_rounds: the same two contractions for every round of the launch (64 rounds per launch)
+            work["chain_turn"] = (4.0 * C * N * D * R / ((R + 63) // 64), "fp64")
     if metric_mode == "i8" and args.sampler != "hmc":        # kinds 0 / 1 are the sums of the two i8 kernels there
         work.pop("metric_fp"); work.pop("metric_closing")
         if args.partials == "matrix_free" and os.environ.get("RMHMC_I8_LEVERAGE", "1") != "0":
@@ -434,6 +437,7 @@ def gpu_main(args):
         "trace_pass": "k_pass<PAIR|TRACE> (tr(G^-1 dG_d) and u^T dG_d u passes, FP64 DMMA.8x8x4)",
         "i8_gemm": "k_i8_gemm (G = V . KR2(X) as 15 exact INT8 digit GEMMs: tcgen05.mma.kind::i8, TMEM, tensor-map TMA)",
         "i8_vslice": "k_i8_vslice_mma / k_i8_vslice (f = X theta, logistic terms, base-256 digits of v; FP64)",
+        "chain_turn": "k_hmc_rounds (64 leapfrog rounds per launch: f = X w, X^T (t - sigma(f)) on FP64 DMMA.8x8x4, chain state in registers)",
     }
     peaks = {"fp64": (dmma_peak, "TFLOP/s", "DMMA.8x8x4 issue peak measured live (blr_device_peaks)"),
              "i8": (i8_peak, "TOP/s", "tcgen05.mma.kind::i8 128x256x32 issue peak measured live (blr_device_peaks)")}

@@ -241,6 +241,10 @@ int mmala_run(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done);
  * either may be NULL.  Lets a host that owns the random stream (the single-chain iwls() drop-in) draw the proposal itself
  * and pass the engine z = L^-1 (w' - mean).  Synchronises. */
 int mmala_read_proposal(rmhmc_handle* h, double* mean, double* chol_lower);
+/* HMC launch shape (default fused = 1, 64 rounds per launch; env RMHMC_HMC_FUSED=0): fused runs up to rounds_per_launch
+ * leapfrog rounds of hmc.py:51-62 per kernel launch with the chain state in registers (D <= 32, not row-sharded);
+ * 0 = three launches per round.  The two can be mixed on one chain set.  rounds_per_launch = 0 keeps the current value. */
+int hmc_set_fused(rmhmc_handle* h, int fused, int rounds_per_launch);
 int mmala_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop);     /* one round = one iteration of every chain */
 
 /* ---- tools.py:32-74 batched ------------------------------------------------------------------ */

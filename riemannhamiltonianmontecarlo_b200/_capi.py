@@ -58,6 +58,7 @@ SIGNATURES = {
     "hmc_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "hmc_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     "hmc_advance": (c_int, [c_void_p, c_int64, c_int64]),
+    "hmc_set_fused": (c_int, [c_void_p, c_int, c_int]),
     "mmala_chains_init": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_double]),
     "mmala_set_tape": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "mmala_run": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),

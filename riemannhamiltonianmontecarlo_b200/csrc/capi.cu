@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "ess_kernel.cuh"
 #include "hmc_kernels.cuh"
+#include "hmc_fused.cuh"
 #include "i8_metric.cuh"
 #include "metric_kernel.cuh"
 #include "mf_kernels.cuh"
@@ -99,6 +100,8 @@ struct rmhmc_handle {
     bool fuse_epilogues = false;
     bool gemm_split_k = true;       // plain-GEMM metric build: split K against wave quantisation (RMHMC_GEMM_SPLITK=0 disables)
     bool metric_gemm = true;        // 32 < D: position-iterate metric builds as v-kernel + plain GEMM (RMHMC_METRIC_GEMM=0: fused kernel)
+    bool hmc_fused = true;          // HMC: many leapfrog rounds per launch (hmc_fused.cuh) instead of three launches per round
+    int hmc_rounds_per_launch = 64;
     int fuse_momentum = 1;          // implicit momentum half-step: 1 all iterates in one k_pass launch, 2 k_mom_fp, 0 unfused
     // row-sharded mode: this handle holds the rows of shard `shard_rank`; every build is all-reduced
     ncclComm_t comm = nullptr;
@@ -1156,6 +1159,35 @@ int hmc_round(rmhmc_handle* h) {
     return RMHMC_OK;
 }
 
+// n_rounds leapfrog rounds in ONE launch (hmc_fused.cuh): chain state in registers, X streamed n_rounds times
+bool hmc_fusable(const rmhmc_handle* h) { return h->hmc_fused && h->dim <= 32 && !h->comm; }
+int hmc_rounds(rmhmc_handle* h, int64_t n_rounds) {
+    if (!hmc_fusable(h)) {
+        for (int64_t r = 0; r < n_rounds; ++r) {
+            int rc = hmc_round(h);
+            if (rc) return rc;
+        }
+        return RMHMC_OK;
+    }
+    const bool small = few_chains(h, (int64_t)148 * 2 * kHfWarps * 8);
+    const int warps = small ? kPassWarpsSmall : kHfWarps;
+    const size_t smem = hmc_fused_smem_bytes(h->xs, warps);
+    void (*kern)(EngineParams, ChainArrays, const double*, int, int, int) = small ? k_hmc_rounds<kPassWarpsSmall> : k_hmc_rounds<kHfWarps>;
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // bounded launches: a launch of 64 rounds is ~30 ms at 65 536 German-shaped chains
+    for (int64_t done = 0; done < n_rounds;) {
+        const int n = (int)std::min<int64_t>(n_rounds - done, h->hmc_rounds_per_launch);
+        {
+            Bracket b(h, 3);
+            kern<<<blocks_for(h->n_chains, warps * 8), warps * 32, smem, h->stream>>>(h->P, h->S, h->x_pad, h->xs, (int)h->n_rows, n);
+        }
+        h->launches += 1;
+        done += n;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return RMHMC_OK;
+}
+
 // ---- manifold MALA (mmala_kernels.cuh): one round = one MCMC iteration of every chain
 int launch_mmala_turn(rmhmc_handle* h, int do_back, int do_front, int init) {
     const unsigned C = (unsigned)h->n_chains;
@@ -1224,10 +1256,8 @@ int run_until(rmhmc_handle* h, int64_t it_stop, int64_t* rounds_done, bool hmc, 
         // every unfinished iteration needs at least one round; keep the host a bounded distance ahead
         int64_t chunk = rem < 512 ? rem : 512;
         if (hmc) {
-            for (int64_t r = 0; r < chunk; ++r) {
-                int rc = hmc_round(h);
-                if (rc) return rc;
-            }
+            int rc = hmc_rounds(h, chunk);
+            if (rc) return rc;
         } else if (mmala) {
             int rc = mmala_rounds(h, chunk);
             if (rc) return rc;
@@ -1387,6 +1417,7 @@ int rmhmc_create(rmhmc_handle** out, int device, int64_t n_rows, int dim, double
 #undef CREATE_TRY
     h->P.n_leapfrog = 6; h->P.step_size = 0.5; h->P.n_fixed = 4;
     if (const char* e = std::getenv("RMHMC_FUSE_MOMENTUM")) h->fuse_momentum = std::atoi(e);
+    if (const char* e = std::getenv("RMHMC_HMC_FUSED")) h->hmc_fused = std::atoi(e) != 0;
     if (const char* e = std::getenv("RMHMC_METRIC_GEMM")) h->metric_gemm = std::atoi(e) != 0;
     if (const char* e = std::getenv("RMHMC_GEMM_SPLITK")) h->gemm_split_k = std::atoi(e) != 0;      // A/B switch for profiling
     if (const char* e = std::getenv("RMHMC_METRIC_MODE")) {
@@ -1788,10 +1819,12 @@ int hmc_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (h->P.rng_mode == 0 && it_stop > h->tape_base + h->tape_window) it_stop = h->tape_base + h->tape_window;
     h->P.it_stop = it_stop;
-    for (int64_t r = 0; r < n_rounds; ++r) {
-        int rc = hmc_round(h);
-        if (rc) return rc;
-    }
+    return hmc_rounds(h, n_rounds);
+}
+int hmc_set_fused(rmhmc_handle* h, int fused, int rounds_per_launch) {
+    if (!h || rounds_per_launch < 0) return h ? fail(h, RMHMC_E_INVALID, "hmc_set_fused: bad arguments") : RMHMC_E_INVALID;
+    h->hmc_fused = fused != 0;
+    if (rounds_per_launch > 0) h->hmc_rounds_per_launch = rounds_per_launch;
     return RMHMC_OK;
 }
 int mmala_advance(rmhmc_handle* h, int64_t n_rounds, int64_t it_stop) {

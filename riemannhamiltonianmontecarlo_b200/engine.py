@@ -400,10 +400,17 @@ class HMCSampler(_SamplerBase):
     _is_hmc = True
     _advance_fn = "hmc_advance"
 
-    def __init__(self, data: LogisticData, n_chains: int, n_leapfrog: int = 100, step_size: float = 0.14, theta0=None):
+    def __init__(self, data: LogisticData, n_chains: int, n_leapfrog: int = 100, step_size: float = 0.14, theta0=None,
+                 fused=None, rounds_per_launch: int = 0):
         super().__init__(data, n_chains, theta0)
         self.n_leapfrog, self.step_size = int(n_leapfrog), float(step_size)
         _capi.check(self._lib.hmc_configure(self.h, self.n_leapfrog, self.step_size), self.h, "hmc_configure")
+        if fused is not None or rounds_per_launch:
+            self.set_fused(True if fused is None else fused, rounds_per_launch)
+
+    def set_fused(self, fused: bool, rounds_per_launch: int = 0):
+        """Many leapfrog rounds per launch with the chain state in registers (default) or three launches per round."""
+        _capi.check(self._lib.hmc_set_fused(self.h, int(bool(fused)), int(rounds_per_launch)), self.h, "hmc_set_fused")
 
     def set_tape(self, z, u_step, u_acc, it_base: int = 0):
         d = self.data

@@ -259,8 +259,14 @@ def test_chains_are_independent_of_batch_composition(pkg, golden, partials):
     assert np.array_equal(tr_all["h_proposed"][:2], tr_two["h_proposed"])
 
 
+# how the HMC rounds are launched (include/rmhmc_b200.h: hmc_set_fused): many rounds per launch with the chain state in
+# registers (the default), one launch of 3 rounds at a time, three launches per round, and the two kernels alternating
+HMC_LAUNCH = ["fused", "fused3", "per_round", "mixed"]
+
+
+@pytest.mark.parametrize("launch", HMC_LAUNCH)
 @pytest.mark.parametrize("name", ["hmc_australian_shaped", "hmc_pima_real"])
-def test_hmc_matches_reference(pkg, golden, name):
+def test_hmc_matches_reference(pkg, golden, name, launch):
     fx = golden(name)
     xx, t = fx["xx"], fx["t"]
     n_iter, burn_in = int(fx["n_iter"]), int(fx["burn_in"])
@@ -270,6 +276,15 @@ def test_hmc_matches_reference(pkg, golden, name):
     s.set_tape(fx["z"], fx["u_step"], fx["u_acc"])
     s.set_samples(n_iter - burn_in, burn_in)
     s.set_trace(n_iter)
+    if launch == "fused3":
+        s.set_fused(True, 3)
+    elif launch == "per_round":
+        s.set_fused(False)
+    elif launch == "mixed":          # trajectories cross the hand-over between the two kernels in both directions
+        for k in range(40):
+            s.set_fused(k % 2 == 0, 5)
+            s.advance(7, n_iter)
+        s.set_fused(True, 64)
     s.run(n_iter)
     tr = s.trace_numpy()
     samples = s.samples.cpu().numpy()
