@@ -358,8 +358,15 @@ __device__ __forceinline__ double chol_fixed(double (&row)[N], double* colbuf, i
         double* cb = colbuf + (k & 1) * 32;
         cb[lane] = lik;
         __syncwarp();
+        // column k broadcast two entries per shared load (16-byte aligned pairs; k is a compile-time constant)
+        if (((k + 1) & 1) && k + 1 < N) row[k + 1] = fma(-lik, cb[k + 1], row[k + 1]);
 #pragma unroll
-        for (int j = k + 1; j < N; ++j) row[j] = fma(-lik, cb[j], row[j]);
+        for (int j = (k + 2) & ~1; j + 1 < N; j += 2) {
+            const double2 cj = *reinterpret_cast<const double2*>(cb + j);
+            row[j] = fma(-lik, cj.x, row[j]);
+            row[j + 1] = fma(-lik, cj.y, row[j + 1]);
+        }
+        if ((N & 1) && ((k + 2) & ~1) <= N - 1) row[N - 1] = fma(-lik, cb[N - 1], row[N - 1]);
     }
     dinv = dinv_acc;
     return warp_sum(lane < N ? log(diag) : 0.0);
@@ -875,10 +882,14 @@ k_chain_turn(EngineParams P, ChainArrays S, int do_back, int do_front, int init)
     }
 }
 
+#ifndef RMHMC_SOLVE_CTAS
+#define RMHMC_SOLVE_CTAS 16
+#endif
+constexpr int kSolveCtas = RMHMC_SOLVE_CTAS;
 // ---------------------------------------------------------------- position fixed-point iterate (x (F-1))
 // solve G(theta_w) u = p, theta_w <- theta + s eps/2 (u0 + u)   (rmhmc.py:116-122)
 template <int N>
-__global__ void __launch_bounds__(32, 16) k_chain_solve(EngineParams P, ChainArrays S, int is_last) {
+__global__ void __launch_bounds__(32, kSolveCtas) k_chain_solve(EngineParams P, ChainArrays S, int is_last) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = blockIdx.x, lane = threadIdx.x, D = P.dim;
     if (c >= P.n_chains) return;
