@@ -115,7 +115,7 @@ struct rmhmc_handle {
     // INT8-slice metric build on tcgen05 (i8_metric.cuh): digit planes of KR2(X)^T per data set, of V per chain set
     int metric_mode = RMHMC_METRIC_FP64_DMMA;
     int i8_slices = 5;              // digits per operand (RMHMC_I8_SLICES = 5 | 6)
-    bool i8_ok = false;             // B planes formed (dim <= 32, rows <= kI8MaxRows, tensor-map encoder available)
+    bool i8_ok = false;             // B planes formed (tensor-map encoder available, planes fit a third of the free memory)
     signed char* b8 = nullptr;      // [S][b_rows][kp]
     double2* colinfo = nullptr;     // [b_rows]
     double* colmax = nullptr;       // [P2p]
@@ -164,7 +164,10 @@ bool few_chains(const rmhmc_handle* h, int64_t threshold) {
     if (h->launch_regime == RMHMC_REGIME_LARGE) return false;
     return h->n_chains < threshold;
 }
-bool use_i8(const rmhmc_handle* h) { return h->metric_mode == RMHMC_METRIC_INT8_TCGEN05 && h->i8_ok; }
+// 32 < D: v reaches the digit kernel through hbuf, which only the matrix-free mode allocates
+bool use_i8(const rmhmc_handle* h) {
+    return h->metric_mode == RMHMC_METRIC_INT8_TCGEN05 && h->i8_ok && (h->dim <= kMaxDimWarp || h->matrix_free);
+}
 
 // ------------------------------------------------------------------ small layout kernels
 __global__ void k_pad_design(const double* __restrict__ xx, const double* __restrict__ t, double* __restrict__ xp,
@@ -914,6 +917,15 @@ bool use_metric_gemm(const rmhmc_handle* h) {
     return h->metric_gemm && is_big(h) && h->kr2n && h->matrix_free &&
            blocks_for(h->n_chains, kTbChains) * ((h->p2p + kTbCols - 1) / kTbCols) >= 148;
 }
+int ensure_split_buf(rmhmc_handle* h, size_t need) {
+    if (need > h->split_cap) {
+        if (h->split_buf) CUDA_TRY(h, cudaFree(h->split_buf));
+        h->split_buf = nullptr; h->split_cap = 0;
+        CUDA_TRY(h, cudaMalloc((void**)&h->split_buf, need * 8));
+        h->split_cap = need;
+    }
+    return RMHMC_OK;
+}
 // g_tmp = hbuf . KR2(X) + I/alpha (no brackets of its own)
 int launch_metric_gemm(rmhmc_handle* h) {
     ChainArrays& S = h->S;
@@ -935,13 +947,8 @@ int launch_metric_gemm(rmhmc_handle* h) {
     }
     const size_t cg = (size_t)C * h->p2p;
     if (splits > 1) {
-        const size_t need = (size_t)splits * cg;
-        if (need > h->split_cap) {
-            if (h->split_buf) CUDA_TRY(h, cudaFree(h->split_buf));
-            h->split_buf = nullptr; h->split_cap = 0;
-            CUDA_TRY(h, cudaMalloc((void**)&h->split_buf, need * 8));
-            h->split_cap = need;
-        }
+        int rc = ensure_split_buf(h, (size_t)splits * cg);
+        if (rc) return rc;
         t.tpack = h->split_buf; t.split_stride = cg;
         grid.z = (unsigned)splits;
     }
@@ -987,14 +994,24 @@ int i8_form_b(rmhmc_handle* h, cudaStream_t st) {
 
 // digit planes of KR2(X)^T + their tensor map; leaves i8_ok false when the shape is outside the kernel's range
 int i8_setup(rmhmc_handle* h) {
-    if (h->dim > kMaxDimWarp || h->n_rows_pad > kI8MaxRows || !tensor_map_encoder()) return RMHMC_OK;
+    if (!tensor_map_encoder()) return RMHMC_OK;
     const int S = h->i8_slices, nc = S == 6 ? I8Shape<6>::NC : I8Shape<5>::NC;
     h->i8_kp = i8_kp(h->n_rows_pad);
     h->i8_b_rows = (h->p2 + nc - 1) / nc * nc;
+    if (const char* e = std::getenv("RMHMC_I8_LEVERAGE")) h->i8_leverage = std::atoi(e) != 0;
+    {
+        // digit planes are S bytes per entry of KR2(X) (and again, by data row, for the leverage GEMM): stay within a
+        // third of the free memory, drop the leverage planes first
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t b_bytes = (size_t)S * h->i8_b_rows * h->i8_kp;
+        const size_t bl_bytes = (size_t)S * ((h->n_rows_pad + nc - 1) / nc * nc) * pad_up(h->p2, kI8BlockK);
+        if (b_bytes > free_b / 3) return RMHMC_OK;
+        if (b_bytes + bl_bytes > free_b / 3) h->i8_leverage = false;
+    }
     CUDA_TRY(h, cudaMalloc((void**)&h->b8, (size_t)S * h->i8_b_rows * h->i8_kp));
     CUDA_TRY(h, cudaMalloc((void**)&h->colinfo, (size_t)h->i8_b_rows * sizeof(double2)));
     CUDA_TRY(h, cudaMalloc((void**)&h->colmax, (size_t)h->p2p * 8));
-    if (const char* e = std::getenv("RMHMC_I8_LEVERAGE")) h->i8_leverage = std::atoi(e) != 0;
     if (h->i8_leverage && h->kr2t) {
         h->i8_kpl = pad_up(h->p2, kI8BlockK);
         h->i8_bl_rows = (h->n_rows_pad + nc - 1) / nc * nc;
@@ -1010,6 +1027,57 @@ int i8_setup(rmhmc_handle* h) {
         return fail(h, RMHMC_E_CUDA, "cuTensorMapEncodeTiled failed for the leverage digit planes");
     h->i8_ok = true;
     return RMHMC_OK;
+}
+
+// G = (digits of V in a8) . KR2(X) digits + I/alpha -> g_out; K is split when the int32 accumulators could overflow
+// (more than kI8MaxRows rows) or when the tiles alone would leave most SMs idle; partial sums are added in split order
+template <int S>
+int i8_metric_gemm(rmhmc_handle* h, int64_t C, int64_t a_rows, const CUtensorMap& map_a, double* g_out) {
+    I8GemmArgs g{};
+    g.g_out = g_out; g.colinfo = h->colinfo; g.alpha_inv = h->shard_rank == 0 ? 1.0 / h->alpha : 0.0;
+    g.n_chains = (int)C; g.p2 = h->p2; g.p2p = h->p2p; g.k_blocks = h->i8_kp / kI8BlockK;
+    g.a_rows = (int)a_rows; g.b_rows = h->i8_b_rows; g.debug_class = -1;
+    const int max_kb = kI8MaxRows / kI8BlockK;
+    int splits = (g.k_blocks + max_kb - 1) / max_kb;
+    const int64_t tiles = (int64_t)i8_chunks<S>(h->p2) * ((C + kI8TileM - 1) / kI8TileM);
+    while (tiles * splits < 148 && g.k_blocks / (splits * 2) >= 64) splits *= 2;
+    const size_t cg = (size_t)C * h->p2p;
+    if (splits > 1) {
+        int rc = ensure_split_buf(h, (size_t)splits * cg);
+        if (rc) return rc;
+        g.kb_split = (g.k_blocks + splits - 1) / splits;
+        splits = (g.k_blocks + g.kb_split - 1) / g.kb_split;
+        g.g_out = h->split_buf; g.split_stride = cg;
+    }
+    cudaError_t e = i8_launch_gemm<S>(map_a, h->map_b, g, h->stream);
+    if (e != cudaSuccess) return fail(h, RMHMC_E_CUDA, std::string("k_i8_gemm: ") + cudaGetErrorString(e));
+    h->launches += 1;
+    if (splits > 1) {
+        k_reduce_splits<<<blocks_for(cg, 256), 256, 0, h->stream>>>(h->split_buf, cg, splits, g_out, cg);
+        h->launches += 1;
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    return RMHMC_OK;
+}
+// 32 < D: v is already in HBM (k_metric<MODE 5 / 6> -> vbuf[C][Np]); digits, then the GEMM
+template <int S>
+int i8_gemm_from_v_s(rmhmc_handle* h, int64_t C, const double* vbuf, signed char* a8, int64_t a_rows, const CUtensorMap& map_a,
+                     double* g_out) {
+    {
+        Bracket bv(h, 8);
+        const long long n = (long long)C * (h->i8_kp / 16);
+        k_i8_vdigits<S><<<blocks_for(n, 256), 256, 0, h->stream>>>(vbuf, h->n_rows_pad, a8, (size_t)a_rows * h->i8_kp, h->i8_kp,
+                                                                    (long long)C);
+        h->launches += 1;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    Bracket bg(h, 9);
+    return i8_metric_gemm<S>(h, C, a_rows, map_a, g_out);
+}
+int i8_gemm_from_v(rmhmc_handle* h, int64_t C, const double* vbuf, signed char* a8, int64_t a_rows, const CUtensorMap& map_a,
+                   double* g_out) {
+    return h->i8_slices == 6 ? i8_gemm_from_v_s<6>(h, C, vbuf, a8, a_rows, map_a, g_out)
+                             : i8_gemm_from_v_s<5>(h, C, vbuf, a8, a_rows, map_a, g_out);
 }
 
 struct I8Closing {              // outputs of the closing build besides G (null: position-iterate build)
@@ -1033,15 +1101,9 @@ int i8_build_s(rmhmc_handle* h, int64_t C, const double* theta, signed char* a8,
         }
     }
     if (e != cudaSuccess) return fail(h, RMHMC_E_CUDA, std::string("k_i8_vslice: ") + cudaGetErrorString(e));
+    h->launches += 1;
     Bracket bg(h, 9);
-    I8GemmArgs g{};
-    g.g_out = g_out; g.colinfo = h->colinfo; g.alpha_inv = h->shard_rank == 0 ? 1.0 / h->alpha : 0.0;
-    g.n_chains = (int)C; g.p2 = h->p2; g.p2p = h->p2p; g.k_blocks = h->i8_kp / kI8BlockK;
-    g.a_rows = (int)a_rows; g.b_rows = h->i8_b_rows; g.debug_class = -1;
-    e = i8_launch_gemm<S>(map_a, h->map_b, g, h->stream);
-    if (e != cudaSuccess) return fail(h, RMHMC_E_CUDA, std::string("k_i8_gemm: ") + cudaGetErrorString(e));
-    h->launches += 2;
-    return RMHMC_OK;
+    return i8_metric_gemm<S>(h, C, a_rows, map_a, g_out);
 }
 int i8_build(rmhmc_handle* h, int64_t C, const double* theta, signed char* a8, int64_t a_rows, const CUtensorMap& map_a,
              double* g_out, const I8Closing* cl) {
@@ -1052,6 +1114,15 @@ int i8_build(rmhmc_handle* h, int64_t C, const double* theta, signed char* a8, i
 int build_metric_iterate(rmhmc_handle* h) {
     ChainArrays& S = h->S;
     const int64_t C = h->n_chains;
+    if (use_i8(h) && is_big(h)) {                // 32 < D: f and v by the FP64 kernel (v -> hbuf), then digits + GEMM
+        Bracket b(h, 0);
+        h->suppress_brackets = true;
+        MetricArgs a = metric_args(h, C, S.theta_w, nullptr, nullptr, nullptr, nullptr);
+        a.vout = S.hbuf;
+        int rc = launch_metric<5>(h, a);
+        h->suppress_brackets = false;
+        return rc ? rc : i8_gemm_from_v(h, C, S.hbuf, h->a8, h->c_pad, h->map_a, S.g_tmp);
+    }
     if (use_i8(h)) {
         Bracket b(h, 0);
         return i8_build(h, C, S.theta_w, h->a8, h->c_pad, h->map_a, S.g_tmp, nullptr);
@@ -1068,6 +1139,16 @@ int build_metric_iterate(rmhmc_handle* h) {
 }
 // closing build of a leapfrog step (G, X^T (t - p), log-likelihood, c_n), same split for 32 < D
 int build_metric_closing(rmhmc_handle* h, int flip) {
+    if (use_i8(h) && is_big(h)) {
+        Bracket b(h, 1);
+        h->suppress_brackets = true;
+        MetricArgs a = closing_args(h, flip);
+        a.g_out = nullptr;
+        a.vout = h->S.hbuf;
+        int rc = launch_metric<6>(h, a);
+        h->suppress_brackets = false;
+        return rc ? rc : i8_gemm_from_v(h, h->n_chains, h->S.hbuf, h->a8, h->c_pad, h->map_a, h->S.g_tmp);
+    }
     if (use_i8(h)) {
         ChainArrays& S = h->S;
         I8Closing cl{S.grad_tmp, S.loglik_tmp, h->matrix_free ? S.cw : S.cbuf, h->matrix_free ? S.cur : nullptr, flip,
@@ -1609,7 +1690,16 @@ int rmhmc_metric(rmhmc_handle* h, int64_t C, const double* theta, double* G, dou
             rc = dev_alloc(h, &a8, (size_t)h->i8_slices * a_rows * h->i8_kp, &tmp);
             if (!rc && !make_tensor_map_u8_k64(&map_a, a8, (uint64_t)h->i8_slices * a_rows, (uint64_t)h->i8_kp, kI8TileM))
                 rc = fail(h, RMHMC_E_CUDA, "cuTensorMapEncodeTiled failed");
-            if (!rc) rc = i8_build(h, C, theta, a8, a_rows, map_a, gp, nullptr);
+            if (!rc && is_big(h)) {
+                double* vbuf = nullptr;
+                rc = dev_alloc(h, &vbuf, (size_t)C * h->n_rows_pad, &tmp);
+                MetricArgs av = metric_args(h, C, theta, nullptr, nullptr, nullptr, nullptr);
+                av.vout = vbuf;
+                if (!rc) rc = launch_metric<5>(h, av);
+                if (!rc) rc = i8_gemm_from_v(h, C, vbuf, a8, a_rows, map_a, gp);
+            } else if (!rc) {
+                rc = i8_build(h, C, theta, a8, a_rows, map_a, gp, nullptr);
+            }
         } else if (!rc) { a.grad_out = nullptr; a.loglik_out = nullptr; rc = launch_metric<0>(h, a); }   // G
     }
     if (!rc) {

@@ -76,6 +76,10 @@ struct I8GemmArgs {
     int n_chains, p2, p2p, k_blocks;      // p2 valid output columns, p2p = row stride of g_out (columns < p2p are stored)
     int a_rows, b_rows;         // rows per digit plane in the A / B tensor maps
     int debug_class;            // >= 0: write accumulator `class` alone (self-test)
+    // split K (more than kI8MaxRows rows: the int32 accumulators hold S * 16384 * 2^14): blockIdx.z takes k-blocks
+    // [z kb_split, (z + 1) kb_split) and writes its scaled partial sum to g_out + z split_stride; 0 = no split
+    int kb_split;
+    size_t split_stride;
 };
 
 struct I8VsArgs {
@@ -223,7 +227,6 @@ __global__ void k_i8_qdigits(const double* __restrict__ qpack, int p2, int p2k, 
     }
 }
 
-// ------------------------------------------------------------------------------------------------ A planes
 // biased digit bytes of one v: returns the S bytes u_{S-1} (least significant) .. u_0 in lo (bytes 0..3) and hi
 template <int S>
 __device__ __forceinline__ void i8_digits(double v, unsigned& lo, unsigned& hi) {
@@ -231,6 +234,37 @@ __device__ __forceinline__ void i8_digits(double v, unsigned& lo, unsigned& hi) 
     lo = (unsigned)__double2loint(t);
     hi = (unsigned)__double2hiint(t);
 }
+
+// digits of v = p (1 - p) already in HBM (32 < D: k_metric<MODE 5 / 6> writes it): vbuf[c][n_rows_pad] -> a8[s][c][kp], fixed
+// scale kI8ScaleA.  One thread converts 16 consecutive rows (128 bytes in, S x 16 bytes out).
+template <int S>
+__global__ void k_i8_vdigits(const double* __restrict__ vbuf, int n_rows_pad, signed char* __restrict__ a8, size_t plane_stride,
+                             int kp, long long n_chains) {
+    const int per_chain = kp / 16;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chains * per_chain) return;
+    const long long c = i / per_chain;
+    const int k0 = (int)(i - c * per_chain) * 16;
+    const double* v = vbuf + (size_t)c * n_rows_pad;
+    unsigned lo[16], hi[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) i8_digits<S>(k0 + j < n_rows_pad ? v[k0 + j] : 0.0, lo[j], hi[j]);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int byte = S - 1 - s;
+        const unsigned b = byte & 3;
+        unsigned w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned v0 = byte < 4 ? lo[4 * j] : hi[4 * j], v1 = byte < 4 ? lo[4 * j + 1] : hi[4 * j + 1];
+            const unsigned v2 = byte < 4 ? lo[4 * j + 2] : hi[4 * j + 2], v3 = byte < 4 ? lo[4 * j + 3] : hi[4 * j + 3];
+            w[j] = __byte_perm(__byte_perm(v0, v1, b | ((4 + b) << 4)), __byte_perm(v2, v3, b | ((4 + b) << 4)), 0x5410) ^ 0x80808080u;
+        }
+        *reinterpret_cast<uint4*>(a8 + (size_t)s * plane_stride + (size_t)c * kp + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ A planes
 
 // thread = chain; the CTA's 128 chains sweep the design matrix in 32-row blocks (cp.async double buffer, X rows are
 // broadcast reads).  DP = parameters rounded up to the unroll bound (even).  blockIdx.y splits the rows (iterate builds).
@@ -665,6 +699,8 @@ __global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * NC;                 // first packed column
     const int m0 = blockIdx.y * kI8TileM;           // first chain
+    const int kb0 = a.kb_split > 0 ? (int)blockIdx.z * a.kb_split : 0;                       // first k-block of this CTA
+    const int nkb = a.kb_split > 0 ? (a.k_blocks - kb0 < a.kb_split ? a.k_blocks - kb0 : a.kb_split) : a.k_blocks;
 
     // one stage of operands: S digit tiles of V (128 chains x 64 bytes of K) and S of KR2(X) (NC columns x 64 bytes)
     auto issue_stage = [&](int kb) {
@@ -673,9 +709,9 @@ __global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) 
         unsigned char* sb = sa + S * Sh::A_SLICE;
         mbar_expect_tx(&full[st], Sh::STAGE_BYTES);
 #pragma unroll
-        for (int s = 0; s < S; ++s) tma_load_2d(sa + s * Sh::A_SLICE, &map_a, kb * kI8BlockK, s * a.a_rows + m0, &full[st]);
+        for (int s = 0; s < S; ++s) tma_load_2d(sa + s * Sh::A_SLICE, &map_a, (kb0 + kb) * kI8BlockK, s * a.a_rows + m0, &full[st]);
 #pragma unroll
-        for (int s = 0; s < S; ++s) tma_load_2d(sb + s * Sh::B_SLICE, &map_b, kb * kI8BlockK, s * a.b_rows + n0, &full[st]);
+        for (int s = 0; s < S; ++s) tma_load_2d(sb + s * Sh::B_SLICE, &map_b, (kb0 + kb) * kI8BlockK, s * a.b_rows + n0, &full[st]);
     };
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a);
@@ -684,7 +720,7 @@ __global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) 
         mbar_init(acc_full, 1);
         mbar_fence_init();
         // the first stages need neither TMEM nor the other warps: their latency overlaps the allocation and the CTA barrier
-        for (int kb = 0; kb < ST && kb < a.k_blocks; ++kb) issue_stage(kb);
+        for (int kb = 0; kb < ST && kb < nkb; ++kb) issue_stage(kb);
     }
     if (warp == 1) tmem_alloc(tmem_slot, Sh::TMEM_COLS);
     tcgen05_fence_before();
@@ -694,7 +730,7 @@ __global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) 
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = ST; kb < a.k_blocks; ++kb) {
+            for (int kb = ST; kb < nkb; ++kb) {
                 mbar_wait_or_trap(&empty[kb % ST], (uint32_t)(((kb / ST) - 1) & 1));
                 issue_stage(kb);
             }
@@ -705,7 +741,7 @@ __global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) 
             // column blocks, and the B digit tiles are adjacent in shared memory: one MMA of N = MB * NC columns covers
             // MB consecutive digits j (fewer, wider MMAs: the A tile is fetched 9 instead of 15 times per K step).
             constexpr int MB = 256 / NC;          // digit tiles per MMA (N <= 256)
-            for (int kb = 0; kb < a.k_blocks; ++kb) {
+            for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % ST;
                 mbar_wait_or_trap(&full[st], (uint32_t)((kb / ST) & 1));
                 tcgen05_fence_after();
@@ -746,6 +782,8 @@ __global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) 
         mbar_wait_or_trap(acc_full, 0);          // all MMAs done: accumulators final, the operand ring is free
         tcgen05_fence_after();
         double* out_s = reinterpret_cast<double*>(base) + (size_t)ew * 32 * OS;
+        double* g_dst = a.g_out + (size_t)blockIdx.z * a.split_stride;
+        const double alpha_inv = blockIdx.z == 0 ? a.alpha_inv : 0.0;
         const int c_lane = m0 + quarter * 32 + lane;
         const double rs = (a.rowscale && c_lane < a.n_chains) ? a.rowscale[c_lane] : 1.0;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -772,7 +810,7 @@ __global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) 
                     for (int w = 0; w < S; ++w) if (w == a.debug_class) t = x[w];
                 }
                 const double2 ci = ci_s[cg * 16 + j];
-                out_s[lane * OS + (cg - cg_begin) * 16 + j] = n0 + cg * 16 + j < a.p2 ? fma(t * rs, ci.x, ci.y * a.alpha_inv) : 0.0;
+                out_s[lane * OS + (cg - cg_begin) * 16 + j] = n0 + cg * 16 + j < a.p2 ? fma(t * rs, ci.x, ci.y * alpha_inv) : 0.0;
             }
         }
         __syncwarp();
@@ -782,7 +820,7 @@ __global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) 
             for (int idx = lane; idx < 32 * n; idx += 32) {
                 const int row = idx / n, col = idx - row * n;
                 const int c = m0 + quarter * 32 + row;
-                if (c < a.n_chains && col0 + col < a.p2p) a.g_out[(size_t)c * a.p2p + col0 + col] = out_s[row * OS + col];
+                if (c < a.n_chains && col0 + col < a.p2p) g_dst[(size_t)c * a.p2p + col0 + col] = out_s[row * OS + col];
             }
         };
         if (ncols == 48) copy_out(std::integral_constant<int, 48>{});
@@ -870,7 +908,8 @@ inline cudaError_t i8_launch_gemm(const CUtensorMap& map_a, const CUtensorMap& m
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const dim3 grid((unsigned)i8_chunks<S>(a.p2), (unsigned)((a.n_chains + kI8TileM - 1) / kI8TileM));
+    const unsigned splits = a.kb_split > 0 ? (unsigned)((a.k_blocks + a.kb_split - 1) / a.kb_split) : 1u;
+    const dim3 grid((unsigned)i8_chunks<S>(a.p2), (unsigned)((a.n_chains + kI8TileM - 1) / kI8TileM), splits);
     k_i8_gemm<S><<<grid, I8Shape<S>::THREADS, I8Shape<S>::SMEM, stream>>>(map_a, map_b, a);
     return cudaGetLastError();
 }

@@ -410,18 +410,20 @@ def test_philox_chains_reach_the_reference_posterior(pkg, golden):
 
 
 # ------------------------------------------------------------------ 32 < D <= 128 (CTA-per-chain path)
+@pytest.mark.parametrize("metric", METRIC)
 @pytest.mark.parametrize("dim,n_rows", [(40, 500), (64, 700), (100, 450)])
-def test_large_dim_seams_match_oracle(pkg, dim, n_rows):
+def test_large_dim_seams_match_oracle(pkg, dim, n_rows, metric):
     xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 4000 + dim)
     thetas = _thetas(dim, 5, 21) * 0.3
-    data = pkg.LogisticData(xx, t)
+    data = pkg.LogisticData(xx, t, metric=metric)
+    assert data.metric_mode == metric
     g, grad, lj = data.metric(thetas)
     dg, tr = data.metric_partials(thetas[:2])
     l, gi, ld = data.chol_logdet(g)
     for c in range(thetas.shape[0]):
         w = thetas[c].reshape(-1, 1)
         _, p, v, g_ref = bo.fisher_metric(xx, w)
-        assert rel_err(g[c], g_ref) < 1e-12
+        assert rel_err(g[c], g_ref) < G_TOL[metric]
         assert rel_err(grad[c], bo.likelihood_gradient(xx, t, w)[:, 0]) < 1e-11
         assert abs(lj[c] - bo._scalar(bo.log_joint(xx, t, w))) < 1e-11 * abs(lj[c])
         assert rel_err(l[c], np.linalg.cholesky(g[c])) < 1e-12
@@ -433,14 +435,40 @@ def test_large_dim_seams_match_oracle(pkg, dim, n_rows):
     data.close()
 
 
+@pytest.mark.parametrize("metric", METRIC)
 @pytest.mark.parametrize("partials", PARTIALS)
 @pytest.mark.parametrize("dim,n_rows", [(40, 500), (64, 700)])
-def test_large_dim_rmhmc_matches_oracle(pkg, dim, n_rows, partials):
+def test_large_dim_rmhmc_matches_oracle(pkg, dim, n_rows, partials, metric):
+    """32 < D: CTA-per-chain stages; metric = i8 runs v through HBM, the digit kernel and the tcgen05 GEMM (matrix-free
+    partials; with the packed-tensor partials the build stays on the FP64 kernel)."""
     xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 4100 + dim)
     n_iter, burn, c = 5, 1, 3
     tapes = [bo.make_tape(n_iter, dim, 9100 + i) for i in range(c)]
     ref, infos = bo.rmhmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=4, step_size=0.3, n_fixed=4)
-    out, _, info = pkg.rmhmc_batched(xx, t, c, n_iter, burn, 4, 0.3, 4, draws=bo.stack_tapes(tapes), partials=partials)
+    out, _, info = pkg.rmhmc_batched(xx, t, c, n_iter, burn, 4, 0.3, 4, draws=bo.stack_tapes(tapes), partials=partials,
+                                     metric=metric)
+    assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
+    assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
+
+
+def test_int8_build_splits_k_beyond_the_int32_range(pkg):
+    """More than 16 384 data rows: the int32 accumulators of the digit GEMM could overflow, so K is split over blockIdx.z
+    and the scaled partial sums are added in FP64 (i8_metric_gemm).  G per build and a short run against the oracle."""
+    dim, n_rows = 10, 40000
+    xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 4700)
+    thetas = _thetas(dim, 5, 23) * 0.5
+    thetas[1] = 0.0                  # v = 1/4 on every row: the largest accumulator values
+    data = pkg.LogisticData(xx, t, metric="i8")
+    assert data.metric_mode == "i8"
+    g, grad, lj = data.metric(thetas)
+    for c in range(thetas.shape[0]):
+        _, _, _, g_ref = bo.fisher_metric(xx, thetas[c].reshape(-1, 1))
+        assert rel_err(g[c], g_ref) < G_TOL["i8"]
+    data.close()
+    n_iter, burn, c = 3, 0, 3
+    tapes = [bo.make_tape(n_iter, dim, 9700 + i) for i in range(c)]
+    ref, infos = bo.rmhmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=3, step_size=0.05, n_fixed=4)
+    out, _, info = pkg.rmhmc_batched(xx, t, c, n_iter, burn, 3, 0.05, 4, draws=bo.stack_tapes(tapes), metric="i8")
     assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
     assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
 
@@ -481,8 +509,6 @@ def test_row_sharded_code_path_on_one_rank_matches_oracle(pkg, dim, n_rows, metr
     """BASELINE.json configs[4] mechanism on ONE GPU: rmhmc_comm_init(world = 1) switches the engine to the row-sharded
     schedule (an NCCL all-reduce after every metric build and every pass, unfused momentum iterates); with one rank the
     sums are the data set's, so the chains must follow the oracle (the 2-GPU test compares real shards as well)."""
-    if dim > 32 and metric == "i8":
-        pytest.skip("the INT8 build covers dim <= 32")
     xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 5100 + dim)
     n_iter, burn, c = 5, 1, 4
     tapes = [bo.make_tape(n_iter, dim, 9350 + i) for i in range(c)]
