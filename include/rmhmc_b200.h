@@ -68,7 +68,10 @@ int rmhmc_get_partials_mode(const rmhmc_handle* h);
  *                  digits, the digit products accumulate EXACTLY in int32 TMEM accumulators (tcgen05.mma.kind::i8,
  *                  operands staged by tensor-map TMA) and are recombined in int64 / FP64.  Same G up to the digit
  *                  truncation (max relative error 1-5e-12 with 5 digits, 1e-14 with 6); gradient, log-likelihood and
- *                  c_n are evaluated in FP64 as before.  dim <= 32 and at most 16384 rows per rank.
+ *                  c_n are evaluated in FP64 as before.  Default whenever the digit planes of KR2(X) (5 bytes per
+ *                  entry) fit a third of the free device memory.  More than 16384 rows: K is split so that every int32
+ *                  accumulation stays exact, partial sums added in FP64.  32 < dim: v goes through HBM (FP64 kernel ->
+ *                  digit kernel -> GEMM) and needs the MATRIX_FREE partials (else the FP64 build runs).
  * Frees the handle's chains (call before *_chains_init).  The seam rmhmc_metric follows the mode. */
 enum { RMHMC_METRIC_FP64_DMMA = 0, RMHMC_METRIC_INT8_TCGEN05 = 1 };
 int rmhmc_set_metric_mode(rmhmc_handle* h, int mode);

@@ -27,7 +27,8 @@ x = (x - x.mean(0)) / x.std(0)                       # per-shard standardisation
 xx = np.hstack([np.ones((N_PER, 1)), x])
 beta = np.random.default_rng(99).normal(0, 0.05, (D, 1))
 t = (rng.random(N_PER) < 1 / (1 + np.exp(-(xx @ beta)[:, 0]))).astype(np.float64)
-data = r.LogisticData(xx, t, device=f"cuda:{local}", row_shard=(rank, world) if world > 1 else None)
+data = r.LogisticData(xx, t, device=f"cuda:{local}", row_shard=(rank, world) if world > 1 else None,
+                      metric=os.environ.get("CFG5_METRIC") or None)
 s = r.RMHMCSampler(data, C, 6, 0.02, 6)
 s.set_philox(5, 0)
 s.advance(1); torch.cuda.synchronize()
@@ -46,7 +47,7 @@ if rank == 0:
     P2 = D * (D + 1) // 2
     P2p, F = (P2 + 7) // 8 * 8, 6
     ar_ms, ar_n = prof.get("allreduce", (0.0, 0))
-    out = {"rows_total": N_PER * world, "rows_per_rank": N_PER, "dim": D, "chains": C, "ranks": world, "partials": data.partials_mode,
+    out = {"metric_build": data.metric_mode, "rows_total": N_PER * world, "rows_per_rank": N_PER, "dim": D, "chains": C, "ranks": world, "partials": data.partials_mode,
            "ms_per_round": dt / R * 1e3, "ranks_bit_identical": same,
            "allreduce": {"launches_per_round": ar_n / R, "ms_per_round": ar_ms / R, "share_of_round": ar_ms / (dt * 1e3),
                          "message_bytes": {"metric_iterate (G)": C * P2p * 8, "metric_closing (G | X^T(t-p) | loglik)": C * (P2p + D + 1) * 8,
