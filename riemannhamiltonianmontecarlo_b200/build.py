@@ -9,8 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "librmhmc_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["common.cuh", "metric_kernel.cuh", "tbuild_kernel.cuh", "chain_kernels.cuh", "chain_big.cuh", "mf_kernels.cuh", "momfp_kernel.cuh", "pass_kernel.cuh", "mmala_kernels.cuh", "hmc_kernels.cuh",
-           "ess_kernel.cuh", os.path.join("..", "..", "include", "rmhmc_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "rmhmc_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -6,7 +6,7 @@
 // DMMA accumulator layout -- in registers:
 //   per round:  [new iteration: p = z, RandomStep, H_current]            hmc.py:41-48,72
 //               p += eps/2 grad(w);  w' = w + eps p                      hmc.py:52-58   (NaN momentum ends the trajectory, :56-57)
-//               one pass over X:  f = X w' (DMMA), r = t - sigma(f), grad = X^T r (DMMA; C -> A fragment by four shuffles),
+//               one pass over X:  f = X w' (DMMA), r = t - sigma(f), grad = X^T r (DMMA; the C fragment of f is the A fragment of r),
 //                                 log-likelihood only for chains whose trajectory ends in this round
 //               p += eps/2 grad(w');  end of trajectory: H, accept / reject, sample store, trace          hmc.py:60-84
 // Chains free-run exactly as in the round-per-launch path (one round = one leapfrog step of every chain), the X row
@@ -90,8 +90,9 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
             }
     };
     load_slot(step == 0 ? cur : 1 - cur, step > 0);
-    const int src0 = g * 4 + (q >> 1), src1 = src0 + 2;      // shuffle sources of the C -> A fragment conversion
-    const bool odd = q & 1;
+    const int s_row = (g >> 1) + 4 * (g & 1);                // data row (within an 8-row group) behind S-stage column g: this
+                                                             // lane's two f values belong to rows q and q + 4, the rows it
+                                                             // feeds to the gradient contraction -- no C -> A shuffle
     double* wsm = scratch + (size_t)warp * 8 * 32;
     const double half_log = 0.5 * log(2.0 * 3.14159265358979323846 * alpha);
     const int k_steps = (D + 3) / 4, d_tiles = (D + 7) / 8;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
 #pragma unroll
             for (int r8 = 0; r8 < 4; ++r8) sv[r8][0] = sv[r8][1] = 0.0;
             {
-                const double* xrow = xb + (size_t)g * xs + q;
+                const double* xrow = xb + (size_t)s_row * xs + q;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     if (ks < k_steps) {
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
                     const double e = fast_exp_nonpos(-fabs(fv), exp_tab);
                     const double qq = fast_rcp_1to2(1.0 + e);
                     const double pn = fv >= 0.0 ? qq : e * qq;
-                    const int rloc = r8 * 8 + 2 * q + j;
+                    const int rloc = r8 * 8 + q + 4 * j;
                     const double t = xb[(size_t)rloc * xs + tcol];
                     const bool ovf = fv > 709.782712893384;      // the reference's exp(f) overflows: NaN gradient, -inf log-likelihood
                     rr[j] = ovf ? __longlong_as_double(0x7ff8000000000000LL) : t - pn;                 // hmc.py:53,61
@@ -203,10 +204,8 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
                         ll += t * fv - l1pe;                                                          // hmc.py:65-66
                     }
                 }
-                const double e0 = __shfl_sync(kFullMask, rr[0], src0), o0 = __shfl_sync(kFullMask, rr[1], src0);
-                const double e1 = __shfl_sync(kFullMask, rr[0], src1), o1 = __shfl_sync(kFullMask, rr[1], src1);
-                aq[r8][0] = odd ? o0 : e0;
-                aq[r8][1] = odd ? o1 : e1;
+                aq[r8][0] = rr[0];
+                aq[r8][1] = rr[1];
             }
 #pragma unroll
             for (int r8 = 0; r8 < 4; ++r8) {

@@ -8,7 +8,8 @@
 // on the FP64 tensor cores (DMMA.8x8x4).  One WARP owns 8 chains (one DMMA m-tile) for the whole kernel and does
 // both contractions of a pass itself:
 //   S[8 chains x 8 rows] = U . X^T (K = D; U fragments live in registers), R = c .* S .* S (or c .* h),
-//   R's C-fragment -> A-fragment by four warp shuffles,  Q[8 chains x D] += R . X (K = 8 rows)
+//   R's C-fragment used directly as A-fragment (the S stage's columns are fed the rows in the order that makes the two
+//   layouts coincide),  Q[8 chains x D] += R . X (K = 8 rows)
 // so there is no hand-off between warps: the only shared object is the X row-block ring (bulk TMA + full/empty
 // mbarriers, one wait and one arrive per warp per 32 rows).  The warp-specialised formulation these replace
 // (k_metric MODE 3/4, k_mom_fp: F-warps -> shared R tile -> G-warps) was issue-bound on its barrier traffic
@@ -77,8 +78,11 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
     }
     const bool active = slot >= 0;
     // rows beyond n_chains exist in the c_n / leverage buffers (chain padding), so the loads below stay in bounds
-    const double* cw_row = S.cw + (slot > 0 ? P.slot_cw : 0) + (size_t)c * P.n_rows_pad + 2 * q;
-    const double* h_row = WITH_H ? S.hbuf + (size_t)c * P.n_rows_pad + 2 * q : nullptr;
+    // DMMA column n of the S stage carries data row (n >> 1) + 4 (n & 1) of the 8-row group: this lane's two S values
+    // (columns 2q, 2q + 1) then belong to rows q and q + 4, which are exactly the rows it supplies as A fragments to
+    // the two 4-row k-steps of the Q stage -- no C -> A shuffle; the sums run over the same rows in the same order
+    const double* cw_row = S.cw + (slot > 0 ? P.slot_cw : 0) + (size_t)c * P.n_rows_pad + q;
+    const double* h_row = WITH_H ? S.hbuf + (size_t)c * P.n_rows_pad + q : nullptr;
     double ua[8];                  // U A-fragments: u[c][4 ks + q], zero beyond D (the staged label column meets a zero)
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
@@ -103,8 +107,7 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
     }
     const int k_steps = (D + 3) / 4;
     const int d_tiles = (D + 7) / 8;
-    const int src0 = g * 4 + (q >> 1), src1 = src0 + 2;      // shuffle sources of the C -> A fragment conversion
-    const bool odd = q & 1;
+    const int s_row = (g >> 1) + 4 * (g & 1);                // data row (within an 8-row group) behind S-stage column g
     double* pm_s = scratch + (size_t)warp * 2 * 8 * 32;      // [8][32]
     double* u_s = pm_s + 8 * 32;                             // [8][32]
 
@@ -116,11 +119,11 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
         for (int rb = 0; rb < n_blocks; ++rb, ++gb) {
             const int stage = gb % ST;
             // c_n (and h_n) of the block's four row groups: issued before the barrier wait
-            double2 cwv[4], hv[4];
+            double2 cwv[4], hv[4];                           // .x: row q, .y: row q + 4 of the group
 #pragma unroll
             for (int r8 = 0; r8 < 4; ++r8) {
-                cwv[r8] = *reinterpret_cast<const double2*>(cw_row + rb * NB + r8 * 8);
-                if (WITH_H) hv[r8] = *reinterpret_cast<const double2*>(h_row + rb * NB + r8 * 8);
+                cwv[r8] = make_double2(cw_row[rb * NB + r8 * 8], cw_row[rb * NB + r8 * 8 + 4]);
+                if (WITH_H) hv[r8] = make_double2(h_row[rb * NB + r8 * 8], h_row[rb * NB + r8 * 8 + 4]);
             }
             if (warp == 0 && lane == 0 && gb >= 1 && gb - 1 + ST < n_total) {
                 // refill the stage of block gb-1 once every warp has released it
@@ -128,6 +131,17 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
                 mbar_wait(&x_empty[ns], (uint32_t)(((gb - 1) / ST) & 1));
                 mbar_expect_tx(&x_full[ns], stage_bytes);
                 tma_bulk_g2s(xs_ring + (size_t)ns * NB * xs, x + (size_t)(nb % n_blocks) * NB * xs, stage_bytes, &x_full[ns]);
+            }
+            if (KIND == kPassMomFp && rb == n_blocks - 3) {
+                // the G^-1 of the warp's 8 chains is read right after this pass (u = G^-1 PM): pull it into L2 now so
+                // that the dependent loads of that phase do not wait for HBM
+                const int lines = (D * D * 8 + 127) / 128;
+                for (int j = 0; j < 8; ++j) {
+                    const int slot_j = __shfl_sync(kFull, slot, j * 4);
+                    if (slot_j < 0) continue;
+                    const char* gp = reinterpret_cast<const char*>(S.invg + slot_j * P.slot_invg + (size_t)(chain0 + j) * D * D);
+                    for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + (size_t)l * 128));
+                }
             }
             __syncwarp();
             mbar_wait(&x_full[stage], (uint32_t)((gb / ST) & 1));
@@ -138,7 +152,7 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
 #pragma unroll
             for (int r8 = 0; r8 < 4; ++r8) sv[r8][0] = sv[r8][1] = 0.0;
             if (WITH_U) {
-                const double* xrow = xb + (size_t)g * xs + q;
+                const double* xrow = xb + (size_t)s_row * xs + q;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     if (ks < k_steps) {
@@ -147,24 +161,18 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
                     }
                 }
             }
-            // R = c .* S .* S (and / or c .* h); C fragment (chain g; rows 2q, 2q+1) -> A fragments (chain g; row q) of
-            // the two 4-row k-steps of every group
+            // R = c .* S .* S (and / or c .* h): this lane's C-fragment values (chain g; rows q, q + 4) ARE its A
+            // fragments (chain g; k = q) of the two 4-row k-steps of every group
             double aq[4][2], at[4][2];
 #pragma unroll
             for (int r8 = 0; r8 < 4; ++r8) {
                 if (KIND != kPassTrace) {
-                    const double r0 = cwv[r8].x * sv[r8][0] * sv[r8][0], r1 = cwv[r8].y * sv[r8][1] * sv[r8][1];
-                    const double e0 = __shfl_sync(kFull, r0, src0), o0 = __shfl_sync(kFull, r1, src0);
-                    const double e1 = __shfl_sync(kFull, r0, src1), o1 = __shfl_sync(kFull, r1, src1);
-                    aq[r8][0] = odd ? o0 : e0;
-                    aq[r8][1] = odd ? o1 : e1;
+                    aq[r8][0] = cwv[r8].x * sv[r8][0] * sv[r8][0];
+                    aq[r8][1] = cwv[r8].y * sv[r8][1] * sv[r8][1];
                 }
                 if (WITH_H) {
-                    const double t0 = cwv[r8].x * hv[r8].x, t1 = cwv[r8].y * hv[r8].y;
-                    const double e0 = __shfl_sync(kFull, t0, src0), o0 = __shfl_sync(kFull, t1, src0);
-                    const double e1 = __shfl_sync(kFull, t0, src1), o1 = __shfl_sync(kFull, t1, src1);
-                    at[r8][0] = odd ? o0 : e0;
-                    at[r8][1] = odd ? o1 : e1;
+                    at[r8][0] = cwv[r8].x * hv[r8].x;
+                    at[r8][1] = cwv[r8].y * hv[r8].y;
                 }
             }
             // stage 2: Q += R . X over the block's eight 4-row k-steps; d-tiles are the independent chains

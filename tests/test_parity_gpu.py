@@ -176,6 +176,32 @@ def test_large_regime_kernels_on_a_small_batch(pkg, golden, partials, metric):
     assert np.array_equal(tr_s["theta_steps"], tr_b["theta_steps"][:c_fx], equal_nan=True)
 
 
+@pytest.mark.parametrize("sampler", ["rmhmc_i8", "rmhmc_dmma", "hmc_fused"])
+def test_repeated_runs_are_bit_identical_at_bench_scale(pkg, sampler):
+    """compute-sanitizer is closed on this pool (profiles/r02/racecheck_refused.txt); the substitute for its racecheck on
+    the mbarrier / TMA rings (k_i8_gemm, k_i8_vslice_mma*, k_pass, k_hmc_rounds, k_metric): a benchmark-sized Philox run
+    repeated on a fresh handle must reproduce every chain bit for bit -- a race on a stage of a ring or on a shared
+    scratch tile shows up as a difference in some of the 20 517 chains."""
+    xx, t = pkg.datasets.shaped("german")
+    outs = []
+    for rep in range(2):
+        data = pkg.LogisticData(xx, t, metric="dmma" if sampler == "rmhmc_dmma" else "i8")
+        if sampler == "hmc_fused":
+            s = pkg.HMCSampler(data, BENCH_SCALE_CHAINS, 20, 0.05)
+            rounds = 45
+        else:
+            s = pkg.RMHMCSampler(data, BENCH_SCALE_CHAINS, 6, 0.5, 6)
+            rounds = 9
+        s.set_philox(4242, 0)
+        s.advance(rounds)
+        st = s.state()
+        outs.append((st["theta"].copy(), st["iters"].copy(), st["accepted"].copy(), st["leapfrogs"].copy()))
+        data.close()
+    assert outs[0][1].sum() > 0 and outs[0][3].sum() > 0
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
 def test_tape_window_is_enforced(pkg, golden):
     """A host tape covers a window of iterations; running past it (or starting before it) is an error, not a read
     beyond the tape buffers."""
