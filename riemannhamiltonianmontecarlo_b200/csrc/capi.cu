@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "chain_kernels.cuh"
+#include "chain_tpc.cuh"
 #include "common.cuh"
 #include "ess_kernel.cuh"
 #include "hmc_kernels.cuh"
@@ -698,6 +699,8 @@ int set_chain_smem_attrs(rmhmc_handle* h) {
     CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
     CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<32, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
     CUDA_TRY(h, cudaFuncSetAttribute(k_seam_factor<32, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, seam));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_solve_tpc<kTpcTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpc_smem_bytes(h->dim)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_chain_factor_tpc<kTpcTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpc_smem_bytes(h->dim)));
     return RMHMC_OK;
 }
 
@@ -743,11 +746,26 @@ int launch_mf_mom_iter(rmhmc_handle* h, int is_last) {
     return RMHMC_OK;
 }
 
+// thread-per-chain Cholesky stages (chain_tpc.cuh): an alternative formulation, measured and NOT the default.  3x fewer
+// warp instructions than the warp-per-chain kernels, but the 32 packed metrics of a warp fill 105 KB of shared memory, so
+// only two warps are resident per SM and the kernel is bound by the latency of a single warp per scheduler: solve
+// 0.275 ms (warp per chain: 0.272 ms), factor 1.25 ms (0.55 ms) at 65 536 German-shaped chains
+// (tests/native/tpc_bench.cu, profiles/r02/tpc_bench.log).  RMHMC_CHAIN_TPC=1 / RMHMC_FACTOR_TPC=1 switch them on.
+bool use_tpc(const rmhmc_handle* h) {
+    static const int forced = [] { const char* e = getenv("RMHMC_CHAIN_TPC"); return e ? atoi(e) : 0; }();
+    return forced != 0 && !is_big(h);
+}
+bool use_tpc_factor(const rmhmc_handle* h) {
+    static const int forced = [] { const char* e = getenv("RMHMC_FACTOR_TPC"); return e ? atoi(e) : 0; }();
+    return forced != 0 && !is_big(h);
+}
+
 int launch_factor(rmhmc_handle* h, int init) {
     const unsigned C = (unsigned)h->n_chains;
     {
         Bracket b(h, 4);
         if (is_big(h)) k_chain_factor_big<<<C, kBigThreads, big_mat_smem_bytes(h->dim, 2), h->stream>>>(h->P, h->S, init);
+        else if (use_tpc_factor(h)) k_chain_factor_tpc<kTpcTile><<<(C + 31) / 32, 32, tpc_smem_bytes(h->dim), h->stream>>>(h->P, h->S, init);
         else switch (chain_order(h->dim)) {
             case 8: k_chain_factor<8><<<C, 32, factor_smem_bytes(8), h->stream>>>(h->P, h->S, init); break;
             case 16: k_chain_factor<16><<<C, 32, factor_smem_bytes(16), h->stream>>>(h->P, h->S, init); break;
@@ -765,6 +783,7 @@ int launch_solve(rmhmc_handle* h, int is_last) {
     {
         Bracket b(h, 4);
         if (is_big(h)) k_chain_solve_big<<<C, kBigThreads, big_mat_smem_bytes(h->dim, 1), h->stream>>>(h->P, h->S, is_last);
+        else if (use_tpc(h)) k_chain_solve_tpc<kTpcTile><<<(C + 31) / 32, 32, tpc_smem_bytes(h->dim), h->stream>>>(h->P, h->S, is_last);
         else switch (chain_order(h->dim)) {
             case 8: k_chain_solve<8><<<C, 32, solve_smem_bytes(8), h->stream>>>(h->P, h->S, is_last); break;
             case 16: k_chain_solve<16><<<C, 32, solve_smem_bytes(16), h->stream>>>(h->P, h->S, is_last); break;
@@ -844,13 +863,10 @@ template <int KIND>
 int launch_pass(rmhmc_handle* h) {
     // 64 chains per CTA; 16 when that grid would leave SMs idle (BASELINE.json configs[1]: 4096 chains)
     // (the fused momentum fixed point has its own few-chains formulation, k_mom_fp: mf_momentum_fixed_point)
-    const bool small = KIND != kPassMomFp && few_chains(h, (int64_t)148 * 2 * kPassWarps * 8);
+    const bool small = few_chains(h, (int64_t)148 * 2 * kPassWarps * 8);
     const int warps = small ? kPassWarpsSmall : kPassWarps;
     const size_t smem = pass_smem_bytes(h->xs, warps);
-    void (*kern)(EngineParams, ChainArrays, const double*, int) = k_pass<KIND, kPassWarps>;
-    if constexpr (KIND != kPassMomFp) {
-        if (small) kern = k_pass<KIND, kPassWarpsSmall>;
-    }
+    void (*kern)(EngineParams, ChainArrays, const double*, int) = small ? k_pass<KIND, kPassWarpsSmall> : k_pass<KIND, kPassWarps>;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         Bracket b(h, KIND == kPassTrace || KIND == kPassPair ? 7 : 5);
@@ -869,7 +885,8 @@ int mf_momentum_fixed_point(rmhmc_handle* h) {
     // (momfp_kernel.cuh; shorter dependent chains, 0.08 vs 0.23 ms when 4096 chains leave most of the GPU idle)
     const bool fusable = !is_big(h) && !h->comm && h->P.n_fixed >= 2 && !h->P.student_t;      // Student-t: per-iterate kernels
     const bool few = few_chains(h, (int64_t)148 * 2 * kPassWarps * 8);
-    if (fusable && (h->fuse_momentum == 1 && !few)) return launch_pass<kPassMomFp>(h);
+    static const int small_pass = [] { const char* e = getenv("RMHMC_MOMFP_SMALL_PASS"); return e ? atoi(e) : 0; }();
+    if (fusable && (h->fuse_momentum == 1 && (!few || small_pass))) return launch_pass<kPassMomFp>(h);
     if (fusable && (h->fuse_momentum == 2 || (h->fuse_momentum == 1 && few))) {
         const size_t smem = momfp_smem_bytes(h->xs);
         CUDA_TRY(h, cudaFuncSetAttribute(k_mom_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

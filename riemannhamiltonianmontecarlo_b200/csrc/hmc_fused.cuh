@@ -177,12 +177,26 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
             for (int r8 = 0; r8 < 4; ++r8) sv[r8][0] = sv[r8][1] = 0.0;
             {
                 const double* xrow = xb + (size_t)s_row * xs + q;
+                auto s_stage = [&](auto ksc) {                       // k-step count as a compile-time constant (pass_kernel.cuh)
+                    constexpr int KS = decltype(ksc)::value;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    if (ks < k_steps) {
+                    for (int ks = 0; ks < KS; ++ks) {
+                        double b[4];
 #pragma unroll
-                        for (int r8 = 0; r8 < 4; ++r8) dmma884(sv[r8][0], sv[r8][1], ua[ks], xrow[(size_t)(r8 * 8) * xs + ks * 4]);
+                        for (int r8 = 0; r8 < 4; ++r8) b[r8] = xrow[(size_t)(r8 * 8) * xs + ks * 4];
+#pragma unroll
+                        for (int r8 = 0; r8 < 4; ++r8) dmma884(sv[r8][0], sv[r8][1], ua[ks], b[r8]);
                     }
+                };
+                switch (k_steps) {
+                    case 1: s_stage(std::integral_constant<int, 1>{}); break;
+                    case 2: s_stage(std::integral_constant<int, 2>{}); break;
+                    case 3: s_stage(std::integral_constant<int, 3>{}); break;
+                    case 4: s_stage(std::integral_constant<int, 4>{}); break;
+                    case 5: s_stage(std::integral_constant<int, 5>{}); break;
+                    case 6: s_stage(std::integral_constant<int, 6>{}); break;
+                    case 7: s_stage(std::integral_constant<int, 7>{}); break;
+                    default: s_stage(std::integral_constant<int, 8>{}); break;
                 }
             }
             double aq[4][2];
@@ -207,20 +221,30 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
                 aq[r8][0] = rr[0];
                 aq[r8][1] = rr[1];
             }
+            // d-tile count as a compile-time constant; columns >= D of the last tile read what follows the row's D
+            // entries (inside shared memory: the ring is followed by the per-warp scratch) and only reach accumulator
+            // columns that are never used (pass_kernel.cuh)
+            auto q_stage = [&](auto dtc) {
+                constexpr int DT = decltype(dtc)::value;
+                const double* xq = xb + (size_t)q * xs + g;
 #pragma unroll
-            for (int r8 = 0; r8 < 4; ++r8) {
+                for (int r8 = 0; r8 < 4; ++r8) {
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const double* xr = xb + (size_t)(r8 * 8 + kk * 4 + q) * xs;
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const double* xr = xq + (size_t)(r8 * 8 + kk * 4) * xs;
+                        double b[DT];
 #pragma unroll
-                    for (int dt = 0; dt < 4; ++dt) {
-                        if (dt < d_tiles) {
-                            const int dcol = dt * 8 + g;
-                            const double b = dcol < D ? xr[dcol] : 0.0;
-                            dmma884(acc[dt][0], acc[dt][1], aq[r8][kk], b);
-                        }
+                        for (int dt = 0; dt < DT; ++dt) b[dt] = xr[dt * 8];
+#pragma unroll
+                        for (int dt = 0; dt < DT; ++dt) dmma884(acc[dt][0], acc[dt][1], aq[r8][kk], b[dt]);
                     }
                 }
+            };
+            switch (d_tiles) {
+                case 1: q_stage(std::integral_constant<int, 1>{}); break;
+                case 2: q_stage(std::integral_constant<int, 2>{}); break;
+                case 3: q_stage(std::integral_constant<int, 3>{}); break;
+                default: q_stage(std::integral_constant<int, 4>{}); break;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_empty[stage]);

@@ -15,6 +15,8 @@
 // (k_metric MODE 3/4, k_mom_fp: F-warps -> shared R tile -> G-warps) was issue-bound on its barrier traffic
 // (ncu: 2.06 G instructions, 3.0 ms for the six passes of one momentum half-step at 65 536 chains).
 #pragma once
+#include <type_traits>
+
 #include "chain_kernels.cuh"
 #include "common.cuh"
 
@@ -153,12 +155,26 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
             for (int r8 = 0; r8 < 4; ++r8) sv[r8][0] = sv[r8][1] = 0.0;
             if (WITH_U) {
                 const double* xrow = xb + (size_t)s_row * xs + q;
+                auto s_stage = [&](auto ksc) {                       // k-step count as a compile-time constant, as in q_stage
+                    constexpr int KS = decltype(ksc)::value;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    if (ks < k_steps) {
+                    for (int ks = 0; ks < KS; ++ks) {
+                        double b[4];
 #pragma unroll
-                        for (int r8 = 0; r8 < 4; ++r8) dmma884(sv[r8][0], sv[r8][1], ua[ks], xrow[(size_t)(r8 * 8) * xs + ks * 4]);
+                        for (int r8 = 0; r8 < 4; ++r8) b[r8] = xrow[(size_t)(r8 * 8) * xs + ks * 4];
+#pragma unroll
+                        for (int r8 = 0; r8 < 4; ++r8) dmma884(sv[r8][0], sv[r8][1], ua[ks], b[r8]);
                     }
+                };
+                switch (k_steps) {
+                    case 1: s_stage(std::integral_constant<int, 1>{}); break;
+                    case 2: s_stage(std::integral_constant<int, 2>{}); break;
+                    case 3: s_stage(std::integral_constant<int, 3>{}); break;
+                    case 4: s_stage(std::integral_constant<int, 4>{}); break;
+                    case 5: s_stage(std::integral_constant<int, 5>{}); break;
+                    case 6: s_stage(std::integral_constant<int, 6>{}); break;
+                    case 7: s_stage(std::integral_constant<int, 7>{}); break;
+                    default: s_stage(std::integral_constant<int, 8>{}); break;
                 }
             }
             // R = c .* S .* S (and / or c .* h): this lane's C-fragment values (chain g; rows q, q + 4) ARE its A
@@ -175,23 +191,37 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
                     at[r8][1] = cwv[r8].y * hv[r8].y;
                 }
             }
-            // stage 2: Q += R . X over the block's eight 4-row k-steps; d-tiles are the independent chains
+            // stage 2: Q += R . X over the block's eight 4-row k-steps; d-tiles are the independent chains.  The tile
+            // count is a compile-time constant inside q_stage (one warp-uniform switch per block): the B fragments of a
+            // k-step are loaded together and nothing but DMMAs sits between them.  Columns >= D of the last tile read
+            // whatever follows the row's D entries (padding, the label, the next row; the ring is followed by the
+            // scratch area, so the reads stay inside shared memory): column n of the product depends on column n of B
+            // alone and the accumulator columns >= D are never used.
+            auto q_stage = [&](auto dtc) {
+                constexpr int DT = decltype(dtc)::value;
+                const double* xq = xb + (size_t)q * xs + g;
 #pragma unroll
-            for (int r8 = 0; r8 < 4; ++r8) {
+                for (int r8 = 0; r8 < 4; ++r8) {
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const double* xr = xb + (size_t)(r8 * 8 + kk * 4 + q) * xs;
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const double* xr = xq + (size_t)(r8 * 8 + kk * 4) * xs;
+                        double b[DT];
 #pragma unroll
-                    for (int dt = 0; dt < 4; ++dt) {
-                        if (dt < d_tiles) {
-                            const int dcol = dt * 8 + g;
-                            const double b = dcol < D ? xr[dcol] : 0.0;
-                            if (KIND == kPassTrace) dmma884(acc[dt][0], acc[dt][1], at[r8][kk], b);
-                            else dmma884(acc[dt][0], acc[dt][1], aq[r8][kk], b);
-                            if (KIND == kPassPair) dmma884(acc2[dt][0], acc2[dt][1], at[r8][kk], b);
+                        for (int dt = 0; dt < DT; ++dt) b[dt] = xr[dt * 8];
+#pragma unroll
+                        for (int dt = 0; dt < DT; ++dt) {
+                            if (KIND == kPassTrace) dmma884(acc[dt][0], acc[dt][1], at[r8][kk], b[dt]);
+                            else dmma884(acc[dt][0], acc[dt][1], aq[r8][kk], b[dt]);
+                            if (KIND == kPassPair) dmma884(acc2[dt][0], acc2[dt][1], at[r8][kk], b[dt]);
                         }
                     }
                 }
+            };
+            switch (d_tiles) {
+                case 1: q_stage(std::integral_constant<int, 1>{}); break;
+                case 2: q_stage(std::integral_constant<int, 2>{}); break;
+                case 3: q_stage(std::integral_constant<int, 3>{}); break;
+                default: q_stage(std::integral_constant<int, 4>{}); break;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_empty[stage]);

@@ -194,3 +194,13 @@ def test_dataset_dispatch_and_ripley_cubic_basis(tmp_path):
         datasets.load_dataset("mnist", str(tmp_path))
     from riemannhamiltonianmontecarlo_b200 import harness
     assert set(harness.HMC_STEP_SIZES) == set(datasets.DATASETS)
+
+
+def test_thread_per_chain_linear_algebra_core(tmp_path):
+    """csrc/tpc_core.h (packed in-place Cholesky / solve / inverse, one thread per chain) compiled for the host and
+    checked against dense arithmetic; the two-column factorisation must be bit-identical to the one-column one."""
+    exe = tmp_path / "tpc_host_test"
+    src = os.path.join(ROOT, "tests", "native", "tpc_host_test.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-o", str(exe), src], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout[-2000:]
