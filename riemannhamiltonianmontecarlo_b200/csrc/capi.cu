@@ -859,11 +859,15 @@ int build_partials(rmhmc_handle* h, int flip) {
 // ---- matrix-free partials (mf_kernels.cuh)
 // F iterates of the implicit momentum half-step (rmhmc.py:102-110): quadratic forms by a pass over the data,
 // then the per-chain update and u = G^-1 PM for the next pass
+constexpr int64_t kPassSmallBelow = (int64_t)148 * 6 * kPassWarpsSmall * 8;      // 14 208 chains
+constexpr int64_t kMomFpBelow = 1024;
 template <int KIND>
 int launch_pass(rmhmc_handle* h) {
-    // 64 chains per CTA; 16 when that grid would leave SMs idle (BASELINE.json configs[1]: 4096 chains)
-    // (the fused momentum fixed point has its own few-chains formulation, k_mom_fp: mf_momentum_fixed_point)
-    const bool small = few_chains(h, (int64_t)148 * 2 * kPassWarps * 8);
+    // 64 chains per CTA, or 16 (kPassWarpsSmall) while the 16-chain CTAs are all resident at once (6 per SM): one
+    // warp owns 8 chains for the whole kernel either way -- the two tilings are bit-identical -- and with few chains the
+    // finer tiles balance the SMs (quad pass, German-shaped: 12 288 chains 0.45 vs 0.57 ms, 16 384 chains 0.76 vs 0.58 ms;
+    // profiles/r02/regimes_small_large.txt)
+    const bool small = few_chains(h, kPassSmallBelow);
     const int warps = small ? kPassWarpsSmall : kPassWarps;
     const size_t smem = pass_smem_bytes(h->xs, warps);
     void (*kern)(EngineParams, ChainArrays, const double*, int) = small ? k_pass<KIND, kPassWarpsSmall> : k_pass<KIND, kPassWarps>;
@@ -884,9 +888,10 @@ int mf_momentum_fixed_point(rmhmc_handle* h) {
     // (pass_kernel.cuh; 2.58 vs 3.02 ms at 65 536 German-shaped chains) or 12 cooperating warps per 32 chains
     // (momfp_kernel.cuh; shorter dependent chains, 0.08 vs 0.23 ms when 4096 chains leave most of the GPU idle)
     const bool fusable = !is_big(h) && !h->comm && h->P.n_fixed >= 2 && !h->P.student_t;      // Student-t: per-iterate kernels
-    const bool few = few_chains(h, (int64_t)148 * 2 * kPassWarps * 8);
-    static const int small_pass = [] { const char* e = getenv("RMHMC_MOMFP_SMALL_PASS"); return e ? atoi(e) : 0; }();
-    if (fusable && (h->fuse_momentum == 1 && (!few || small_pass))) return launch_pass<kPassMomFp>(h);
+    // k_mom_fp only where latency counts (a handful of chains: the single-chain drop-in, the seam tests) or when the
+    // SMALL regime is pinned; 8192 chains: k_pass<MOMFP, 2 warps> 0.38 ms, k_mom_fp 0.44 ms
+    const bool few = h->launch_regime == RMHMC_REGIME_AUTO ? h->n_chains < kMomFpBelow : few_chains(h, 0);
+    if (fusable && (h->fuse_momentum == 1 && !few)) return launch_pass<kPassMomFp>(h);
     if (fusable && (h->fuse_momentum == 2 || (h->fuse_momentum == 1 && few))) {
         const size_t smem = momfp_smem_bytes(h->xs);
         CUDA_TRY(h, cudaFuncSetAttribute(k_mom_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1267,7 +1272,7 @@ int hmc_rounds(rmhmc_handle* h, int64_t n_rounds) {
         }
         return RMHMC_OK;
     }
-    const bool small = few_chains(h, (int64_t)148 * 2 * kHfWarps * 8);
+    const bool small = few_chains(h, kPassSmallBelow);
     const int warps = small ? kPassWarpsSmall : kHfWarps;
     const size_t smem = hmc_fused_smem_bytes(h->xs, warps);
     void (*kern)(EngineParams, ChainArrays, const double*, int, int, int) = small ? k_hmc_rounds<kPassWarpsSmall> : k_hmc_rounds<kHfWarps>;

@@ -176,6 +176,31 @@ def test_large_regime_kernels_on_a_small_batch(pkg, golden, partials, metric):
     assert np.array_equal(tr_s["theta_steps"], tr_b["theta_steps"][:c_fx], equal_nan=True)
 
 
+MID_SCALE_CHAINS = 2048 + 37          # 1024 <= chains < 14 208: 16-chain pass tiles (k_pass<*, 2>), incl. the momentum fixed point
+
+
+@pytest.mark.parametrize("metric", METRIC)
+@pytest.mark.parametrize("partials", PARTIALS)
+def test_mid_scale_batch_matches_reference(pkg, golden, partials, metric):
+    """Between the handful-of-chains kernels (k_mom_fp) and the throughput tiles sits the regime a strong-scaled
+    configs[3] runs in on 8 GPUs (8192 chains per GPU): k_pass<MOMFP / PAIR, 2 warps>.  Replicas bit-identical, the
+    first follows the reference, and -- one warp owns 8 chains whatever the CTA size -- the trajectories equal the
+    LARGE-regime ones bit for bit."""
+    fx = golden("rmhmc_australian_shaped")
+    c_fx = fx["z"].shape[1]
+    tr, samples, st = _run_tape_fixture(pkg, fx, n_chains=MID_SCALE_CHAINS, partials=partials, metric=metric)
+    idx = np.arange(MID_SCALE_CHAINS) % c_fx
+    for key in ("theta_steps", "mom_end", "h_proposed", "flags"):
+        assert np.array_equal(tr[key], tr[key][idx], equal_nan=True), key
+    _assert_trace_matches_fixture(fx, tr, samples, st, chains=list(range(c_fx)) + [15, 16, 1023, 1024, MID_SCALE_CHAINS - 1])
+    if (partials, metric) != ("matrix_free", "i8"):
+        return                  # the FP64 builds split the data rows when their grid is small: summation order differs
+    tr_l, s_l, _ = _run_tape_fixture(pkg, fx, partials=partials, metric=metric, regime="large")
+    assert np.array_equal(s_l, samples[:c_fx])
+    assert np.array_equal(tr_l["theta_steps"], tr["theta_steps"][:c_fx], equal_nan=True)
+    assert np.array_equal(tr_l["h_proposed"], tr["h_proposed"][:c_fx])
+
+
 @pytest.mark.parametrize("sampler", ["rmhmc_i8", "rmhmc_dmma", "hmc_fused"])
 def test_repeated_runs_are_bit_identical_at_bench_scale(pkg, sampler):
     """compute-sanitizer is closed on this pool (profiles/r02/racecheck_refused.txt); the substitute for its racecheck on
