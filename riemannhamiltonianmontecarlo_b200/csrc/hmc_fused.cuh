@@ -90,9 +90,10 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
             }
     };
     load_slot(step == 0 ? cur : 1 - cur, step > 0);
-    const int s_row = (g >> 1) + 4 * (g & 1);                // data row (within an 8-row group) behind S-stage column g: this
-                                                             // lane's two f values belong to rows q and q + 4, the rows it
-                                                             // feeds to the gradient contraction -- no C -> A shuffle
+    const int q_hi = 4 + (q ^ 2);                            // bank-conflict-free row pairing, see pass_kernel.cuh
+    const int s_row = (g & 1) ? 4 + ((g >> 1) ^ 2) : (g >> 1);   // data row (within an 8-row group) behind S-stage column g: this
+                                                                 // lane's two f values belong to rows q and q_hi, the rows it
+                                                                 // feeds to the gradient contraction -- no C -> A shuffle
     double* wsm = scratch + (size_t)warp * 8 * 32;
     const double half_log = 0.5 * log(2.0 * 3.14159265358979323846 * alpha);
     const int k_steps = (D + 3) / 4, d_tiles = (D + 7) / 8;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
                     const double e = fast_exp_nonpos(-fabs(fv), exp_tab);
                     const double qq = fast_rcp_1to2(1.0 + e);
                     const double pn = fv >= 0.0 ? qq : e * qq;
-                    const int rloc = r8 * 8 + q + 4 * j;
+                    const int rloc = r8 * 8 + (j ? q_hi : q);
                     const double t = xb[(size_t)rloc * xs + tcol];
                     const bool ovf = fv > 709.782712893384;      // the reference's exp(f) overflows: NaN gradient, -inf log-likelihood
                     rr[j] = ovf ? __longlong_as_double(0x7ff8000000000000LL) : t - pn;                 // hmc.py:53,61
@@ -226,12 +227,12 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
             // columns that are never used (pass_kernel.cuh)
             auto q_stage = [&](auto dtc) {
                 constexpr int DT = decltype(dtc)::value;
-                const double* xq = xb + (size_t)q * xs + g;
+                const double* xq[2] = {xb + (size_t)q * xs + g, xb + (size_t)q_hi * xs + g};
 #pragma unroll
                 for (int r8 = 0; r8 < 4; ++r8) {
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
-                        const double* xr = xq + (size_t)(r8 * 8 + kk * 4) * xs;
+                        const double* xr = xq[kk] + (size_t)(r8 * 8) * xs;
                         double b[DT];
 #pragma unroll
                         for (int dt = 0; dt < DT; ++dt) b[dt] = xr[dt * 8];

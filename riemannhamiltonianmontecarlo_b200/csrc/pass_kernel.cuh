@@ -9,7 +9,7 @@
 // both contractions of a pass itself:
 //   S[8 chains x 8 rows] = U . X^T (K = D; U fragments live in registers), R = c .* S .* S (or c .* h),
 //   R's C-fragment used directly as A-fragment (the S stage's columns are fed the rows in the order that makes the two
-//   layouts coincide),  Q[8 chains x D] += R . X (K = 8 rows)
+//   layouts coincide and keeps both stages free of bank conflicts),  Q[8 chains x D] += R . X (K = 8 rows)
 // so there is no hand-off between warps: the only shared object is the X row-block ring (bulk TMA + full/empty
 // mbarriers, one wait and one arrive per warp per 32 rows).  The warp-specialised formulation these replace
 // (k_metric MODE 3/4, k_mom_fp: F-warps -> shared R tile -> G-warps) was issue-bound on its barrier traffic
@@ -80,11 +80,17 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
     }
     const bool active = slot >= 0;
     // rows beyond n_chains exist in the c_n / leverage buffers (chain padding), so the loads below stay in bounds
-    // DMMA column n of the S stage carries data row (n >> 1) + 4 (n & 1) of the 8-row group: this lane's two S values
-    // (columns 2q, 2q + 1) then belong to rows q and q + 4, which are exactly the rows it supplies as A fragments to
-    // the two 4-row k-steps of the Q stage -- no C -> A shuffle; the sums run over the same rows in the same order
-    const double* cw_row = S.cw + (slot > 0 ? P.slot_cw : 0) + (size_t)c * P.n_rows_pad + q;
-    const double* h_row = WITH_H ? S.hbuf + (size_t)c * P.n_rows_pad + q : nullptr;
+    // The S stage's DMMA columns are fed the data rows of an 8-row group in an order that makes this lane's two S values
+    // (columns 2q, 2q + 1) belong to exactly the two rows it supplies as A fragments to the two 4-row k-steps of the Q
+    // stage -- no C -> A shuffle.
+    // Which rows: column 2q carries row q, column 2q + 1 row q_hi = 4 + (q ^ 2).  With the row stride 4 * odd, rows r and
+    // r + 4 of a group share their shared-memory banks; this pairing keeps the four rows of every half-warp distinct
+    // mod 4 in BOTH stages (S stage: lanes g = 0..3 read rows 0, 6, 1, 7, lanes g = 4..7 rows 2, 4, 3, 5; Q stage:
+    // lanes q = 0..3 read rows 0..3, then 6, 7, 4, 5), so neither stage has bank conflicts (the plain q, q + 4 pairing
+    // cost the S stage a 2-way conflict on every load: ncu r02 v8, 92 M excess wavefronts per launch)
+    const int q_hi = 4 + (q ^ 2);
+    const double* cw_row = S.cw + (slot > 0 ? P.slot_cw : 0) + (size_t)c * P.n_rows_pad;
+    const double* h_row = WITH_H ? S.hbuf + (size_t)c * P.n_rows_pad : nullptr;
     double ua[8];                  // U A-fragments: u[c][4 ks + q], zero beyond D (the staged label column meets a zero)
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
     }
     const int k_steps = (D + 3) / 4;
     const int d_tiles = (D + 7) / 8;
-    const int s_row = (g >> 1) + 4 * (g & 1);                // data row (within an 8-row group) behind S-stage column g
+    const int s_row = (g & 1) ? 4 + ((g >> 1) ^ 2) : (g >> 1);   // data row (within an 8-row group) behind S-stage column g
     double* pm_s = scratch + (size_t)warp * 2 * 8 * 32;      // [8][32]
     double* u_s = pm_s + 8 * 32;                             // [8][32]
 
@@ -121,11 +127,11 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
         for (int rb = 0; rb < n_blocks; ++rb, ++gb) {
             const int stage = gb % ST;
             // c_n (and h_n) of the block's four row groups: issued before the barrier wait
-            double2 cwv[4], hv[4];                           // .x: row q, .y: row q + 4 of the group
+            double2 cwv[4], hv[4];                           // .x: row q, .y: row q_hi of the group
 #pragma unroll
             for (int r8 = 0; r8 < 4; ++r8) {
-                cwv[r8] = make_double2(cw_row[rb * NB + r8 * 8], cw_row[rb * NB + r8 * 8 + 4]);
-                if (WITH_H) hv[r8] = make_double2(h_row[rb * NB + r8 * 8], h_row[rb * NB + r8 * 8 + 4]);
+                cwv[r8] = make_double2(cw_row[rb * NB + r8 * 8 + q], cw_row[rb * NB + r8 * 8 + q_hi]);
+                if (WITH_H) hv[r8] = make_double2(h_row[rb * NB + r8 * 8 + q], h_row[rb * NB + r8 * 8 + q_hi]);
             }
             if (warp == 0 && lane == 0 && gb >= 1 && gb - 1 + ST < n_total) {
                 // refill the stage of block gb-1 once every warp has released it
@@ -199,12 +205,12 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
             // alone and the accumulator columns >= D are never used.
             auto q_stage = [&](auto dtc) {
                 constexpr int DT = decltype(dtc)::value;
-                const double* xq = xb + (size_t)q * xs + g;
+                const double* xq[2] = {xb + (size_t)q * xs + g, xb + (size_t)q_hi * xs + g};
 #pragma unroll
                 for (int r8 = 0; r8 < 4; ++r8) {
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
-                        const double* xr = xq + (size_t)(r8 * 8 + kk * 4) * xs;
+                        const double* xr = xq[kk] + (size_t)(r8 * 8) * xs;
                         double b[DT];
 #pragma unroll
                         for (int dt = 0; dt < DT; ++dt) b[dt] = xr[dt * 8];
@@ -259,6 +265,7 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
                 double y0 = 0.0, y1 = 0.0;
                 const double* xv = pm_s + j * 32;
                 if (lane < D) {
+                    // (issuing all D loads of the column before the first FMA was measured slower: 8192 chains 0.39 -> 0.47 ms)
                     const double* col = S.invg + slot_j * P.slot_invg + (size_t)cj * D * D + lane;
                     int b = 0;
 #pragma unroll 4
