@@ -421,22 +421,24 @@ __global__ void __launch_bounds__(kI8VsThreads) k_i8_vslice(I8VsArgs a) {
 // 8 (chain, row) pairs of each lane, digits through a warp-private shared-memory transpose so that the planes are
 // written as 16-byte row runs.  One warp = 32 chains x 16 rows per step; no CTA-wide synchronisation.
 constexpr int kI8VmWarps = 8;
-template <int S, int KS>
-__global__ void __launch_bounds__(kI8VmWarps * 32, 2) k_i8_vslice_mma(I8VsArgs a) {
+// MT = m-tiles of 8 chains per warp: 4 (32 chains per CTA row, 128 registers, 16 warps per SM) or 2 (16 chains, Theta
+// fragments and logistic temporaries halve: 24 warps per SM; every X fragment then feeds 2 instead of 4 DMMAs)
+template <int S, int KS, int MT>
+__global__ void __launch_bounds__(kI8VmWarps * 32, MT == 4 ? 2 : 3) k_i8_vslice_mma(I8VsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* exp_tab = reinterpret_cast<double*>(smem_raw);                                   // [256]
-    unsigned char* out_all = smem_raw + 256 * 8;                                             // [warps][S][32][16]
+    unsigned char* out_all = smem_raw + 256 * 8;                                             // [warps][S][8 MT][16]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-    const int chain0 = blockIdx.x * 32;
+    const int chain0 = blockIdx.x * (MT * 8);
     const int xs = a.xs;
     exp_tab[tid] = exp_table_entry(tid);
     __syncthreads();
-    unsigned char* out_w = out_all + (size_t)warp * S * 32 * 16;
+    unsigned char* out_w = out_all + (size_t)warp * S * (MT * 8) * 16;
 
     // Theta fragments: a[m][ks] = theta[chain0 + 8 m + g][4 ks + q]
-    double th[4][KS];
+    double th[MT][KS];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < MT; ++m) {
         const int c = chain0 + m * 8 + g;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
@@ -466,15 +468,15 @@ __global__ void __launch_bounds__(kI8VmWarps * 32, 2) k_i8_vslice_mma(I8VsArgs a
             // prefetch the next 8-row tile of this warp
             if (nt == 0) load_b(row0 + 8, bnext);
             else if (u + kI8VmWarps < u_end) load_b((u + kI8VmWarps) * 16, bnext);
-            double f[4][2];
+            double f[MT][2];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) f[m][0] = f[m][1] = 0.0;
+            for (int m = 0; m < MT; ++m) f[m][0] = f[m][1] = 0.0;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-                for (int m = 0; m < 4; ++m) dmma884(f[m][0], f[m][1], th[m][ks], b[ks]);
+                for (int m = 0; m < MT; ++m) dmma884(f[m][0], f[m][1], th[m][ks], b[ks]);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < MT / 2; ++half) {
                 double ev[4], qq[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) ev[i] = fast_exp_nonpos(-fabs(f[2 * half + (i >> 1)][i & 1]), exp_tab);
@@ -492,18 +494,18 @@ __global__ void __launch_bounds__(kI8VmWarps * 32, 2) k_i8_vslice_mma(I8VsArgs a
                         const int byte = S - 1 - s;
                         const unsigned bsel = byte & 3;
                         const unsigned pr = __byte_perm(byte < 4 ? lo0 : hi0, byte < 4 ? lo1 : hi1, bsel | ((4 + bsel) << 4));
-                        *reinterpret_cast<unsigned short*>(dst + (size_t)s * 32 * 16) = (unsigned short)((pr & 0xFFFFu) ^ 0x8080u);
+                        *reinterpret_cast<unsigned short*>(dst + (size_t)s * (MT * 8) * 16) = (unsigned short)((pr & 0xFFFFu) ^ 0x8080u);
                     }
                 }
             }
         }
         __syncwarp();
         const int c = chain0 + lane;
-        if (c < a.n_chains) {
+        if (lane < MT * 8 && c < a.n_chains) {
 #pragma unroll
             for (int s = 0; s < S; ++s)
                 *reinterpret_cast<uint4*>(a.a8 + (size_t)s * a.plane_stride + (size_t)c * a.kp + row0) =
-                    *reinterpret_cast<const uint4*>(out_w + ((size_t)s * 32 + lane) * 16);
+                    *reinterpret_cast<const uint4*>(out_w + ((size_t)s * (MT * 8) + lane) * 16);
         }
         __syncwarp();
     }
@@ -850,22 +852,31 @@ template <int S> inline int i8_chunks(int p2) { return (p2 + I8Shape<S>::NC - 1)
 inline size_t i8_vslice_smem(int xs) { return (size_t)2 * kI8VsRows * xs * 8 + 256 * 8 + 256 * 8; }
 
 #ifdef __CUDACC__
-inline size_t i8_vslice_mma_smem(int s) { return 256 * 8 + (size_t)kI8VmWarps * s * 32 * 16; }
+inline size_t i8_vslice_mma_smem(int s, int mt) { return 256 * 8 + (size_t)kI8VmWarps * s * (mt * 8) * 16; }
+// 16 chains per warp (MT = 2) unless RMHMC_VSLICE_MT=4
+inline int i8_vslice_mt() {
+    static const int mt = [] { const char* e = getenv("RMHMC_VSLICE_MT"); return e && atoi(e) == 4 ? 4 : 2; }();
+    return mt;
+}
 // position-iterate builds: DMMA variant (KS = k-steps of 4 parameters)
-template <int S>
-inline cudaError_t i8_launch_vslice_mma(const I8VsArgs& a, cudaStream_t stream) {
-    const unsigned gx = (unsigned)((a.n_chains + 31) / 32);
+template <int S, int MT>
+inline cudaError_t i8_launch_vslice_mma_mt(const I8VsArgs& a, cudaStream_t stream) {
+    const unsigned gx = (unsigned)((a.n_chains + MT * 8 - 1) / (MT * 8));
     unsigned gy = 1;
     const int units = a.n_rows_pad / 16;
     while (gx * gy < 148 * 4 && (int)gy * 2 * kI8VmWarps <= units) gy *= 2;      // few chains: split the rows too
     const dim3 grid(gx, gy);
-    const size_t smem = i8_vslice_mma_smem(S);
+    const size_t smem = i8_vslice_mma_smem(S, MT);
     const int ks = (a.dim + 3) / 4;
-    if (ks <= 2) k_i8_vslice_mma<S, 2><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
-    else if (ks <= 4) k_i8_vslice_mma<S, 4><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
-    else if (ks <= 7) k_i8_vslice_mma<S, 7><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
-    else k_i8_vslice_mma<S, 8><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
+    if (ks <= 2) k_i8_vslice_mma<S, 2, MT><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
+    else if (ks <= 4) k_i8_vslice_mma<S, 4, MT><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
+    else if (ks <= 7) k_i8_vslice_mma<S, 7, MT><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
+    else k_i8_vslice_mma<S, 8, MT><<<grid, kI8VmWarps * 32, smem, stream>>>(a);
     return cudaGetLastError();
+}
+template <int S>
+inline cudaError_t i8_launch_vslice_mma(const I8VsArgs& a, cudaStream_t stream) {
+    return i8_vslice_mt() == 4 ? i8_launch_vslice_mma_mt<S, 4>(a, stream) : i8_launch_vslice_mma_mt<S, 2>(a, stream);
 }
 template <int KS> inline size_t i8_vslice_mma_closing_smem(int s) {
     return (size_t)(256 + 256 + kI8VcWarps * 16 * ((KS + 1) / 2 * 8 + 1)) * 8 + (size_t)kI8VcWarps * s * 16 * 16;
