@@ -418,6 +418,8 @@ def gpu_main(args):
         "leverage_gemm": (2.0 * C * N * P2, "fp64"), "trace_pass": (2.0 * C * N * D * (3 if rm else 1), "fp64"),
         "i8_gemm": (2.0 * n_digit_products * C * N * P2, "i8"),
         "i8_vslice": (2.0 * C * N * (D + 20), "fp64"),      # f = X theta plus ~20 FP64 operations of the logistic terms and digits
+        # closing build: the same plus X^T (t - p) and ~14 FP64 operations of t - p, log(1 + e), c_n
+        "i8_vslice_closing": (2.0 * C * N * (2 * D + 34), "fp64"),
     }
     if args.sampler == "hmc":
         work["metric_closing"] = (4.0 * C * N * D, "fp64")          # k_metric<MODE 2>: f = X theta and X^T (t - p)
@@ -436,7 +438,8 @@ def gpu_main(args):
         "leverage_gemm": "leverage GEMM h = q . KR2(X)^T (k_i8_gemm in INT8 metric mode, else k_tbuild_pre on FP64 DMMA.8x8x4)",
         "trace_pass": "k_pass<PAIR|TRACE> (tr(G^-1 dG_d) and u^T dG_d u passes, FP64 DMMA.8x8x4)",
         "i8_gemm": "k_i8_gemm (G = V . KR2(X) as 15 exact INT8 digit GEMMs: tcgen05.mma.kind::i8, TMEM, tensor-map TMA)",
-        "i8_vslice": "k_i8_vslice_mma / k_i8_vslice (f = X theta, logistic terms, base-256 digits of v; FP64)",
+        "i8_vslice": "k_i8_vslice_mma (position iterates: f = X theta on DMMA.8x8x4, logistic terms, base-256 digits of v; FP64)",
+        "i8_vslice_closing": "k_i8_vslice_mma_closing (closing build: f, digits of v, X^T (t - p), log-likelihood, c_n; FP64)",
         "chain_turn": "k_hmc_rounds (64 leapfrog rounds per launch: f = X w, X^T (t - sigma(f)) on FP64 DMMA.8x8x4, chain state in registers)",
     }
     peaks = {"fp64": (dmma_peak, "TFLOP/s", "DMMA.8x8x4 issue peak measured live (blr_device_peaks)"),
@@ -466,7 +469,7 @@ def gpu_main(args):
         ("german", 65536, "metric_fp"): (13.44e6 + 117.75e6, "profiles/r01/ncu_v3_metric_fp_raw.csv"),
         ("german", 65536, "partials"): (539.19e6 + 1487.65e6, "profiles/r01/ncu_v2_tbuild_raw.csv"),
         ("german", 65536, "i8_gemm"): (337.59e6 + 144.97e6, "profiles/r02/ncu_r02_i8_gemm_metric_raw.csv"),
-        ("german", 65536, "quad_pass"): (5233.21e6 + 38.79e6, "profiles/r02/ncu_r02_mom_fixed_point_raw.csv"),
+        ("german", 65536, "quad_pass"): (5603.04e6 + 54.84e6, "profiles/r02/ncu_r02_final_mom_fixed_point_raw.csv"),
         ("german", 65536, "i8_vslice"): (25.08e6 + 286.99e6, "profiles/r02/ncu_r02_i8_vslice_iterate_raw.csv"),
         ("german", 65536, "chain_solve"): (212.91e6 + 11.90e6, "profiles/r02/ncu_r02_chain_solve_raw.csv"),
     }

@@ -205,8 +205,10 @@ int64_t rmhmc_launch_count(const rmhmc_handle* h);
  * 1 metric build (closing), 2 partials build (tensor mode), 3 per-chain turn (end of one leapfrog step +
  * start of the next; matrix-free: also the momentum iterates), 4 per-chain position solve / factorisation,
  * 5 quadratic-form pass, 6 leverage GEMM, 7 trace pass (matrix-free mode), 8 / 9 the two kernels of the INT8 metric
- * build (v digits, tcgen05 GEMM; their sum is also counted under 0 / 1), 10 the NCCL all-reduces of the row-sharded
- * mode.  Returns accumulated
+ * build of a position iterate (k_i8_vslice_mma: f = X theta and the digits of v; k_i8_gemm: tcgen05 digit GEMM, all its
+ * launches; the sum of a build's two kernels is also counted under 0 / 1), 10 the NCCL all-reduces of the row-sharded
+ * mode, 11 the digit kernel of the closing build (k_i8_vslice_mma_closing: also X^T (t - p), log-likelihood, c_n),
+ * 12 k_i8_qdigits (digits of the packed G^-1 for the leverage GEMM).  Returns accumulated
  * milliseconds and launch count since the last reset; synchronises. */
 int rmhmc_profile_enable(rmhmc_handle* h, int enable);
 int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches);

@@ -110,7 +110,7 @@ struct rmhmc_handle {
     double* t_tmp = nullptr;        // [C][P3p] contiguous partials of the last build (sharded mode)
     double* split_buf = nullptr;    // partial outputs of row-split metric builds / passes
     size_t split_cap = 0;
-    ProfSlot prof[11];
+    ProfSlot prof[13];
     ncclComm_t stats_comm = nullptr;   // chain-sharded runs: end-of-run statistics only (rmhmc_stats_comm_init)
     int stats_world = 1;
     // INT8-slice metric build on tcgen05 (i8_metric.cuh): digit planes of KR2(X)^T per data set, of V per chain set
@@ -532,7 +532,7 @@ template <int S>
 int i8_leverage_s(rmhmc_handle* h) {
     const int64_t C = h->n_chains;
     {
-        Bracket b(h, 8);
+        Bracket b(h, 12);
         k_i8_qdigits<S><<<blocks_for(C, 8), 256, 0, h->stream>>>(h->S.qpack, h->p2, h->p2k, h->aq8, (size_t)h->c_pad * h->i8_kpl,
                                                                   h->i8_kpl, h->qscale, (int)C);
     }
@@ -1113,7 +1113,7 @@ int i8_build_s(rmhmc_handle* h, int64_t C, const double* theta, signed char* a8,
     v.n_chains = (int)C; v.n_rows = (int)h->n_rows; v.n_rows_pad = h->n_rows_pad; v.dim = h->dim; v.xs = h->xs;
     cudaError_t e;
     {
-        Bracket bv(h, 8);
+        Bracket bv(h, cl ? 11 : 8);
         if (cl) {
             v.grad_out = cl->grad_out; v.loglik_out = cl->loglik_out; v.cbuf = cl->cbuf;
             v.cw_cur = cl->cw_cur; v.cw_flip = cl->cw_flip; v.cw_slot = cl->cw_slot;
@@ -2087,7 +2087,7 @@ int rmhmc_profile_enable(rmhmc_handle* h, int enable) {
     return RMHMC_OK;
 }
 int rmhmc_profile_read(rmhmc_handle* h, int kind, double* ms, int64_t* launches) {
-    if (!h || kind < 0 || kind > 10) return RMHMC_E_INVALID;
+    if (!h || kind < 0 || kind > 12) return RMHMC_E_INVALID;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     drain_profile(h);
     if (ms) *ms = h->prof[kind].ms;

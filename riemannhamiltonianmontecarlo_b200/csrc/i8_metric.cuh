@@ -864,7 +864,10 @@ inline cudaError_t i8_launch_vslice_mma_mt(const I8VsArgs& a, cudaStream_t strea
     const unsigned gx = (unsigned)((a.n_chains + MT * 8 - 1) / (MT * 8));
     unsigned gy = 1;
     const int units = a.n_rows_pad / 16;
-    while (gx * gy < 148 * 4 && (int)gy * 2 * kI8VmWarps <= units) gy *= 2;      // few chains: split the rows too
+    // few chains: split the rows too, until the grid is at least ~4 waves of the resident CTAs (8192 chains x 16 per CTA
+    // = 512 CTAs on 444 slots would be 1.15 waves)
+    const unsigned resident = 148u * (MT == 4 ? 2 : 3);
+    while (gx * gy < 4 * resident && (int)gy * 2 * kI8VmWarps <= units) gy *= 2;
     const dim3 grid(gx, gy);
     const size_t smem = i8_vslice_mma_smem(S, MT);
     const int ks = (a.dim + 3) / 4;

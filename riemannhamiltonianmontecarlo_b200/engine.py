@@ -54,7 +54,7 @@ def rhat_from_moments(moments, c_total: int, n_samples: int):
 
 
 PROFILE_KINDS = ["metric_fp", "metric_closing", "partials", "chain_turn", "chain_solve", "quad_pass", "leverage_gemm",
-                 "trace_pass", "i8_vslice", "i8_gemm", "allreduce"]
+                 "trace_pass", "i8_vslice", "i8_gemm", "allreduce", "i8_vslice_closing", "i8_qdigits"]
 
 
 def device_peaks(device=0):
