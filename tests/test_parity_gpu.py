@@ -971,3 +971,37 @@ def test_studentt_rmhmc_matches_oracle_port_under_a_tape(pkg, shape, metric):
             assert abs(tr["h_proposed"][ci, it] - rec[it]["h_proposed"]) < 1e-8 * abs(rec[it]["h_proposed"])
         assert rel_err(out[ci], refs[ci][0]) < 1e-8
     assert np.array_equal(state["renorm_momentum"], np.zeros(c)) and np.array_equal(state["renorm_position"], np.zeros(c))
+
+
+ENV_VARIANTS = {
+    # thread-per-chain Cholesky solve + factorisation (csrc/chain_tpc.cuh) instead of the warp-per-chain kernels
+    "chain_tpc": {"RMHMC_CHAIN_TPC": "1", "RMHMC_FACTOR_TPC": "1"},
+    # 32 chains per warp in the INT8 mode's digit kernel of the position iterates
+    "vslice_mt4": {"RMHMC_VSLICE_MT": "4"},
+    # implicit momentum half-step: k_mom_fp whatever the chain count / one launch pair per iterate
+    "momentum_k_mom_fp": {"RMHMC_FUSE_MOMENTUM": "2"},
+    "momentum_unfused": {"RMHMC_FUSE_MOMENTUM": "0"},
+    # FP64 leverage GEMM next to the INT8 metric build; six digits per operand
+    "fp64_leverage": {"RMHMC_I8_LEVERAGE": "0"},
+    "six_digits": {"RMHMC_I8_SLICES": "6"},
+}
+
+
+@pytest.mark.parametrize("variant", sorted(ENV_VARIANTS))
+def test_kernel_variants_behind_environment_switches(variant):
+    """Every kernel variant the library can be switched to (environment switches) replays the golden
+    tapes like the default ones: the trajectory tests of the Australian- and German-shaped fixtures and the mid-scale
+    replica test run in a fresh process with the switch set (the library reads the switches once per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, **ENV_VARIANTS[variant])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = ("(test_rmhmc_trajectories_match_reference and (australian_shaped or german_shaped)) "
+           "or test_mid_scale_batch_matches_reference")
+    if variant == "chain_tpc":
+        sel += " or test_mmala_matches_oracle_under_a_tape"      # the factorisation kernel is shared with the mMALA rounds
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_parity_gpu.py"), "-x", "-q",
+                          "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"], env=env, cwd=root, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-1500:]
