@@ -869,8 +869,12 @@ int launch_pass(rmhmc_handle* h) {
     // profiles/r02/regimes_small_large.txt)
     const bool small = few_chains(h, kPassSmallBelow);
     const int warps = small ? kPassWarpsSmall : kPassWarps;
-    const size_t smem = pass_smem_bytes(h->xs, warps);
-    void (*kern)(EngineParams, ChainArrays, const double*, int) = small ? k_pass<KIND, kPassWarpsSmall> : k_pass<KIND, kPassWarps>;
+    const size_t smem = pass_smem_bytes(h->xs, warps, KIND);
+    // D = 8 k + 1: the last parameter through FMAs instead of a DMMA k-step and d-tile of its own (pass_kernel.cuh)
+    const bool tail = (h->dim & 7) == 1 && h->dim > 8;
+    void (*kern)(EngineParams, ChainArrays, const double*, int) =
+        small ? (tail ? k_pass<KIND, kPassWarpsSmall, true> : k_pass<KIND, kPassWarpsSmall, false>)
+              : (tail ? k_pass<KIND, kPassWarps, true> : k_pass<KIND, kPassWarps, false>);
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         Bracket b(h, KIND == kPassTrace || KIND == kPassPair ? 7 : 5);
@@ -1275,7 +1279,10 @@ int hmc_rounds(rmhmc_handle* h, int64_t n_rounds) {
     const bool small = few_chains(h, kPassSmallBelow);
     const int warps = small ? kPassWarpsSmall : kHfWarps;
     const size_t smem = hmc_fused_smem_bytes(h->xs, warps);
-    void (*kern)(EngineParams, ChainArrays, const double*, int, int, int) = small ? k_hmc_rounds<kPassWarpsSmall> : k_hmc_rounds<kHfWarps>;
+    const bool tail = (h->dim & 7) == 1 && h->dim > 8;
+    void (*kern)(EngineParams, ChainArrays, const double*, int, int, int) =
+        small ? (tail ? k_hmc_rounds<kPassWarpsSmall, true> : k_hmc_rounds<kPassWarpsSmall, false>)
+              : (tail ? k_hmc_rounds<kHfWarps, true> : k_hmc_rounds<kHfWarps, false>);
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // bounded launches: a launch of 64 rounds is ~30 ms at 65 536 German-shaped chains
     for (int64_t done = 0; done < n_rounds;) {

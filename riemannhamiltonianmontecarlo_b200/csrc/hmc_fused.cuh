@@ -32,7 +32,7 @@ __device__ __forceinline__ double quad_sum(double v) {          // over the four
     return v;
 }
 
-template <int W>
+template <int W, bool TAIL>
 __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EngineParams P, ChainArrays S, const double* __restrict__ x,
                                                                         int xs, int n_rows, int n_rounds) {
     constexpr int NB = kPassRows, ST = kPassStages;
@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
                                                                  // feeds to the gradient contraction -- no C -> A shuffle
     double* wsm = scratch + (size_t)warp * 8 * 32;
     const double half_log = 0.5 * log(2.0 * 3.14159265358979323846 * alpha);
-    const int k_steps = (D + 3) / 4, d_tiles = (D + 7) / 8;
+    // D = 8 k + 1: the last parameter goes through plain FMAs instead of a k-step and a d-tile of its own (pass_kernel.cuh)
+    constexpr bool tail = TAIL;                          // the launcher passes (D & 7) == 1 && D > 8
+    const int k_steps = tail ? D / 4 : (D + 3) / 4, d_tiles = tail ? D / 8 : (D + 7) / 8;
 
     int gb = 0;
     for (int r = 0; r < n_rounds; ++r) {
@@ -156,10 +158,11 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
         double ua[8];
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) ua[ks] = wsm[g * 32 + ks * 4 + q];
+        const double u_tail = tail ? wsm[g * 32 + D - 1] : 0.0;
         const bool ends_after = moving && !broken && step + 1 >= nsteps;      // needs the log-likelihood at w'
 
         // ---- one pass over the data: grad = X^T (t - sigma(X w')), log-likelihood
-        double acc[4][2], ll = 0.0;
+        double acc[4][2], ll = 0.0, acc_t = 0.0;
 #pragma unroll
         for (int dt = 0; dt < 4; ++dt) acc[dt][0] = acc[dt][1] = 0.0;
         for (int rb = 0; rb < n_blocks; ++rb, ++gb) {
@@ -200,6 +203,14 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
                     default: s_stage(std::integral_constant<int, 8>{}); break;
                 }
             }
+            const double* xtq = xb + (D - 1);
+            if (tail) {
+#pragma unroll
+                for (int r8 = 0; r8 < 4; ++r8) {
+                    sv[r8][0] = fma(u_tail, xtq[(size_t)(r8 * 8 + q) * xs], sv[r8][0]);
+                    sv[r8][1] = fma(u_tail, xtq[(size_t)(r8 * 8 + q_hi) * xs], sv[r8][1]);
+                }
+            }
             double aq[4][2];
 #pragma unroll
             for (int r8 = 0; r8 < 4; ++r8) {
@@ -221,6 +232,13 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
                 }
                 aq[r8][0] = rr[0];
                 aq[r8][1] = rr[1];
+            }
+            if (tail) {                                      // column D - 1 of X^T (t - p)
+#pragma unroll
+                for (int r8 = 0; r8 < 4; ++r8) {
+                    acc_t = fma(aq[r8][0], xtq[(size_t)(r8 * 8 + q) * xs], acc_t);
+                    acc_t = fma(aq[r8][1], xtq[(size_t)(r8 * 8 + q_hi) * xs], acc_t);
+                }
             }
             // d-tile count as a compile-time constant; columns >= D of the last tile read what follows the row's D
             // entries (inside shared memory: the ring is followed by the per-warp scratch) and only reach accumulator
@@ -251,6 +269,13 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_hmc_rounds(EnginePar
             if (lane == 0) mbar_arrive(&x_empty[stage]);
         }
 
+        if (tail) {
+            acc_t += __shfl_xor_sync(kFullMask, acc_t, 1);
+            acc_t += __shfl_xor_sync(kFullMask, acc_t, 2);
+#pragma unroll
+            for (int dt = 1; dt < 4; ++dt)
+                if (dt == d_tiles && q == 0) acc[dt][0] = acc_t;
+        }
         // ---- gradient of the log joint, log joint at w'                                              hmc.py:60-67
         double lp = 0.0;
 #pragma unroll

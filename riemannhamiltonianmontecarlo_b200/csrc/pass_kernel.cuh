@@ -28,19 +28,24 @@ constexpr int kPassRows = 32;          // rows per staged X block
 constexpr int kPassStages = 4;
 enum { kPassQuad = 0, kPassTrace = 1, kPassPair = 2, kPassMomFp = 3 };
 
-__host__ inline size_t pass_smem_bytes(int xs, int warps) {
-    return (size_t)kPassStages * kPassRows * xs * 8 + (size_t)warps * 2 * 8 * 32 * 8 + 2 * kPassStages * 8;
+// per-warp scratch tiles of [8 chains][32]: PM and u; the 8-warp momentum fixed point also parks p and grad - tr/2 there
+__host__ __device__ constexpr int pass_scratch_tiles(int kind, int warps) { return (kind == kPassMomFp && warps >= 4) ? 4 : 2; }
+__host__ inline size_t pass_smem_bytes(int xs, int warps, int kind) {
+    return (size_t)kPassStages * kPassRows * xs * 8 + (size_t)warps * pass_scratch_tiles(kind, warps) * 8 * 32 * 8 + 2 * kPassStages * 8;
 }
 
 #ifdef __CUDACC__
-template <int KIND, int W>
+template <int KIND, int W, bool TAIL>
 __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P, ChainArrays S, const double* __restrict__ x, int xs) {
     constexpr int NB = kPassRows, ST = kPassStages;
     constexpr bool WITH_U = KIND != kPassTrace, WITH_H = KIND == kPassTrace || KIND == kPassPair;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* xs_ring = reinterpret_cast<double*>(smem_raw);                    // [ST][NB][xs]
-    double* scratch = xs_ring + (size_t)ST * NB * xs;                         // [W][2][8][32]  PM and u of the warp's chains
-    uint64_t* x_full = reinterpret_cast<uint64_t*>(scratch + (size_t)W * 2 * 8 * 32);
+    constexpr int SCR = pass_scratch_tiles(KIND, W);
+    constexpr bool PARK = SCR == 4;           // p and grad - tr/2 in shared memory (the 2-warp CTAs keep them in registers:
+                                              // their residency, 6 CTAs per SM, leaves no shared memory for it)
+    double* scratch = xs_ring + (size_t)ST * NB * xs;                         // [W][SCR][8][32]  PM, u (, p, grad - tr/2) of the warp's chains
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(scratch + (size_t)W * SCR * 8 * 32);
     uint64_t* x_empty = x_full + ST;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
@@ -97,7 +102,12 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
         const int d = ks * 4 + q;
         ua[ks] = (WITH_U && active && d < D) ? S.uvec[(size_t)c * D + d] : 0.0;
     }
-    // momentum fixed point: p and grad - tr/2 of this lane's (chain, parameter) pairs, in accumulator layout
+    // momentum fixed point: p and grad - tr/2 of this lane's (chain, parameter) pairs, in accumulator layout; parked in
+    // shared memory (read once per iterate) -- the row-block loop needs the registers
+    double* pm_s = scratch + (size_t)warp * SCR * 8 * 32;    // [8][32]
+    double* u_s = pm_s + 8 * 32;                             // [8][32]
+    double* pl_s = u_s + 8 * 32;                             // [8][32] (PARK)
+    double* bl_s = pl_s + 8 * 32;                            // [8][32] (PARK)
     double pl[4][2], bl[4][2];
     if (KIND == kPassMomFp) {
 #pragma unroll
@@ -105,25 +115,35 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int d = dt * 8 + 2 * q + j;
-                pl[dt][j] = bl[dt][j] = 0.0;
+                double pv = 0.0, bv = 0.0;
                 if (active && d < D) {
                     const size_t so = slot * P.slot_theta + (size_t)c * D + d;
-                    pl[dt][j] = S.mom[(size_t)c * D + d];
-                    bl[dt][j] = S.grad[so] - 0.5 * S.trace[so];
+                    pv = S.mom[(size_t)c * D + d];
+                    bv = S.grad[so] - 0.5 * S.trace[so];
                 }
+                if (PARK) { pl_s[g * 32 + d] = pv; bl_s[g * 32 + d] = bv; }
+                else { pl[dt][j] = pv; bl[dt][j] = bv; }
             }
+        __syncwarp();
     }
-    const int k_steps = (D + 3) / 4;
-    const int d_tiles = (D + 7) / 8;
+    // D = 8 k + 1 (German credit: 25): the last parameter would cost a whole k-step of the S stage and a whole d-tile of
+    // the Q stage (12 of 60 DMMAs per row block for one column of 25).  It is carried by plain FMAs instead: S gets
+    // u_{D-1} x_{n,D-1} added per row, and column D-1 of Q is a per-lane dot product over the lane's own rows, reduced
+    // over the four lanes of a chain at the end of the pass.
+    // (TAIL is a template parameter: the launcher passes (D & 7) == 1 && D > 8, and the other instantiation is exactly
+    // the kernel without this path)
+    constexpr bool tail = TAIL;
+    const int k_steps = tail ? D / 4 : (D + 3) / 4;
+    const int d_tiles = tail ? D / 8 : (D + 7) / 8;
+    double u_tail = (tail && WITH_U && active) ? S.uvec[(size_t)c * D + D - 1] : 0.0;
     const int s_row = (g & 1) ? 4 + ((g >> 1) ^ 2) : (g >> 1);   // data row (within an 8-row group) behind S-stage column g
-    double* pm_s = scratch + (size_t)warp * 2 * 8 * 32;      // [8][32]
-    double* u_s = pm_s + 8 * 32;                             // [8][32]
 
     int gb = 0;
     for (int fi = 0; fi < n_iter; ++fi) {
         double acc[4][2], acc2[4][2];                        // acc: QUAD / TRACE; acc2: QUAD of PAIR
 #pragma unroll
         for (int dt = 0; dt < 4; ++dt) acc[dt][0] = acc[dt][1] = acc2[dt][0] = acc2[dt][1] = 0.0;
+        double acc_t = 0.0, acc2_t = 0.0;                    // column D - 1 of acc / acc2 when `tail`
         for (int rb = 0; rb < n_blocks; ++rb, ++gb) {
             const int stage = gb % ST;
             // c_n (and h_n) of the block's four row groups: issued before the barrier wait
@@ -184,7 +204,17 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
                     default: s_stage(std::integral_constant<int, 8>{}); break;
                 }
             }
-            // R = c .* S .* S (and / or c .* h): this lane's C-fragment values (chain g; rows q, q + 4) ARE its A
+            // x_{n,D-1} of this lane's rows (q, q_hi of every group) is read twice, here and for column D - 1 of Q below:
+            // keeping the eight values across the R computation costs the PAIR kind its last registers
+            const double* xtq = xb + (D - 1);
+            if (tail && WITH_U) {
+#pragma unroll
+                for (int r8 = 0; r8 < 4; ++r8) {
+                    sv[r8][0] = fma(u_tail, xtq[(size_t)(r8 * 8 + q) * xs], sv[r8][0]);
+                    sv[r8][1] = fma(u_tail, xtq[(size_t)(r8 * 8 + q_hi) * xs], sv[r8][1]);
+                }
+            }
+            // R = c .* S .* S (and / or c .* h): this lane's C-fragment values (chain g; rows q, q_hi) ARE its A
             // fragments (chain g; k = q) of the two 4-row k-steps of every group
             double aq[4][2], at[4][2];
 #pragma unroll
@@ -196,6 +226,17 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
                 if (WITH_H) {
                     at[r8][0] = cwv[r8].x * hv[r8].x;
                     at[r8][1] = cwv[r8].y * hv[r8].y;
+                }
+            }
+            if (tail) {                                      // column D - 1 of Q
+#pragma unroll
+                for (int r8 = 0; r8 < 4; ++r8) {
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const double xv = xtq[(size_t)(r8 * 8 + (kk ? q_hi : q)) * xs];
+                        acc_t = fma(KIND == kPassTrace ? at[r8][kk] : aq[r8][kk], xv, acc_t);
+                        if (KIND == kPassPair) acc2_t = fma(at[r8][kk], xv, acc2_t);
+                    }
                 }
             }
             // stage 2: Q += R . X over the block's eight 4-row k-steps; d-tiles are the independent chains.  The tile
@@ -233,6 +274,18 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_empty[stage]);
         }
+        if (tail) {
+            // the four lanes of a chain hold the partial sums of their rows; lane q = 0 owns column D - 1 = 8 d_tiles
+            acc_t += __shfl_xor_sync(kFull, acc_t, 1);
+            acc_t += __shfl_xor_sync(kFull, acc_t, 2);
+            if (KIND == kPassPair) {
+                acc2_t += __shfl_xor_sync(kFull, acc2_t, 1);
+                acc2_t += __shfl_xor_sync(kFull, acc2_t, 2);
+            }
+#pragma unroll
+            for (int dt = 1; dt < 4; ++dt)
+                if (dt == d_tiles && q == 0) { acc[dt][0] = acc_t; acc2[dt][0] = acc2_t; }
+        }
 
         if (KIND != kPassMomFp) {
             if (active) {
@@ -251,10 +304,12 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
         } else {
             // ---- PM = p + s eps/2 (grad - tr/2 + quad/2) for this lane's pairs                      rmhmc.py:108
 #pragma unroll
-            for (int dt = 0; dt < 4; ++dt)
+            for (int dt = 0; dt < 4; ++dt) {
+                const double2 pv = PARK ? *reinterpret_cast<const double2*>(pl_s + g * 32 + dt * 8 + 2 * q) : make_double2(pl[dt][0], pl[dt][1]);
+                const double2 bv = PARK ? *reinterpret_cast<const double2*>(bl_s + g * 32 + dt * 8 + 2 * q) : make_double2(bl[dt][0], bl[dt][1]);
                 *reinterpret_cast<double2*>(pm_s + g * 32 + dt * 8 + 2 * q) =
-                    make_double2(pl[dt][0] + hstep * (bl[dt][0] + 0.5 * acc[dt][0]),
-                                 pl[dt][1] + hstep * (bl[dt][1] + 0.5 * acc[dt][1]));
+                    make_double2(pv.x + hstep * (bv.x + 0.5 * acc[dt][0]), pv.y + hstep * (bv.y + 0.5 * acc[dt][1]));
+            }
             __syncwarp();
             // ---- u = G^-1 PM, one chain at a time: lane i owns u_i, G^-1 read by columns (coalesced)   rmhmc.py:103
             const bool last = fi + 1 == n_iter;
@@ -288,6 +343,7 @@ __global__ void __launch_bounds__(W * 32, 512 / (W * 32)) k_pass(EngineParams P,
             __syncwarp();
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) ua[ks] = active ? u_s[g * 32 + ks * 4 + q] : 0.0;
+            if (tail) u_tail = active ? u_s[g * 32 + D - 1] : 0.0;
             __syncwarp();
         }
     }
