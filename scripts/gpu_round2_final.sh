@@ -1,6 +1,7 @@
 #!/bin/bash
 # round 2 final record: GPU test suite, bench lines of every sampler / workload, ncu launch list of the default command
 mkdir -p gpurun_out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests_final.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/gpu_tests_final.log
 run() { name=$1; shift; timeout 900 python bench.py "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err; python - "$name" <<'PY'
 import json,sys
