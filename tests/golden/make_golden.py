@@ -184,11 +184,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--long", action="store_true")
     ap.add_argument("--only-iwls", action="store_true", help="regenerate only the IWLS fixtures")
+    ap.add_argument("--only-hmc-german", action="store_true", help="generate only the German-shaped HMC fixture")
     args = ap.parse_args()
     assert ref_live.available(), "needs /root/reference"
 
     xa, ta = datasets.shaped("australian")
     xg, tg = datasets.shaped("german")
+    if args.only_hmc_german:
+        hmc_fixture("hmc_german_shaped", xg, tg, seeds=[901, 902], n_iter=24, burn_in=4, n_leapfrog=100, step_size=0.05)
+        return
     if args.only_iwls:
         xp, tp = datasets.load_csv(os.path.join(ref_live.REFERENCE_CODE, "data", "pima.csv"))
         iwls_fixture("iwls_australian_shaped", xa, ta, seeds=[701, 702, 703], n_iter=30, burn_in=6)
@@ -208,6 +212,8 @@ def main():
                 n_leapfrog=100, step_size=0.1)
     hmc_fixture("hmc_pima_real", xp, tp, seeds=[601, 602], n_iter=40, burn_in=8,
                 n_leapfrog=100, step_size=0.1)
+    # D = 25 = 8 k + 1: the fused HMC kernel's FMA path for the last parameter (csrc/hmc_fused.cuh); BLR_hmc.m:72 step size
+    hmc_fixture("hmc_german_shaped", xg, tg, seeds=[901, 902], n_iter=24, burn_in=4, n_leapfrog=100, step_size=0.05)
     iwls_fixture("iwls_australian_shaped", xa, ta, seeds=[701, 702, 703], n_iter=30, burn_in=6)
     iwls_fixture("iwls_pima_real", xp, tp, seeds=[801, 802], n_iter=30, burn_in=6)
     tools_fixture()

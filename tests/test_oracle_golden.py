@@ -44,7 +44,7 @@ def test_uniform_is_consumed_only_when_ratio_not_positive(golden):
     assert fx["used_uniform"].any() and (~fx["used_uniform"]).any()
 
 
-@pytest.mark.parametrize("name", ["hmc_australian_shaped", "hmc_pima_real"])
+@pytest.mark.parametrize("name", ["hmc_australian_shaped", "hmc_pima_real", "hmc_german_shaped"])
 def test_hmc_oracle_reproduces_reference_fixture(golden, name):
     fx = golden(name)
     tapes = _tapes(fx, with_dir=False)
