@@ -551,6 +551,33 @@ def test_int8_build_splits_k_beyond_the_int32_range(pkg):
     assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
 
 
+@pytest.mark.parametrize("regime", ["small", "large"])
+@pytest.mark.parametrize("dim", [3, 9, 12, 17, 24, 26, 32])
+def test_dimension_sweep_matches_oracle(pkg, dim, regime):
+    """Every k-step / d-tile instantiation of the pass kernels (k_pass, k_hmc_rounds: 1..8 k-steps, 1..4 d-tiles) and the
+    FMA path for the last parameter when D = 8 k + 1 (9, 17; 25 is the German-shaped fixtures): RMHMC and HMC under a
+    fresh tape against the oracle, with the small-batch and the benchmark's kernel variants."""
+    xx, t = pkg.datasets.synthetic_logistic(300, dim, 4300 + dim)
+    n_iter, burn, c = 5, 1, 3
+    tapes = [bo.make_tape(n_iter, dim, 9300 + 10 * dim + i) for i in range(c)]
+    st = bo.stack_tapes(tapes)
+    ref, infos = bo.rmhmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=4, step_size=0.4, n_fixed=4)
+    out, _, info = pkg.rmhmc_batched(xx, t, c, n_iter, burn, 4, 0.4, 4, draws=st, regime=regime)
+    assert rel_err(out[:, 1:], ref[:, 1:]) < RTOL
+    assert np.array_equal(info["accepted"], [i["accepted"].sum() for i in infos])
+    ref_h, infos_h = bo.hmc_chains(xx, t, tapes, n_iter=n_iter, burn_in=burn, n_leapfrog=15, step_size=0.05)
+    data = pkg.LogisticData(xx, t, regime=regime)
+    s = pkg.HMCSampler(data, c, 15, 0.05)
+    s.set_tape(st["z"], st["u_step"], st["u_acc"])
+    s.set_samples(n_iter - burn, burn)
+    s.run(n_iter)
+    out_h = s.samples.cpu().numpy()
+    acc_h = s.state()["accepted"]
+    data.close()
+    assert rel_err(out_h[:, 1:], ref_h[:, 1:]) < RTOL
+    assert np.array_equal(acc_h, [i["accepted"].sum() for i in infos_h])
+
+
 def test_large_dim_hmc_matches_oracle(pkg):
     dim, n_rows = 48, 600
     xx, t = pkg.datasets.synthetic_logistic(n_rows, dim, 4248)
