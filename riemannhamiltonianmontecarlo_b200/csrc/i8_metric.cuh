@@ -743,6 +743,9 @@ __global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) 
             // column blocks, and the B digit tiles are adjacent in shared memory: one MMA of N = MB * NC columns covers
             // MB consecutive digits j (fewer, wider MMAs: the A tile is fetched 9 instead of 15 times per K step).
             constexpr int MB = 256 / NC;          // digit tiles per MMA (N <= 256)
+            // (Measured and rejected: issuing the mostly-padding last column chunk -- German-shaped: 325 = 3 x 96 + 37 -- as 15
+            // un-merged MMAs of N = 48 per K step instead of 9 of N = 96 / 192.  Half the tensor work, but 0.32 -> 0.35 ms
+            // per launch: narrow MMAs cost almost as much as wide ones.)
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % ST;
                 mbar_wait_or_trap(&full[st], (uint32_t)((kb / ST) & 1));
@@ -791,6 +794,7 @@ __global__ void __launch_bounds__(I8Shape<S>::THREADS, I8Shape<S>::CTAS_PER_SM) 
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
         for (int cg = cg_begin; cg < cg_end; ++cg) {
+            if (n0 + cg * 16 >= a.p2p) continue;             // padding beyond the stored columns of the last chunk
             uint32_t r[S][16];
 #pragma unroll
             for (int w = 0; w < S; ++w) tmem_ld16(lane_base + w * NC + cg * 16, r[w]);
