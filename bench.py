@@ -469,7 +469,7 @@ def gpu_main(args):
         ("german", 65536, "metric_fp"): (13.44e6 + 117.75e6, "profiles/r01/ncu_v3_metric_fp_raw.csv"),
         ("german", 65536, "partials"): (539.19e6 + 1487.65e6, "profiles/r01/ncu_v2_tbuild_raw.csv"),
         ("german", 65536, "i8_gemm"): (337.59e6 + 144.97e6, "profiles/r02/ncu_r02_i8_gemm_metric_raw.csv"),
-        ("german", 65536, "quad_pass"): (5603.04e6 + 54.84e6, "profiles/r02/ncu_r02_final_mom_fixed_point_raw.csv"),
+        ("german", 65536, "quad_pass"): (5578.80e6 + 38.33e6, "profiles/r02/ncu_r02_final2_mom_fixed_point_raw.csv"),
         ("german", 65536, "i8_vslice"): (25.08e6 + 286.99e6, "profiles/r02/ncu_r02_i8_vslice_iterate_raw.csv"),
         ("german", 65536, "chain_solve"): (212.91e6 + 11.90e6, "profiles/r02/ncu_r02_chain_solve_raw.csv"),
     }

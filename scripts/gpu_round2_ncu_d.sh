@@ -11,6 +11,6 @@ cap() {  # name regex skip
   ncu -i /tmp/prof_$name.ncu-rep --page details --csv > gpurun_out/ncu_r02_${name}_details.csv 2>/dev/null
   ncu -i /tmp/prof_$name.ncu-rep --page source --csv > gpurun_out/ncu_r02_${name}_source.csv 2>/dev/null
 }
-cap v8_mom_fixed_point '^k_pass$' 1
-cap v8_pair_pass '^k_pass$' 2
+cap final2_mom_fixed_point '^k_pass$' 1
+cap final2_pair_pass '^k_pass$' 2
 ls -la gpurun_out | tail -8
